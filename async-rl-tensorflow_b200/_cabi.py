@@ -1,0 +1,123 @@
+"""ctypes binding of libasyncrl_b200.so (include/asyncrl_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call
+fails, this module raises.  PyTorch is only the carrier of device memory and
+streams; every tensor is handed to the library as a raw device pointer.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libasyncrl_b200.so")
+
+c_int, c_i64, c_u64, c_f32, c_vp = (ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                     ctypes.c_float, ctypes.c_void_p)
+
+# name -> argtypes (all return int except where noted); mirrors include/asyncrl_b200.h
+SIGNATURES = {
+    "arl_init": [c_int],
+    "arl_param_layout": [c_int, ctypes.POINTER(c_i64)],
+    "arl_preprocess_push": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_history_get": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_history_reset": [c_vp, c_int, c_int, c_vp],
+    "arl_conv1_forward": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_conv2_forward": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_fc_forward": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_heads_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_forward": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                    c_vp, c_vp],
+    "arl_sample_actions": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_u64, c_vp],
+    "arl_greedy_actions": [c_vp, c_vp, c_int, c_int, c_vp],
+    "arl_returns_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,
+                             c_int, c_int, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp],
+    "arl_heads_backward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_fc_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_conv2_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_backward": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "arl_clip_rmsprop": [c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
+}
+OTHER = {
+    "arl_last_error": ([], ctypes.c_char_p),
+    "arl_version": ([], c_int),
+    "arl_backward_workspace_bytes": ([c_int], c_i64),
+}
+EXPORTS = tuple(SIGNATURES) + tuple(OTHER)
+
+
+class ArlError(RuntimeError):
+    pass
+
+
+_lib = None
+_inited = set()
+
+
+def load():
+    """dlopen the in-tree library (no GPU needed) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ArlError("%s is missing: build it with async-rl-tensorflow_b200/csrc/build.sh "
+                       "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, c_int
+    for name, (argtypes, restype) in OTHER.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, restype
+    _lib = lib
+    return lib
+
+
+def check(rc, name):
+    if rc != 0:
+        raise ArlError("%s failed (%d): %s" % (name, rc, load().arl_last_error().decode()))
+
+
+def init(device):
+    """arl_init once per device.  Raises if there is no CUDA device."""
+    if not torch.cuda.is_available():
+        raise ArlError("asyncrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _inited:
+        check(load().arl_init(idx), "arl_init")
+        _inited.add(idx)
+    return idx
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ArlError("expected a CUDA tensor, got device %s" % t.device)
+    if not t.is_contiguous():
+        raise ArlError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def param_layout(action_size):
+    """(names, offsets[11]) of the flat parameter buffer."""
+    off = (c_i64 * 11)()
+    check(load().arl_param_layout(int(action_size), off), "arl_param_layout")
+    return list(off)
+
+
+def workspace_bytes(action_size):
+    return int(load().arl_backward_workspace_bytes(int(action_size)))

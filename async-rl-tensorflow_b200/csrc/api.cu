@@ -1,0 +1,103 @@
+// C-ABI glue: error reporting, init, parameter layout and the composed forward/backward.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace arl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return ARL_ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+int preprocess_init(int device);
+int conv_init();
+int heads_init();
+
+}  // namespace arl
+
+using namespace arl;
+
+extern "C" const char* arl_last_error(void) { return g_err; }
+extern "C" int arl_version(void) { return 100; }
+
+extern "C" int arl_init(int device) {
+  int count = 0;
+  ARL_CUDA(cudaGetDeviceCount(&count));
+  ARL_REQUIRE(device >= 0 && device < count, "arl_init: device %d not in [0,%d)", device, count);
+  int prev = 0;
+  ARL_CUDA(cudaGetDevice(&prev));
+  ARL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ARL_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("arl_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+              device, prop.major, prop.minor);
+    cudaSetDevice(prev);
+    return ARL_ERR_UNSUPPORTED;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  int rc = preprocess_init(device);
+  if (rc == ARL_OK) rc = conv_init();
+  if (rc == ARL_OK) rc = heads_init();
+  cudaSetDevice(prev);
+  return rc;
+}
+
+extern "C" int arl_param_layout(int action_size, int64_t* offsets) {
+  ARL_REQUIRE(offsets, "arl_param_layout: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_param_layout: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  const ParamLayout L = param_layout(action_size);
+  memcpy(offsets, L.off, sizeof(L.off));
+  return ARL_OK;
+}
+
+extern "C" int64_t arl_backward_workspace_bytes(int action_size) {
+  // largest user: fc weight-gradient split-K partials (8 x 2592 x 256 floats)
+  (void)action_size;
+  return (int64_t)8 * ARL_A2_ELEMS * ARL_FC * sizeof(float) + (1 << 20);
+}
+
+extern "C" int arl_forward(const float* params, int action_size, const uint8_t* ring, int num_envs,
+                           int ring_slots, int first_slot, int steps, float* a1, float* a2, float* h,
+                           float* logits, float* probs, float* value, void* stream) {
+  const int64_t N = (int64_t)num_envs * steps;
+  int rc = arl_conv1_forward(params, ring, a1, num_envs, ring_slots, first_slot, steps, stream);
+  if (rc) return rc;
+  rc = arl_conv2_forward(params, a1, a2, N, stream);
+  if (rc) return rc;
+  rc = arl_fc_forward(params, a2, h, N, stream);
+  if (rc) return rc;
+  return arl_heads_forward(params, action_size, h, logits, probs, value, N, stream);
+}
+
+extern "C" int arl_backward(const float* params, int action_size, const uint8_t* ring, int num_envs,
+                            int ring_slots, int first_slot, int steps, const float* a1,
+                            const float* a2, const float* h, const float* dlogits,
+                            const float* dvalue, float* d_h, float* d_a2, float* d_a1, float* grads,
+                            void* workspace, void* stream) {
+  const int64_t N = (int64_t)num_envs * steps;
+  int rc = arl_heads_backward(params, action_size, h, dlogits, dvalue, d_h, grads, workspace, N,
+                              stream);
+  if (rc) return rc;
+  rc = arl_fc_backward(params, a2, d_h, d_a2, grads, workspace, N, stream);
+  if (rc) return rc;
+  rc = arl_conv2_backward(params, a1, d_a2, d_a1, grads, workspace, N, stream);
+  if (rc) return rc;
+  return arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps,
+                            stream);
+}

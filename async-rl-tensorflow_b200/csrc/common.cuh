@@ -1,0 +1,124 @@
+// Shared helpers for the asyncrl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/asyncrl_b200.h"
+
+namespace arl {
+
+// thread-local error text behind arl_last_error()
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int num_sms();
+
+#define ARL_REQUIRE(cond, ...)                       \
+  do {                                               \
+    if (!(cond)) {                                   \
+      arl::set_error(__VA_ARGS__);                   \
+      return ARL_ERR_INVALID;                        \
+    }                                                \
+  } while (0)
+
+#define ARL_CUDA(expr)                                             \
+  do {                                                             \
+    cudaError_t e__ = (expr);                                      \
+    if (e__ != cudaSuccess) return arl::cuda_fail(e__, #expr);     \
+  } while (0)
+
+#define ARL_LAUNCH_CHECK(name)                                     \
+  do {                                                             \
+    cudaError_t e__ = cudaGetLastError();                          \
+    if (e__ != cudaSuccess) return arl::cuda_fail(e__, name);      \
+  } while (0)
+
+// flat parameter layout (floats)
+struct ParamLayout {
+  int64_t off[ARL_NUM_TENSORS + 1];
+};
+enum { T_L1W = 0, T_L1B, T_L2W, T_L2B, T_L4W, T_L4B, T_PW, T_PB, T_QW, T_QB };
+
+inline ParamLayout param_layout(int A) {
+  ParamLayout L;
+  const int64_t sz[ARL_NUM_TENSORS] = {8 * 8 * 4 * 16, 16,  4 * 4 * 16 * 32, 32, 2592 * 256,
+                                       256,            256 * (int64_t)A, A,  256, 1};
+  L.off[0] = 0;
+  for (int i = 0; i < ARL_NUM_TENSORS; ++i) L.off[i + 1] = L.off[i] + sz[i];
+  return L;
+}
+
+constexpr int kPlane = ARL_SCREEN * ARL_SCREEN;  // 7056 bytes, 441 x 16 B
+
+// ---- small device helpers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D TMA bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace arl

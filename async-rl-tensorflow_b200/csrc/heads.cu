@@ -1,0 +1,353 @@
+// K3 (heads) + K4: policy/value heads, softmax, action sampling, n-step returns and the
+// loss gradients.
+//   heads fwd : logits = h.p_w + p_b (network.py:62), value = h.q_w + q_b (network.py:79),
+//               probs = softmax(logits) (network.py:65)
+//   sampling  : network.py:72 batch_sample -> Philox4x32-10 + inverse CDF (oracle/philox.py)
+//   returns   : Algorithm 3 + agent.py:154,188-190;  loss grads: network.py:81-94 (repaired)
+//   heads bwd : d_h, d p_w/p_b/q_w/q_b
+#include "common.cuh"
+
+namespace arl {
+
+int reduce_partials(const float* partials, float* out, int num_partials, int n,
+                    cudaStream_t stream);
+
+// ------------------------------- heads forward --------------------------------------------
+// CTA = 128 threads, 16 samples.  Wcat [A+1][257] in smem (policy columns then value).
+constexpr int kHfSamples = 16;
+constexpr int kHfThreads = 128;
+__global__ void __launch_bounds__(kHfThreads)
+heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
+                 const float* __restrict__ qw, const float* __restrict__ qb,
+                 const float* __restrict__ h, float* __restrict__ logits,
+                 float* __restrict__ probs, float* __restrict__ value, int64_t num_samples, int A) {
+  extern __shared__ __align__(16) float sm[];
+  const int J = A + 1;
+  float* wt = sm;                       // [J][257]
+  float* hs = wt + J * 257;             // [16][256]
+  float* zs = hs + kHfSamples * 256;    // [16][J]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256 * A; i += kHfThreads) {
+    const int k = i / A, j = i - k * A;
+    wt[j * 257 + k] = pw[i];
+  }
+  for (int k = tid; k < 256; k += kHfThreads) wt[A * 257 + k] = qw[k];
+
+  const int64_t num_tiles = (num_samples + kHfSamples - 1) / kHfSamples;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t n0 = tile * kHfSamples;
+    const int ns = (int)((num_samples - n0) < kHfSamples ? (num_samples - n0) : kHfSamples);
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(h + n0 * 256);
+    for (int i = tid; i < ns * 64; i += kHfThreads) reinterpret_cast<float4*>(hs)[i] = src[i];
+    __syncthreads();
+    for (int o = tid; o < ns * J; o += kHfThreads) {
+      const int s = o / J, j = o - s * J;
+      const float* hp = hs + s * 256;
+      const float* wp = wt + j * 257;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 256; k += 4) {
+        a0 = fmaf(hp[k], wp[k], a0);
+        a1 = fmaf(hp[k + 1], wp[k + 1], a1);
+        a2 = fmaf(hp[k + 2], wp[k + 2], a2);
+        a3 = fmaf(hp[k + 3], wp[k + 3], a3);
+      }
+      zs[s * J + j] = (a0 + a1) + (a2 + a3) + (j < A ? pb[j] : qb[0]);
+    }
+    __syncthreads();
+    if (tid < ns) {
+      const float* z = zs + tid * J;
+      const int64_t n = n0 + tid;
+      float mx = z[0];
+      for (int j = 1; j < A; ++j) mx = fmaxf(mx, z[j]);
+      float den = 0.f;
+      for (int j = 0; j < A; ++j) den += expf(z[j] - mx);
+      const float inv = 1.0f / den;
+      for (int j = 0; j < A; ++j) {
+        logits[n * A + j] = z[j];
+        probs[n * A + j] = expf(z[j] - mx) * inv;
+      }
+      value[n] = z[A];
+    }
+  }
+}
+
+// ------------------------------- action selection -----------------------------------------
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+__global__ void sample_actions_kernel(const float* __restrict__ probs, int32_t* __restrict__ actions,
+                                      int num_envs, int A, uint64_t env_id_base, uint64_t step,
+                                      uint64_t seed) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= num_envs) return;
+  const uint32_t env = (uint32_t)(env_id_base + (uint64_t)b);
+  const uint32_t x = philox_first(env, (uint32_t)step, (uint32_t)(step >> 32), 0u, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  const float u = (float)(x >> 8) * 5.9604644775390625e-08f;       // 2^-24
+  const float* p = probs + (size_t)b * A;
+  float c = 0.f;
+  int a = A - 1;
+  for (int j = 0; j < A; ++j) {
+    c = __fadd_rn(c, p[j]);
+    if (u < c) { a = j; break; }
+  }
+  actions[b] = a;
+}
+
+__global__ void greedy_actions_kernel(const float* __restrict__ scores, int32_t* __restrict__ actions,
+                                      int num_envs, int A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= num_envs) return;
+  const float* p = scores + (size_t)b * A;
+  int a = 0;
+  float best = p[0];
+  for (int j = 1; j < A; ++j)
+    if (p[j] > best) { best = p[j]; a = j; }        // ties -> lowest index (tf.argmax)
+  actions[b] = a;
+}
+
+// ------------------------------- returns + loss gradients ---------------------------------
+// One thread per env walks t = T-1 .. 0.
+__global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
+                                        const uint8_t* __restrict__ terminals,
+                                        const int32_t* __restrict__ actions,
+                                        const float* __restrict__ logits,
+                                        const float* __restrict__ value,
+                                        const float* __restrict__ v_boot, float* __restrict__ returns,
+                                        float* __restrict__ dlogits, float* __restrict__ dvalue,
+                                        float* __restrict__ loss_sums, int T, int B, int A,
+                                        float gamma, float beta, float rmin, float rmax,
+                                        float grad_scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;
+  if (b < B) {
+    float R = v_boot[b];
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t n = (size_t)t * B + b;
+      const float r = fminf(fmaxf(rewards[n], rmin), rmax);               // agent.py:154
+      R = fmaf(gamma * (1.0f - (terminals[n] ? 1.0f : 0.0f)), R, r);      // agent.py:190
+      returns[n] = R;
+      const float* z = logits + n * A;
+      float zz[ARL_MAX_ACTIONS];
+      float mx = z[0];
+#pragma unroll 1
+      for (int j = 0; j < A; ++j) { zz[j] = z[j]; mx = fmaxf(mx, zz[j]); }
+      float den = 0.f;
+      for (int j = 0; j < A; ++j) den += expf(zz[j] - mx);
+      const float lse = mx + logf(den);
+      float ent = 0.f;
+      for (int j = 0; j < A; ++j) {
+        const float lp = zz[j] - lse;
+        ent -= expf(lp) * lp;                                             // network.py:69
+      }
+      const float v = value[n];
+      const float adv = R - v;
+      const int a = actions[n];
+      float* dz = dlogits + n * A;
+      for (int j = 0; j < A; ++j) {
+        const float lp = zz[j] - lse, p = expf(lp);
+        const float g = -adv * ((j == a ? 1.0f : 0.0f) - p) + beta * p * (lp + ent);
+        dz[j] = g * grad_scale;
+      }
+      dvalue[n] = -adv * grad_scale;                                      // d/dV (R-V)^2/2
+      s_pol += -(zz[a] - lse) * adv - beta * ent;                         // network.py:87-88
+      s_val += 0.5f * adv * adv;                                          // network.py:91
+      s_ent += ent;
+    }
+  }
+  if (loss_sums) {
+    s_pol = warp_sum(s_pol); s_val = warp_sum(s_val); s_ent = warp_sum(s_ent);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(loss_sums + 0, s_pol);
+      atomicAdd(loss_sums + 1, s_val);
+      atomicAdd(loss_sums + 2, s_ent);
+    }
+  }
+}
+
+// ------------------------------- heads backward -------------------------------------------
+// CTA = 256 threads (thread k owns hidden unit k).  Per sample: d_h[n][k] = (h>0) * sum_j
+// dz[n][j]*Wcat[k][j];  dWcat[k][j] += h[n][k]*dz[n][j];  dbcat[j] += dz[n][j].
+// Partials per CTA -> workspace [grid][256*J + J], reduced deterministically afterwards.
+constexpr int kHbChunk = 64;
+template <int JMAX>
+__global__ void __launch_bounds__(256)
+heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
+                 const float* __restrict__ h, const float* __restrict__ dlogits,
+                 const float* __restrict__ dvalue, float* __restrict__ d_h,
+                 float* __restrict__ partials, int64_t num_samples, int A) {
+  __shared__ float dzs[kHbChunk][JMAX];
+  const int J = A + 1;
+  const int k = threadIdx.x;
+  float w[JMAX], acc[JMAX];
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j) {
+    w[j] = j < A ? pw[k * A + j] : (j == A ? qw[k] : 0.f);
+    acc[j] = 0.f;
+  }
+  float bacc = 0.f;                                   // thread j < J: sum of dz[:, j]
+  const int64_t per = (num_samples + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = per * blockIdx.x;
+  const int64_t end = beg + per < num_samples ? beg + per : num_samples;
+  for (int64_t c0 = beg; c0 < end; c0 += kHbChunk) {
+    const int nc = (int)(end - c0 < kHbChunk ? end - c0 : kHbChunk);
+    __syncthreads();
+    for (int i = k; i < nc * J; i += 256) {
+      const int s = i / J, j = i - s * J;
+      dzs[s][j] = j < A ? dlogits[(c0 + s) * A + j] : dvalue[c0 + s];
+    }
+    __syncthreads();
+    for (int s = 0; s < nc; ++s) {
+      const float hv = h[(c0 + s) * 256 + k];
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < JMAX; ++j) {
+        if (j < J) {
+          const float g = dzs[s][j];
+          d = fmaf(g, w[j], d);
+          acc[j] = fmaf(hv, g, acc[j]);
+        }
+      }
+      d_h[(c0 + s) * 256 + k] = hv > 0.f ? d : 0.f;
+    }
+    if (k < J)
+      for (int s = 0; s < nc; ++s) bacc += dzs[s][k];
+  }
+  float* out = partials + (size_t)blockIdx.x * (256 * J + J);
+  // layout of a partial: p_w [256][A] | p_b [A] | q_w [256] | q_b [1]  (flat-buffer order)
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j) {
+    if (j < A) out[k * A + j] = acc[j];
+    else if (j == A) out[256 * A + A + k] = acc[j];
+  }
+  if (k < A) out[256 * A + k] = bacc;
+  else if (k == A) out[256 * A + A + 256] = bacc;
+}
+
+int heads_init() {
+  const int J = ARL_MAX_ACTIONS + 1;
+  ARL_CUDA(cudaFuncSetAttribute(
+      heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      (int)((J * 257 + kHfSamples * 256 + kHfSamples * J) * sizeof(float))));
+  return ARL_OK;
+}
+
+}  // namespace arl
+
+using namespace arl;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int arl_heads_forward(const float* params, int action_size, const float* h,
+                                 float* logits, float* probs, float* value, int64_t num_samples,
+                                 void* stream) {
+  ARL_REQUIRE(params && h && logits && probs && value, "arl_heads_forward: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_heads_forward: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(num_samples >= 0, "arl_heads_forward: negative size");
+  ARL_REQUIRE(aligned16(h), "arl_heads_forward: h must be 16-byte aligned");
+  if (num_samples == 0) return ARL_OK;
+  const ParamLayout L = param_layout(action_size);
+  const int J = action_size + 1;
+  const size_t smem = (size_t)(J * 257 + kHfSamples * 256 + kHfSamples * J) * sizeof(float);
+  const int64_t tiles = (num_samples + kHfSamples - 1) / kHfSamples;
+  const int grid = (int)(tiles < 4LL * num_sms() ? tiles : 4LL * num_sms());
+  heads_fwd_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(
+      params + L.off[T_PW], params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h,
+      logits, probs, value, num_samples, action_size);
+  ARL_LAUNCH_CHECK("heads_fwd_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_sample_actions(const float* probs, int32_t* actions, int num_envs,
+                                  int action_size, int64_t env_id_base, int64_t step, uint64_t seed,
+                                  void* stream) {
+  ARL_REQUIRE(probs && actions, "arl_sample_actions: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_sample_actions: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(num_envs >= 0 && env_id_base >= 0 && step >= 0, "arl_sample_actions: negative argument");
+  if (num_envs == 0) return ARL_OK;
+  sample_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      probs, actions, num_envs, action_size, (uint64_t)env_id_base, (uint64_t)step, seed);
+  ARL_LAUNCH_CHECK("sample_actions_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_greedy_actions(const float* scores, int32_t* actions, int num_envs,
+                                  int action_size, void* stream) {
+  ARL_REQUIRE(scores && actions, "arl_greedy_actions: null pointer");
+  ARL_REQUIRE(action_size >= 1 && num_envs >= 0, "arl_greedy_actions: bad size");
+  if (num_envs == 0) return ARL_OK;
+  greedy_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      scores, actions, num_envs, action_size);
+  ARL_LAUNCH_CHECK("greedy_actions_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
+                                    const int32_t* actions, const float* logits, const float* value,
+                                    const float* v_boot, float* returns, float* dlogits,
+                                    float* dvalue, float* loss_sums, int t_max, int num_envs,
+                                    int action_size, float gamma, float beta, float reward_min,
+                                    float reward_max, float grad_scale, void* stream) {
+  ARL_REQUIRE(rewards && terminals && actions && logits && value && v_boot && returns && dlogits &&
+                  dvalue,
+              "arl_returns_lossgrad: null pointer");
+  ARL_REQUIRE(t_max >= 0 && num_envs >= 0, "arl_returns_lossgrad: negative size");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_returns_lossgrad: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  if (t_max == 0 || num_envs == 0) return ARL_OK;
+  returns_lossgrad_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      rewards, terminals, actions, logits, value, v_boot, returns, dlogits, dvalue, loss_sums,
+      t_max, num_envs, action_size, gamma, beta, reward_min, reward_max, grad_scale);
+  ARL_LAUNCH_CHECK("returns_lossgrad_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_heads_backward(const float* params, int action_size, const float* h,
+                                  const float* dlogits, const float* dvalue, float* d_h,
+                                  float* grads, void* workspace, int64_t num_samples, void* stream) {
+  ARL_REQUIRE(params && h && dlogits && dvalue && d_h && grads && workspace,
+              "arl_heads_backward: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_heads_backward: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(num_samples >= 0, "arl_heads_backward: negative size");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(action_size);
+  const int A = action_size, J = A + 1;
+  float* g = grads + L.off[T_PW];
+  if (num_samples == 0) {
+    ARL_CUDA(cudaMemsetAsync(g, 0, (size_t)(256 * J + J) * sizeof(float), st));
+    return ARL_OK;
+  }
+  int grid = 2 * num_sms();
+  if ((int64_t)grid > (num_samples + kHbChunk - 1) / kHbChunk)
+    grid = (int)((num_samples + kHbChunk - 1) / kHbChunk);
+  // empty trailing CTAs would write zero partials, which is fine; keep every CTA non-empty anyway
+  const int64_t per = (num_samples + grid - 1) / grid;
+  grid = (int)((num_samples + per - 1) / per);
+  float* part = (float*)workspace;
+  if (J <= 8)
+    heads_bwd_kernel<8><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
+                                             dvalue, d_h, part, num_samples, A);
+  else if (J <= 20)
+    heads_bwd_kernel<20><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h,
+                                              dlogits, dvalue, d_h, part, num_samples, A);
+  else
+    heads_bwd_kernel<ARL_MAX_ACTIONS + 1><<<grid, 256, 0, st>>>(
+        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, d_h, part, num_samples, A);
+  ARL_LAUNCH_CHECK("heads_bwd_kernel");
+  return reduce_partials(part, g, grid, 256 * J + J, st);
+}

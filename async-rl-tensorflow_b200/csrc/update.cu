@@ -1,0 +1,106 @@
+// K5: per-tensor clip_by_norm (agent.py:316-319) fused with the shared RMSProp apply
+// (agent.py:321; optimizer built at main.py:63-65: decay .99, momentum 0, epsilon .1; slot
+// `rms` starts at 1.0 in TF).  Two launches over the flat buffers:
+//   1. sumsq_kernel   : one CTA per (tensor, 4096-element chunk) -> partial sum of squares
+//   2. rmsprop_kernel : same grid; each CTA first adds up its tensor's partials in a fixed
+//                       order (deterministic), derives scale = clip / max(norm, clip), then
+//                       ms += (g^2 - ms)(1 - decay);  w -= lr * g / sqrt(ms + eps)
+// 20 B per parameter per update (read g, ms, w; write ms, w) + 4 B for the norm pass.
+#include "common.cuh"
+
+namespace arl {
+
+constexpr int kChunk = 4096;
+constexpr int kUpThreads = 256;
+
+struct UpdatePlan {
+  int64_t off[ARL_NUM_TENSORS + 1];
+  int chunk_begin[ARL_NUM_TENSORS + 1];   // first chunk index of each tensor
+};
+
+__device__ __forceinline__ int find_tensor(const UpdatePlan& p, int chunk) {
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < ARL_NUM_TENSORS; ++i) t += (chunk >= p.chunk_begin[i]) ? 1 : 0;
+  return t;
+}
+
+__global__ void __launch_bounds__(kUpThreads)
+sumsq_kernel(const float* __restrict__ grads, float* __restrict__ partial, UpdatePlan plan) {
+  __shared__ float red[kUpThreads / 32];
+  const int t = find_tensor(plan, blockIdx.x);
+  const int64_t beg = plan.off[t] + (int64_t)(blockIdx.x - plan.chunk_begin[t]) * kChunk;
+  const int64_t end = beg + kChunk < plan.off[t + 1] ? beg + kChunk : plan.off[t + 1];
+  float s = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += kUpThreads) {
+    const float g = grads[i];
+    s = fmaf(g, g, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < kUpThreads / 32; ++i) v += red[i];
+    partial[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kUpThreads)
+rmsprop_kernel(float* __restrict__ params, float* __restrict__ rms, const float* __restrict__ grads,
+               const float* __restrict__ partial, float* __restrict__ norms_out, UpdatePlan plan,
+               float lr, float decay, float eps, float clip) {
+  __shared__ float s_scale;
+  const int t = find_tensor(plan, blockIdx.x);
+  if (threadIdx.x == 0) {
+    float ss = 0.f;
+    for (int c = plan.chunk_begin[t]; c < plan.chunk_begin[t + 1]; ++c) ss += partial[c];
+    const float norm = sqrtf(ss);
+    s_scale = clip / fmaxf(norm, clip);                      // tf.clip_by_norm
+    if (norms_out && blockIdx.x == plan.chunk_begin[t]) norms_out[t] = norm;
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const float omd = 1.0f - decay;
+  const int64_t beg = plan.off[t] + (int64_t)(blockIdx.x - plan.chunk_begin[t]) * kChunk;
+  const int64_t end = beg + kChunk < plan.off[t + 1] ? beg + kChunk : plan.off[t + 1];
+  for (int64_t i = beg + threadIdx.x; i < end; i += kUpThreads) {
+    const float g = grads[i] * scale;
+    float ms = rms[i];
+    ms = fmaf(fmaf(g, g, -ms), omd, ms);                     // ms += (g*g - ms) * (1 - decay)
+    rms[i] = ms;
+    params[i] -= lr * g / sqrtf(ms + eps);                   // epsilon inside the sqrt (TF)
+  }
+}
+
+}  // namespace arl
+
+using namespace arl;
+
+extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size,
+                                float lr, float decay, float eps, float clip_norm, float* norms_out,
+                                void* workspace, void* stream) {
+  ARL_REQUIRE(params && rms && grads && workspace, "arl_clip_rmsprop: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_clip_rmsprop: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(clip_norm > 0.f && eps >= 0.f, "arl_clip_rmsprop: clip_norm must be > 0, eps >= 0");
+  const ParamLayout L = param_layout(action_size);
+  UpdatePlan plan;
+  int chunks = 0;
+  for (int t = 0; t < ARL_NUM_TENSORS; ++t) {
+    plan.off[t] = L.off[t];
+    plan.chunk_begin[t] = chunks;
+    chunks += (int)((L.off[t + 1] - L.off[t] + kChunk - 1) / kChunk);
+  }
+  plan.off[ARL_NUM_TENSORS] = L.off[ARL_NUM_TENSORS];
+  plan.chunk_begin[ARL_NUM_TENSORS] = chunks;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)workspace;
+  sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
+  ARL_LAUNCH_CHECK("sumsq_kernel");
+  rmsprop_kernel<<<chunks, kUpThreads, 0, st>>>(params, rms, grads, partial, norms_out, plan, lr,
+                                               decay, eps, clip_norm);
+  ARL_LAUNCH_CHECK("rmsprop_kernel");
+  return ARL_OK;
+}

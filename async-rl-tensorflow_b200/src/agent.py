@@ -1,0 +1,121 @@
+"""Agent: the A3C worker loop (reference src/agent.py:14-396: before_train / train / predict /
+observe / batch_update / lr), batched over ``num_envs`` environments per GPU.
+
+What maps to what (DESIGN.md has the full table):
+  predict      agent.py:141-151   forward of the current stack + action selection (sampled from
+                                  pi, network.py:72, instead of the epsilon-greedy of the async-Q code)
+  observe      agent.py:153-167   reward clip (in-kernel), history push (K1 fused), rollout append,
+                                  update every t_max steps (reference: every train_frequency)
+  batch_update agent.py:169-207   bootstrap, n-step returns, loss grads, backward, [allreduce],
+                                  clip + RMSProp  == Algorithm 3's accumulate-then-apply
+  lr           agent.py:393-395   linear anneal on the worker-local step
+
+Asynchronous hogwild updates through a parameter server (main.py:60-62, agent.py:321) become
+synchronous data parallelism: every rank holds a replica, gradients are summed with one NCCL
+all-reduce per t_max cycle, every rank applies the identical update.
+"""
+import torch
+import torch.distributed as dist
+
+from .. import _cabi
+from .base import BaseModel
+from .history import History
+from .network import Network
+
+
+class Agent(BaseModel):
+    def __init__(self, config, environment, optimizer=None, lr_op=None, device=None):
+        super(Agent, self).__init__(config)
+        self.weight_dir = 'weights'
+        self.env = environment
+        self.device = torch.device(device if device is not None else environment.device)
+        self.history = History(self.config, num_envs=self.num_envs, device=self.device)
+
+        self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.env_id_base = self.rank * self.num_envs           # global env ids: sharding-independent RNG
+        self.global_envs = self.world_size * self.num_envs
+
+        self.step_op = 0                                         # agent.py:25 global step (host int)
+        self.network = Network(
+            action_size=self.env.action_size, data_format=self.cnn_format,
+            history_length=self.history_length, screen_height=self.screen_height,
+            screen_width=self.screen_width, gamma=self.discount, beta=self.beta,
+            num_envs=self.num_envs, t_max=self.t_max, device=self.device, seed=self.seed,
+            decay=self.decay, epsilon=self.epsilon, clip_norm=self.clip_norm,
+            min_reward=self.min_reward, max_reward=self.max_reward)
+        self.w = self.network.w
+
+        T, B = self.t_max, self.num_envs
+        self.batch_reward = torch.zeros(T, B, device=self.device)
+        self.batch_terminal = torch.zeros(T, B, dtype=torch.uint8, device=self.device)
+        self.batch_action = self.network.sampled_action.view(T, B)
+        self.t = 0                                               # position inside the rollout
+        self.step = 0
+        self.T = 0
+        self.update_count = 0
+
+    # -- agent.py:33-50 ---------------------------------------------------------------------
+    def before_train(self, is_chief=True):
+        self.T = self.step = self.step_op
+        self.env.new_random_game()
+        # agent.py:37-38: the stack starts as 4 copies of the first screen (K1, replicate=4)
+        self.history.add(self.env.frames, replicate=self.history_length)
+        self.t = 0
+        return self.env.frames, 0, 0, self.env.terminal, range(self.step, self.max_step)
+
+    # -- agent.py:52-67 ---------------------------------------------------------------------
+    def train(self, sv=None, is_chief=True, num_steps=None):
+        screen, reward, action, terminal, iterator = self.before_train(is_chief)
+        end = self.max_step if num_steps is None else min(self.max_step, self.step + num_steps)
+        for self.step in range(self.step, end):
+            # 1. predict
+            action = self.predict()
+            # 2. act
+            screen, reward, terminal = self.env.act(action, is_training=True, fused=True)
+            # 3. observe
+            self.observe(screen, reward, action, terminal)
+            # agent.py:66-67: finished envs restart inside the (batched) backend; like the
+            # reference, the History is NOT reset on terminal.
+        self.step_op = self.step + 1
+        return self.step_op
+
+    # -- agent.py:141-151 -------------------------------------------------------------------
+    def predict(self, s_t=None, test_ep=None):
+        """Forward of the current stack (already in the ring; ``s_t`` is accepted for signature
+        compatibility and ignored) and one sampled action per env."""
+        self.network.forward(self.history, self.t)
+        return self.network.sample(self.t, self.step, self.seed, self.env_id_base)
+
+    # -- agent.py:153-167 -------------------------------------------------------------------
+    def observe(self, screen, reward, action, terminal, is_chief=False):
+        self.history.add(screen)                                 # agent.py:156 (K1 when raw frames)
+        self.batch_reward[self.t].copy_(reward)                  # clip happens in K4 (agent.py:154)
+        self.batch_terminal[self.t].copy_(terminal)
+        self.t += 1
+        if self.t == self.t_max:                                 # agent.py:162-163
+            self.batch_update(is_chief)
+        self.T += self.global_envs                               # agent.py:165 counts every worker
+
+    # -- agent.py:169-207 -------------------------------------------------------------------
+    def batch_update(self, is_chief=False):
+        net = self.network
+        v_boot = net.bootstrap_value(self.history)               # R = V(s_T), masked if terminal
+        scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
+        net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
+                              grad_scale=scale)
+        if self.world_size > 1:
+            dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)     # the one exchange per cycle
+        net.apply_gradients(self.lr)
+        self.update_count += 1
+        self.t = 0
+
+    def update_target_q_network(self):
+        """agent.py:342-344: no target network in the A3C path."""
+
+    @property
+    def lr(self):
+        """agent.py:393-395, with ``step`` = env steps taken per env at the START of the cycle
+        (SURVEY §8 step 9)."""
+        step = self.step - (self.t_max - 1)
+        return (self.max_step - step + 1.) / self.max_step * self.learning_rate

@@ -1,0 +1,211 @@
+"""Environment wrappers with the reference's frame API (src/environment.py:14-106), batched
+over ``num_envs`` environments per process.
+
+The emulator itself (gym/ALE) is outside the hot path; ``SyntheticAtari`` stands in for it
+with Atari-shaped u8 frames (BASELINE.json configs).  Any backend with the same batched
+gym-like surface can be passed as ``env=``:
+
+    reset(mask=None) -> frames u8 [B,210,160,3] (cuda)
+    step(actions i32[B]) -> (frames, rewards f32[B], terminals bool[B], info)
+    ale.lives() -> i32 [B];  action_space.n;  action_space.sample() -> i32 [B]
+"""
+import random
+
+import torch
+
+from .. import _cabi
+from .history import SCREEN, FRAME_SHAPE
+
+
+class _ALE(object):
+    def __init__(self, env):
+        self._env = env
+
+    def lives(self):
+        return self._env._lives
+
+
+class _ActionSpace(object):
+    def __init__(self, env, n):
+        self._env, self.n = env, n
+
+    def sample(self):
+        return torch.randint(0, self.n, (self._env.num_envs,), device=self._env.device,
+                             dtype=torch.int32, generator=self._env._gen)
+
+
+class SyntheticAtari(object):
+    """Deterministic stand-in for ``gym.make(name)`` x num_envs.
+
+    Frames come from a rotating pool of ``pool`` pre-generated steps so that a benchmark
+    reads HBM (pool * B * 100 800 B  >>  L2).  rewards in {-1,0,+1} w.p. {.05,.9,.05} times
+    ``reward_scale``; terminals ~ Bernoulli(p_terminal).  ``host=True`` keeps the pool in
+    pinned host memory and copies each step's frames host->device inside ``step`` (the
+    end-to-end path a real emulator would take).
+    """
+
+    def __init__(self, num_envs, action_size=6, seed=123, pool=8, device='cuda', host=False,
+                 p_terminal=0.01, reward_scale=1.0, structured=False, lives=3):
+        self.num_envs, self.device, self.host = int(num_envs), torch.device(device), bool(host)
+        self.pool = int(pool)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed))
+        B, P = self.num_envs, self.pool
+        shape = (P, B) + FRAME_SHAPE
+        if structured:   # few colours, large flat regions (Atari-like)
+            pal = torch.randint(0, 256, (16, 3), device=self.device, dtype=torch.uint8,
+                                generator=self._gen)
+            idx = torch.randint(0, 16, (P, B, 21, 16), device=self.device, generator=self._gen)
+            idx = idx.repeat_interleave(10, dim=2).repeat_interleave(10, dim=3)
+            frames = pal[idx]
+        else:
+            frames = torch.randint(0, 256, shape, device=self.device, dtype=torch.uint8,
+                                   generator=self._gen)
+        u = torch.rand(P, B, device=self.device, generator=self._gen)
+        self._rewards = (torch.where(u < 0.05, -1.0, torch.where(u > 0.95, 1.0, 0.0))
+                         * reward_scale).float()
+        self._terminals = torch.rand(P, B, device=self.device, generator=self._gen) < p_terminal
+        if self.host:
+            self._frames = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+            self._frames.copy_(frames)
+            self._stage = torch.empty((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device)
+            del frames
+        else:
+            self._frames = frames
+        self._lives = torch.full((B,), int(lives), dtype=torch.int32, device=self.device)
+        self._i = 0
+        self.ale = _ALE(self)
+        self.action_space = _ActionSpace(self, int(action_size))
+        self.h2d_bytes_per_step = B * FRAME_SHAPE[0] * FRAME_SHAPE[1] * FRAME_SHAPE[2] if host else 0
+
+    def _frame(self, i):
+        f = self._frames[i % self.pool]
+        if self.host:
+            self._stage.copy_(f, non_blocking=True)
+            return self._stage
+        return f
+
+    def reset(self, mask=None):
+        return self._frame(self._i)
+
+    def step(self, actions):
+        i = self._i
+        self._i += 1
+        k = i % self.pool
+        return self._frame(i), self._rewards[k], self._terminals[k], {}
+
+    def render(self):
+        pass
+
+
+class Environment(object):
+    def __init__(self, config, env=None, device=None):
+        self.device = torch.device(device if device is not None else 'cuda')
+        _cabi.init(self.device)
+        self.num_envs = int(getattr(config, 'num_envs', 1))
+        self.env = env if env is not None else SyntheticAtari(
+            self.num_envs, seed=getattr(config, 'seed', 123), device=self.device)
+        screen_width, screen_height, self.action_repeat, self.random_start = \
+            config.screen_width, config.screen_height, config.action_repeat, config.random_start
+        self.display = config.display
+        self.dims = (screen_width, screen_height)
+        if self.dims != (SCREEN, SCREEN):
+            raise ValueError("the preprocessing kernel produces 84x84 screens only")
+        self._screen = None                            # raw frames u8 [B,210,160,3]
+        self.reward = torch.zeros(self.num_envs, device=self.device)
+        self.terminal = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self._scratch = torch.empty(self.num_envs, 4, SCREEN, SCREEN, dtype=torch.uint8,
+                                    device=self.device)
+
+    def new_game(self, from_random_game=False):
+        """environment.py:28-33: reset the envs that are out of lives, then one no-op step."""
+        dead = self.lives == 0
+        if self._screen is None or bool(dead.any()):
+            self._screen = self.env.reset(dead)
+        self._step(self._noop())
+        self.render()
+        return self.screen, 0, 0, self.terminal
+
+    def new_random_game(self):
+        """environment.py:35-40 (one random_start draw shared by the batch)."""
+        self.new_game(True)
+        for _ in range(random.randint(0, self.random_start - 1)):
+            self._step(self._noop())
+        self.render()
+        return self.screen, 0, 0, self.terminal
+
+    def _noop(self):
+        return torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+
+    def _step(self, action):
+        self._screen, self.reward, self.terminal, _ = self.env.step(action)
+
+    def _random_step(self):
+        self._step(self.env.action_space.sample())
+
+    @property
+    def frames(self):
+        """Raw u8 [B,210,160,3] frames of the last step: feed to History.add for the fused path."""
+        return self._screen
+
+    @property
+    def screen(self):
+        """environment.py:49-53 on the device (K1, bit-exact): u8 [B,84,84]."""
+        _cabi.call("arl_preprocess_push", _cabi.ptr(self._screen), _cabi.ptr(self._scratch),
+                   self.num_envs, 4, 0, 1, _cabi.stream_ptr())
+        return self._scratch[:, 0]
+
+    @property
+    def action_size(self):
+        return self.env.action_space.n
+
+    @property
+    def lives(self):
+        return self.env.ale.lives()
+
+    @property
+    def state(self):
+        return self.screen, self.reward, self.terminal
+
+    def render(self):
+        if self.display:
+            self.env.render()
+
+    def after_act(self, action):
+        self.render()
+
+
+class GymEnvironment(Environment):
+    def act(self, action, is_training=True, fused=False):
+        """environment.py:78-96, per env.  ``fused=True`` returns the raw frames instead of the
+        84x84 screen so that History.add can run preprocess+push as one kernel."""
+        cumulated = torch.zeros(self.num_envs, device=self.device)
+        done = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        start_lives = self.lives.clone()
+        for k in range(self.action_repeat):
+            self._step(action)
+            live = ~done
+            cumulated = cumulated + torch.where(live, self.reward, torch.zeros_like(self.reward))
+            term = self.terminal
+            if is_training:
+                lost = (start_lives > self.lives) & live
+                cumulated = cumulated - lost.float()              # environment.py:86-88
+                term = term | lost
+            done = done | term
+            if self.action_repeat > 1 and bool(done.all()):
+                break
+        self.reward, self.terminal = cumulated, done
+        self.after_act(action)
+        if fused:
+            return self.frames, self.reward, self.terminal
+        return self.state
+
+
+class SimpleGymEnvironment(Environment):
+    def act(self, action, is_training=True, fused=False):
+        """environment.py:102-106."""
+        self._step(action)
+        self.after_act(action)
+        if fused:
+            return self.frames, self.reward, self.terminal
+        return self.state

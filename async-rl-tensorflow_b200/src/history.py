@@ -1,0 +1,76 @@
+"""History: the 4-frame stack (reference src/history.py:3-27), batched over envs and kept
+on the device as a ring of u8 planes so the T+1 overlapping stacks of a rollout are windows
+into one buffer instead of T+1 float32 copies (reference agent.py:157 copies 113 KB/step).
+
+    ring u8 [num_envs, ring_slots, 84, 84];  ``head`` = slot of the newest frame.
+    stack at offset t (t = 0 newest state) = slots head-3-t .. head-t, oldest first --
+    the channel order of History.get() (history.py:20-24).
+"""
+import torch
+
+from .. import _cabi
+
+SCREEN = 84
+FRAME_SHAPE = (210, 160, 3)
+
+
+class History(object):
+    def __init__(self, config, num_envs=None, ring_slots=None, device=None):
+        self.cnn_format = getattr(config, 'cnn_format', 'NHWC')
+        self.history_length = config.history_length
+        assert self.history_length == 4, "the kernels are built for history_length 4"
+        assert (config.screen_height, config.screen_width) == (SCREEN, SCREEN)
+        self.num_envs = int(num_envs if num_envs is not None else getattr(config, 'num_envs', 1))
+        t_max = int(getattr(config, 't_max', 5))
+        self.ring_slots = int(ring_slots if ring_slots is not None else t_max + 4)
+        if self.ring_slots < 4:
+            raise ValueError("ring_slots must be >= 4")
+        self.device = torch.device(device if device is not None else 'cuda')
+        _cabi.init(self.device)
+        self.ring = torch.zeros(self.num_envs, self.ring_slots, SCREEN, SCREEN,
+                                dtype=torch.uint8, device=self.device)   # history.py:10-11
+        self.head = self.ring_slots - 1
+
+    # -- reference API ------------------------------------------------------------------
+    def add(self, screen, replicate=1):
+        """history.py:13-15.  ``screen`` is either raw frames u8 [B,210,160,3] (fused
+        Environment.screen + add: one kernel, K1) or ready 84x84 screens u8 [B,84,84]."""
+        new_head = (self.head + 1) % self.ring_slots
+        if tuple(screen.shape[1:]) == FRAME_SHAPE:
+            if screen.dtype != torch.uint8:
+                raise TypeError("frames must be uint8")
+            _cabi.call("arl_preprocess_push", _cabi.ptr(screen), _cabi.ptr(self.ring),
+                       self.num_envs, self.ring_slots, new_head, int(replicate),
+                       _cabi.stream_ptr())
+        elif tuple(screen.shape[1:]) == (SCREEN, SCREEN):
+            for r in range(replicate):
+                self.ring[:, (new_head + r) % self.ring_slots].copy_(screen)
+        else:
+            raise ValueError("expected [B,210,160,3] frames or [B,84,84] screens, got %s"
+                             % (tuple(screen.shape),))
+        self.head = (new_head + replicate - 1) % self.ring_slots
+
+    def reset(self):
+        """history.py:17-18."""
+        _cabi.call("arl_history_reset", _cabi.ptr(self.ring), self.num_envs, self.ring_slots,
+                   _cabi.stream_ptr())
+
+    def get(self, back=0, dtype=torch.float32):
+        """history.py:20-24: [B,84,84,4] (NHWC) or [B,4,84,84]; float32 like the reference."""
+        first = self.first_slot(back)
+        out = torch.empty(self.num_envs, SCREEN, SCREEN, 4, dtype=dtype, device=self.device)
+        _cabi.call("arl_history_get", _cabi.ptr(self.ring), _cabi.ptr(out),
+                   1 if dtype == torch.uint8 else 0, self.num_envs, self.ring_slots, first,
+                   _cabi.stream_ptr())
+        if self.cnn_format == 'NHWC':
+            return out
+        return out.permute(0, 3, 1, 2)
+
+    def copy(self):
+        """history.py:26-27."""
+        return self.get().contiguous()
+
+    # -- ring bookkeeping used by Network/Agent --------------------------------------------
+    def first_slot(self, back=0):
+        """Slot of the OLDEST plane of the stack that ended ``back`` pushes ago."""
+        return (self.head - 3 - back) % self.ring_slots

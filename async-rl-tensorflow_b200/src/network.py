@@ -1,0 +1,219 @@
+"""Network: the A3C policy/value net (reference src/network.py:6-127, 'nips' trunk as wired in
+agent.py:226-252), with the reference's attribute names: ``w`` {l1_w..q_b}, ``policy_logits``,
+``policy``, ``log_policy``, ``policy_entropy``, ``sampled_action``, ``value``, ``R``,
+``total_loss``, ``copy_from_global``, ``save_model``, ``load_model``.
+
+The reference builds a TF graph; this class owns flat f32 device buffers (parameters,
+gradients, RMSProp slot) plus the rollout activations, and launches the sm_100a kernels
+through the C-ABI.  Repairs of the reference's dead/broken graph follow
+the paper's Algorithm 3 and are listed in DESIGN.md.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l4_w", "l4_b", "p_w", "p_b", "q_w", "q_b")
+A1_ELEMS, A2_ELEMS, FC = 6400, 2592, 256
+
+
+def param_shapes(action_size):
+    return OrderedDict([
+        ("l1_w", (8, 8, 4, 16)), ("l1_b", (16,)), ("l2_w", (4, 4, 16, 32)), ("l2_b", (32,)),
+        ("l4_w", (A2_ELEMS, FC)), ("l4_b", (FC,)), ("p_w", (FC, action_size)),
+        ("p_b", (action_size,)), ("q_w", (FC, 1)), ("q_b", (1,))])
+
+
+def initial_weights(action_size, seed=123, stddev=0.02):
+    """network.py:10 truncated_normal(0,.02) for convs, ops.py:36-39 normal(.02) for ``linear``
+    matrices, zero biases (ops.py:24,38-39).  Returns an OrderedDict of CPU float32 tensors."""
+    g = torch.Generator().manual_seed(int(seed))
+    out = OrderedDict()
+    for name, shape in param_shapes(action_size).items():
+        if name.endswith("_b"):
+            out[name] = torch.zeros(shape)
+        elif name in ("l1_w", "l2_w"):
+            w = torch.empty(shape)
+            torch.nn.init.trunc_normal_(w, 0.0, stddev, -2 * stddev, 2 * stddev, generator=g)
+            out[name] = w
+        else:
+            out[name] = torch.randn(shape, generator=g) * stddev
+    return out
+
+
+class Network(object):
+    def __init__(self, sess=None, data_format='NHWC', history_length=4, screen_height=84,
+                 screen_width=84, action_size=6, activation_fn='relu', initializer=None,
+                 gamma=0.99, beta=0.01, global_network=None, global_optim=None, DQN_type='nips',
+                 num_envs=256, t_max=5, device='cuda', seed=123, decay=0.99, epsilon=0.1,
+                 clip_norm=40.0, min_reward=-1.0, max_reward=1.0):
+        if DQN_type.lower() != 'nips':
+            raise NotImplementedError("only the 'nips' trunk (conv16-conv32-fc256) is built; "
+                                      "network.py:30-42 'nature' is out of scope (SURVEY §8f)")
+        if data_format != 'NHWC':
+            raise ValueError("main.py:45 forces NHWC; NCHW is not built")
+        if (history_length, screen_height, screen_width) != (4, 84, 84):
+            raise ValueError("kernels are built for 84x84x4 stacks")
+        if activation_fn not in ('relu', None) and getattr(activation_fn, '__name__', '') != 'relu':
+            raise ValueError("only relu is built")
+        self.sess = sess
+        self.device = torch.device(device)
+        _cabi.init(self.device)
+        self.action_size, self.num_envs, self.t_max = int(action_size), int(num_envs), int(t_max)
+        self.gamma, self.beta = float(gamma), float(beta)
+        self.decay, self.epsilon, self.clip_norm = float(decay), float(epsilon), float(clip_norm)
+        self.min_reward, self.max_reward = float(min_reward), float(max_reward)
+        self.global_network = global_network
+
+        A, B, T = self.action_size, self.num_envs, self.t_max
+        self.offsets = _cabi.param_layout(A)
+        n_params = self.offsets[-1]
+        dev = self.device
+        self.params = torch.zeros(n_params, device=dev)
+        self.grads = torch.zeros(n_params, device=dev)
+        self.rms = torch.ones(n_params, device=dev)           # TF RMSProp slot starts at 1.0
+        self.w, self.g = OrderedDict(), OrderedDict()
+        for i, (name, shape) in enumerate(param_shapes(A).items()):
+            self.w[name] = self.params[self.offsets[i]:self.offsets[i + 1]].view(shape)
+            self.g[name] = self.grads[self.offsets[i]:self.offsets[i + 1]].view(shape)
+        self.set_weights(initial_weights(A, seed))
+
+        N = B * T
+        f32 = dict(device=dev, dtype=torch.float32)
+        # rollout activations, t-major: sample n = t*B + b
+        self.l1 = torch.empty(N, 20, 20, 16, **f32)           # network.py:47-48
+        self.l2 = torch.empty(N, A2_ELEMS, **f32)             # network.py:49-50 (flattened NHWC)
+        self.l4 = torch.empty(N, FC, **f32)                   # network.py:51-52
+        self.policy_logits = torch.empty(N, A, **f32)         # network.py:62
+        self.policy = torch.empty(N, A, **f32)                # network.py:65
+        self.value = torch.empty(N, **f32)                    # network.py:79
+        self.sampled_action = torch.zeros(N, dtype=torch.int32, device=dev)   # network.py:72
+        self.R = torch.empty(N, **f32)                        # network.py:82
+        # bootstrap-state scratch (not kept for backward)
+        self._b = dict(l1=torch.empty(B, 20, 20, 16, **f32), l2=torch.empty(B, A2_ELEMS, **f32),
+                       l4=torch.empty(B, FC, **f32), logits=torch.empty(B, A, **f32),
+                       probs=torch.empty(B, A, **f32), value=torch.empty(B, **f32))
+        # backward scratch
+        self.d_logits = torch.empty(N, A, **f32)
+        self.d_value = torch.empty(N, **f32)
+        self.d_l4 = torch.empty(N, FC, **f32)
+        self.d_l2 = torch.empty(N, A2_ELEMS, **f32)
+        self.d_l1 = torch.empty(N, 20, 20, 16, **f32)
+        self.workspace = torch.empty(_cabi.workspace_bytes(A), dtype=torch.uint8, device=dev)
+        self.loss_sums = torch.zeros(3, **f32)                # sum policy / value loss, entropy
+        self.grad_norms = torch.zeros(len(PARAM_NAMES), **f32)
+
+    # -- parameters -----------------------------------------------------------------------
+    def set_weights(self, weights):
+        for name in PARAM_NAMES:
+            self.w[name].copy_(torch.as_tensor(np.asarray(weights[name]), dtype=torch.float32))
+
+    def get_weights(self):
+        return OrderedDict((k, v.detach().cpu().numpy().copy()) for k, v in self.w.items())
+
+    def copy_from_global(self):
+        """network.py:96-107: theta' <- theta.  Replicas are updated synchronously with the same
+        all-reduced gradient, so this is the identity unless a global_network was given."""
+        if self.global_network is not None and self.global_network is not self:
+            self.params.copy_(self.global_network.params)
+
+    # -- forward ----------------------------------------------------------------------------
+    def _rows(self, t):
+        B = self.num_envs
+        return slice(t * B, (t + 1) * B)
+
+    def forward(self, history, t):
+        """Forward of the current stack into rollout slot ``t``; returns (logits, policy, value)."""
+        r = self._rows(t)
+        _cabi.call("arl_forward", _cabi.ptr(self.params), self.action_size,
+                   _cabi.ptr(history.ring), self.num_envs, history.ring_slots,
+                   history.first_slot(0), 1, _cabi.ptr(self.l1[r]), _cabi.ptr(self.l2[r]),
+                   _cabi.ptr(self.l4[r]), _cabi.ptr(self.policy_logits[r]),
+                   _cabi.ptr(self.policy[r]), _cabi.ptr(self.value[r]), _cabi.stream_ptr())
+        return self.policy_logits[r], self.policy[r], self.value[r]
+
+    def sample(self, t, step, seed, env_id_base=0):
+        """network.py:72-73 sampled_action for rollout slot t."""
+        r = self._rows(t)
+        _cabi.call("arl_sample_actions", _cabi.ptr(self.policy[r]),
+                   _cabi.ptr(self.sampled_action[r]), self.num_envs, self.action_size,
+                   int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
+        return self.sampled_action[r]
+
+    def bootstrap_value(self, history):
+        """V(s_T) under the same theta (Algorithm 3: R = V(s_t, theta'_v))."""
+        b = self._b
+        _cabi.call("arl_forward", _cabi.ptr(self.params), self.action_size,
+                   _cabi.ptr(history.ring), self.num_envs, history.ring_slots,
+                   history.first_slot(0), 1, _cabi.ptr(b['l1']), _cabi.ptr(b['l2']),
+                   _cabi.ptr(b['l4']), _cabi.ptr(b['logits']), _cabi.ptr(b['probs']),
+                   _cabi.ptr(b['value']), _cabi.stream_ptr())
+        return b['value']
+
+    @property
+    def log_policy(self):                                   # network.py:67 (log OF the softmax)
+        return torch.log(self.policy)
+
+    @property
+    def policy_entropy(self):                               # network.py:69
+        return -(self.policy * self.log_policy).sum(1)
+
+    @property
+    def total_loss(self):
+        """network.py:94 summed over the last rollout (policy + value), as a host float."""
+        s = self.loss_sums.tolist()
+        return s[0] + s[1]
+
+    # -- backward ---------------------------------------------------------------------------
+    def compute_gradients(self, history, rewards, terminals, v_boot, actions=None,
+                          grad_scale=1.0):
+        """Returns + loss grads (K4) then the full backward (agent.py:317) over the T*B samples
+        of the rollout.  ``history`` must have had exactly t_max pushes since s_0."""
+        T, B, A = self.t_max, self.num_envs, self.action_size
+        acts = self.sampled_action if actions is None else actions
+        self.loss_sums.zero_()
+        st = _cabi.stream_ptr()
+        _cabi.call("arl_returns_lossgrad", _cabi.ptr(rewards), _cabi.ptr(terminals),
+                   _cabi.ptr(acts), _cabi.ptr(self.policy_logits), _cabi.ptr(self.value),
+                   _cabi.ptr(v_boot), _cabi.ptr(self.R), _cabi.ptr(self.d_logits),
+                   _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
+                   self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
+        _cabi.call("arl_backward", _cabi.ptr(self.params), A, _cabi.ptr(history.ring), B,
+                   history.ring_slots, history.first_slot(T), T, _cabi.ptr(self.l1),
+                   _cabi.ptr(self.l2), _cabi.ptr(self.l4), _cabi.ptr(self.d_logits),
+                   _cabi.ptr(self.d_value), _cabi.ptr(self.d_l4), _cabi.ptr(self.d_l2),
+                   _cabi.ptr(self.d_l1), _cabi.ptr(self.grads), _cabi.ptr(self.workspace), st)
+        return self.grads
+
+    def apply_gradients(self, lr):
+        """agent.py:316-321: per-tensor clip_by_norm(40) + shared RMSProp (K5)."""
+        _cabi.call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                   _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
+                   self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
+                   _cabi.stream_ptr())
+
+    # -- checkpoints (network.py:109-127), reference variable names + the rms slot ----------
+    def save_model(self, saver=None, checkpoint_dir='checkpoints', step=None):
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, "Network-%s.npz" % (step if step is not None else 0))
+        blobs = {k: v.detach().cpu().numpy() for k, v in self.w.items()}
+        blobs["rms"] = self.rms.detach().cpu().numpy()
+        blobs["step"] = np.int64(step if step is not None else 0)
+        np.savez(path, **blobs)
+        return path
+
+    def load_model(self, saver=None, checkpoint_dir='checkpoints'):
+        if not os.path.isdir(checkpoint_dir):
+            return False
+        files = sorted((f for f in os.listdir(checkpoint_dir) if f.startswith("Network-")),
+                       key=lambda f: int(f[8:-4]))
+        if not files:
+            return False
+        z = np.load(os.path.join(checkpoint_dir, files[-1]))
+        self.set_weights({k: z[k] for k in PARAM_NAMES})
+        self.rms.copy_(torch.as_tensor(z["rms"]))
+        self.loaded_step = int(z["step"])
+        return True

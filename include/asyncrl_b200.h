@@ -1,0 +1,158 @@
+/*
+ * asyncrl_b200 -- C-ABI of the B200-native A3C worker hot path.
+ *
+ * Drop-in boundary for datavizweb/async-rl-tensorflow.  The reference has no
+ * FFI of its own: its seams are Python classes plus tf.Session.run(feed_dict)
+ * (SURVEY.md §8b).  Each entry point below replaces the TensorFlow / cv2 work
+ * behind one of those seams and cites it (paths relative to the reference).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All tensor pointers are DEVICE
+ *     pointers owned by the caller; the library allocates nothing per call.
+ *   - every function returns 0 on success, a negative arl_status otherwise; the
+ *     message is in arl_last_error() (thread-local).
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     no hidden synchronisation.
+ *   - samples are indexed n = t * num_envs + b  (t-major).  The frame ring is
+ *     u8 [num_envs][ring_slots][84*84]; sample (t,b) reads the 4 planes
+ *     ring[b][(first_slot + t + k) % ring_slots], k = 0 (oldest) .. 3 (newest),
+ *     i.e. History.get() channel order (src/history.py:20-24).
+ *   - parameters / gradients / RMSProp slots are flat f32 buffers in the
+ *     reference's own variable order and layouts (see arl_param_layout).
+ */
+#ifndef ASYNCRL_B200_H_
+#define ASYNCRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARL_FRAME_H 210
+#define ARL_FRAME_W 160
+#define ARL_FRAME_C 3
+#define ARL_SCREEN 84            /* config.py:38-39 screen_width/height          */
+#define ARL_HISTORY 4            /* config.py:22 history_length                  */
+#define ARL_A1_ELEMS 6400        /* 20*20*16  conv1 output per sample            */
+#define ARL_A2_ELEMS 2592        /* 9*9*32    conv2 output per sample (flatten)  */
+#define ARL_FC 256               /* agent.py:251 / network.py:51                 */
+#define ARL_NUM_TENSORS 10       /* l1_w l1_b l2_w l2_b l4_w l4_b p_w p_b q_w q_b */
+#define ARL_MAX_ACTIONS 32
+
+#if defined(__GNUC__)
+#define ARL_API __attribute__((visibility("default")))
+#else
+#define ARL_API
+#endif
+
+typedef enum {
+  ARL_OK = 0,
+  ARL_ERR_INVALID = -1,          /* bad argument (message says which)            */
+  ARL_ERR_CUDA = -2,             /* CUDA runtime error                           */
+  ARL_ERR_UNSUPPORTED = -3       /* valid request this build does not implement  */
+} arl_status;
+
+/* Thread-local message of the last failing call on this thread. */
+ARL_API const char* arl_last_error(void);
+ARL_API int arl_version(void);
+
+/* One-time per-process set-up on `device`: derives the luma correction bitmap
+ * (the 774 RGB triples where the reference's float64 luma truncates one below the
+ * exact quotient) with IEEE f64 on the device and raises the shared-memory limits
+ * of the big kernels.  Must precede every other call. */
+ARL_API int arl_init(int device);
+
+/* Offsets (in floats) of the 10 tensors inside the flat buffers and the total.
+ * Order/layout: l1_w[8,8,4,16] l1_b[16] l2_w[4,4,16,32] l2_b[32] l4_w[2592,256]
+ * l4_b[256] p_w[256,A] p_b[A] q_w[256,1] q_b[1]  -- ops.py:19-24,36-39;
+ * agent.py:226-229,251; network.py:62,79.  offsets has ARL_NUM_TENSORS+1 entries. */
+ARL_API int arl_param_layout(int action_size, int64_t* offsets);
+
+/* ---- K1: Environment.screen + History.add ------------------------------------------
+ * src/environment.py:49-53 (float64 luma, truncate, cv2.resize INTER_LINEAR 84x84) fused
+ * with src/history.py:13-15 (push newest).  frames u8 [num_envs,210,160,3] ->
+ * ring[b][(slot + r) % ring_slots] for r in [0, replicate)   (replicate = 4 reproduces
+ * agent.py:37-38, which seeds the stack with 4 copies of the first screen).
+ * Bit-exact against the reference's executed expression. */
+ARL_API int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num_envs, int ring_slots,
+                        int slot, int replicate, void* stream);
+
+/* History.get()/copy() (src/history.py:20-27): materialise the NHWC stack
+ * f32 [num_envs,84,84,4] (or u8 when out_is_u8) whose oldest plane is `first_slot`. */
+ARL_API int arl_history_get(const uint8_t* ring, void* out, int out_is_u8, int num_envs,
+                    int ring_slots, int first_slot, void* stream);
+/* History.reset() (src/history.py:17-18): zero every slot. */
+ARL_API int arl_history_reset(uint8_t* ring, int num_envs, int ring_slots, void* stream);
+
+/* ---- K2/K3: trunk + heads forward ---------------------------------------------------
+ * agent.py:226-232,251 (s_t/255 -> conv 8x8s4 relu -> conv 4x4s2 relu -> NHWC flatten ->
+ * fc256 relu), network.py:62 (policy logits), network.py:79 (value), network.py:65
+ * (softmax).  steps*num_envs samples.  a1 [N,20,20,16], a2 [N,2592], h [N,256] are
+ * written for the backward pass; logits/probs [N,A], value [N]. */
+ARL_API int arl_conv1_forward(const float* params, const uint8_t* ring, float* a1, int num_envs,
+                      int ring_slots, int first_slot, int steps, void* stream);
+ARL_API int arl_conv2_forward(const float* params, const float* a1, float* a2, int64_t num_samples,
+                      void* stream);
+ARL_API int arl_fc_forward(const float* params, const float* a2, float* h, int64_t num_samples,
+                   void* stream);
+ARL_API int arl_heads_forward(const float* params, int action_size, const float* h, float* logits,
+                      float* probs, float* value, int64_t num_samples, void* stream);
+/* The four above back to back. */
+ARL_API int arl_forward(const float* params, int action_size, const uint8_t* ring, int num_envs,
+                int ring_slots, int first_slot, int steps, float* a1, float* a2, float* h,
+                float* logits, float* probs, float* value, void* stream);
+
+/* ---- K4: action sampling, returns, loss gradients -----------------------------------
+ * network.py:72 batch_sample(policy) (undefined in the reference): Philox4x32-10 keyed
+ * (seed; env_id_base + b, step), inverse CDF over the f32 running sum.  actions i32. */
+ARL_API int arl_sample_actions(const float* probs, int32_t* actions, int num_envs, int action_size,
+                       int64_t env_id_base, int64_t step, uint64_t seed, void* stream);
+/* agent.py:146-149 epsilon-greedy over argmax (ties -> lowest index, agent.py:254). */
+ARL_API int arl_greedy_actions(const float* scores, int32_t* actions, int num_envs, int action_size,
+                       void* stream);
+
+/* Algorithm 3 (assets/a3c.png) returns with the terminal mask of agent.py:188-190 and the
+ * reward clip of agent.py:154, then d(total_loss)/d(logits,value) per network.py:81-94:
+ *   R_t = clip(r_t) + gamma*(1-term_t)*R_{t+1},  R_T = v_boot
+ *   dlogits = grad_scale*(-(R-V)*(onehot(a)-p) + beta*p*(logp+H)),  dvalue = grad_scale*(V-R)
+ * rewards f32 [T,B], terminals u8 [T,B], actions i32 [T,B], logits [T,B,A], value [T,B].
+ * loss_sums (optional, may be NULL) f32 [3] += {sum policy_loss, sum value_loss, sum entropy}
+ * unscaled. */
+ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals, const int32_t* actions,
+                         const float* logits, const float* value, const float* v_boot,
+                         float* returns, float* dlogits, float* dvalue, float* loss_sums,
+                         int t_max, int num_envs, int action_size, float gamma, float beta,
+                         float reward_min, float reward_max, float grad_scale, void* stream);
+
+/* ---- backward: agent.py:317 compute_gradients ---------------------------------------
+ * Accumulation over the T steps of Algorithm 3 is the reduction over samples inside the
+ * weight-gradient kernels.  grads is the flat buffer (overwritten).  Scratch buffers are
+ * caller-owned: d_h [N,256], d_a2 [N,2592], d_a1 [N,6400], workspace >= arl_backward_workspace_bytes. */
+ARL_API int64_t arl_backward_workspace_bytes(int action_size);
+ARL_API int arl_heads_backward(const float* params, int action_size, const float* h,
+                       const float* dlogits, const float* dvalue, float* d_h, float* grads,
+                       void* workspace, int64_t num_samples, void* stream);
+ARL_API int arl_fc_backward(const float* params, const float* a2, const float* d_h, float* d_a2,
+                    float* grads, void* workspace, int64_t num_samples, void* stream);
+ARL_API int arl_conv2_backward(const float* params, const float* a1, const float* d_a2, float* d_a1,
+                       float* grads, void* workspace, int64_t num_samples, void* stream);
+ARL_API int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads, void* workspace,
+                       int num_envs, int ring_slots, int first_slot, int steps, void* stream);
+ARL_API int arl_backward(const float* params, int action_size, const uint8_t* ring, int num_envs,
+                 int ring_slots, int first_slot, int steps, const float* a1, const float* a2,
+                 const float* h, const float* dlogits, const float* dvalue, float* d_h,
+                 float* d_a2, float* d_a1, float* grads, void* workspace, void* stream);
+
+/* ---- K5: per-tensor clip + shared RMSProp -------------------------------------------
+ * agent.py:316-319 clip_by_norm(g, clip) per tensor, then TF ApplyRMSProp as configured at
+ * main.py:63-65:  ms += (g^2-ms)(1-decay);  w -= lr*g/sqrt(ms+eps).  `lr` per agent.py:393-395
+ * is computed by the caller.  norms_out (optional) f32 [ARL_NUM_TENSORS] = pre-clip norms. */
+ARL_API int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size, float lr,
+                     float decay, float eps, float clip_norm, float* norms_out, void* workspace,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ASYNCRL_B200_H_ */

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads and exports every symbol include/asyncrl_b200.h declares; the
+host-only entry points work; the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "asyncrl_b200.h")).read()
+    return sorted(set(re.findall(r"ARL_API[^;(]*?\b(arl_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = header_symbols()
+    assert len(syms) == 22, syms
+    for must in ("arl_preprocess_push", "arl_forward", "arl_backward", "arl_sample_actions",
+                 "arl_returns_lossgrad", "arl_clip_rmsprop", "arl_param_layout", "arl_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg._cabi.load()
+    for s in header_symbols():
+        assert getattr(lib, s) is not None, s
+    assert set(header_symbols()) == set(pkg._cabi.EXPORTS)      # ctypes table == header
+
+
+def test_param_layout_is_the_reference_order(pkg):
+    off = pkg._cabi.param_layout(6)
+    assert off == [0, 4096, 4112, 12304, 12336, 675888, 676144, 677680, 677686, 677942, 677943]
+    assert pkg._cabi.param_layout(18)[-1] == 681027
+    lib = pkg._cabi.load()
+    buf = (ctypes.c_int64 * 11)()
+    assert lib.arl_param_layout(0, buf) == -1                  # ARL_ERR_INVALID, message set
+    assert b"action_size" in lib.arl_last_error()
+    assert lib.arl_param_layout(6, None) == -1
+
+
+def test_no_cpu_fallback(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg._cabi.ArlError):
+        pkg._cabi.init("cuda:0")
+    with pytest.raises(pkg._cabi.ArlError):
+        pkg.History(pkg.config.M1, num_envs=2)
+    with pytest.raises(pkg._cabi.ArlError):
+        pkg._cabi.ptr(torch.zeros(4))                          # CPU tensors are refused
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "async-rl-tensorflow_b200")
+    for base, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "/root/reference" not in txt, f

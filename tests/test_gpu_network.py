@@ -1,0 +1,305 @@
+"""GPU: network forward/backward, sampling, returns/loss, clip+RMSProp and the full A3C cycle
+through the C-ABI, against the float64 oracle on identical synthetic inputs and weights.
+Tolerance: BASELINE.json north_star -- rel-err <= 1e-3 for logits, values, returns, gradients;
+bit-exact for action sampling on identical probabilities; parameter trajectory within 1e-3
+over 100 updates."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import a3c, philox
+from util import REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(A, seed=0, bias_std=0.01, scale=1.0):
+    p = a3c.init_params(A, seed)
+    rng = np.random.default_rng(seed + 1)
+    for k in p:
+        if k.endswith("_b"):
+            p[k] = rng.normal(0, bias_std, p[k].shape).astype(np.float32)
+        else:
+            p[k] = (p[k] * scale).astype(np.float32)
+    return p
+
+
+def net_for(pkg, A, B, T, params):
+    net = pkg.Network(action_size=A, num_envs=B, t_max=T, device="cuda:0")
+    net.set_weights(params)
+    return net
+
+
+def ring_stacks(ring_np, first_slot, steps):
+    """oracle-side view of the ring: [steps*B, 84, 84, 4], t-major."""
+    B, R = ring_np.shape[:2]
+    out = []
+    for t in range(steps):
+        out.append(np.stack([ring_np[:, (first_slot + t + k) % R] for k in range(4)], axis=-1))
+    return np.concatenate(out, axis=0)
+
+
+@pytest.mark.parametrize("A,B,T,R,first", [(6, 5, 3, 8, 6), (18, 4, 1, 4, 2), (4, 7, 2, 9, 0)])
+def test_forward_layers_vs_oracle(pkg, cuda, A, B, T, R, first):
+    rng = np.random.default_rng(A * 100 + B)
+    params = make_params(A, seed=A, scale=2.0)
+    ring_np = rng.integers(0, 256, (B, R, 84, 84), dtype=np.uint8)
+    ring = torch.as_tensor(ring_np, device=cuda)
+    flat = torch.as_tensor(a3c.flatten_params(params), device=cuda)
+    N = B * T
+    f32 = dict(device=cuda, dtype=torch.float32)
+    a1 = torch.empty(N, 20, 20, 16, **f32); a2 = torch.empty(N, 2592, **f32)
+    h = torch.empty(N, 256, **f32); lg = torch.empty(N, A, **f32)
+    pr = torch.empty(N, A, **f32); v = torch.empty(N, **f32)
+    pkg._cabi.call("arl_forward", flat.data_ptr(), A, ring.data_ptr(), B, R, first, T,
+                   a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
+                   v.data_ptr(), pkg._cabi.stream_ptr())
+    torch.cuda.synchronize()
+    logits, value, keep = a3c.forward(a3c.to_torch(params), ring_stacks(ring_np, first, T), keep=True)
+    pi, _, _ = a3c.policy_terms(logits)
+    errs = dict(a1=rel_err(a1.cpu(), keep["a1"]), a2=rel_err(a2.cpu(), keep["a2"]),
+                h=rel_err(h.cpu(), keep["h"]), logits=rel_err(lg.cpu(), logits),
+                value=rel_err(v.cpu(), value), probs=rel_err(pr.cpu(), pi))
+    print("forward rel-err", errs)
+    assert max(errs.values()) <= REL_TOL, errs
+    assert float(a1.min()) >= 0 and float(h.min()) >= 0 and float((a2 == 0).float().mean()) > 0.05
+
+
+def test_ops_wrappers_layer_by_layer(pkg, cuda):
+    """conv2d / linear / heads / batch_sample of src/ops.py against the oracle."""
+    A, B = 6, 6
+    params = make_params(A, seed=3, scale=2.0)
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": 5})
+    hist = pkg.History(cfg, num_envs=B, device=cuda)
+    rng = np.random.default_rng(9)
+    hist.ring.copy_(torch.as_tensor(rng.integers(0, 256, tuple(hist.ring.shape), dtype=np.uint8)))
+    flat = torch.as_tensor(a3c.flatten_params(params), device=cuda)
+    ops = pkg.ops
+    l1 = ops.conv2d(hist, flat, 16, [8, 8], [4, 4], name='l1')
+    l2 = ops.conv2d(l1, flat, 32, [4, 4], [2, 2], name='l2')
+    l4 = ops.linear(l2, flat, 256, name='l4')
+    lg, pr, v = ops.heads(l4, flat, A)
+    act = ops.batch_sample(pr, step=5, seed=123, env_id_base=10)
+    torch.cuda.synchronize()
+    stacks = hist.get().cpu().numpy()
+    logits, value, keep = a3c.forward(a3c.to_torch(params), stacks, keep=True)
+    assert rel_err(l1.cpu(), keep["a1"]) <= REL_TOL and rel_err(l4.cpu(), keep["h"]) <= REL_TOL
+    assert rel_err(lg.cpu(), logits) <= REL_TOL and rel_err(v.cpu(), value) <= REL_TOL
+    ref_act = philox.sample_actions(pr.cpu().numpy(), np.arange(10, 10 + B), 5, 123)
+    assert np.array_equal(act.cpu().numpy(), ref_act)
+    with pytest.raises(NotImplementedError):
+        ops.conv2d(l1, flat, 64, [3, 3], [1, 1], name='l3')
+
+
+@pytest.mark.parametrize("A,B", [(6, 4096), (18, 1000), (4, 33)])
+def test_sampler_bit_exact_on_identical_probs(pkg, cuda, A, B):
+    g = torch.Generator(device=cuda).manual_seed(A)
+    probs = torch.softmax(torch.randn(B, A, device=cuda, generator=g) * 2, dim=1).contiguous()
+    for step, seed, base in [(0, 123, 0), (77, 123, 4096), (2 ** 33 + 5, 2 ** 40 + 9, 12345)]:
+        act = pkg.ops.batch_sample(probs, step=step, seed=seed, env_id_base=base)
+        ref = philox.sample_actions(probs.cpu().numpy(), np.arange(base, base + B), step, seed)
+        assert np.array_equal(act.cpu().numpy(), ref)
+    # degenerate rows
+    z = torch.zeros(5, A, device=cuda)
+    assert (pkg.ops.batch_sample(z).cpu().numpy() == A - 1).all()
+    # argmax: ties -> lowest index
+    s = torch.tensor([[1., 3., 3., 0.], [2., 2., 2., 2.]], device=cuda)
+    assert pkg.ops.argmax(s).cpu().tolist() == [1, 0]
+
+
+@pytest.mark.parametrize("A,T,B", [(6, 5, 37), (18, 20, 8), (4, 1, 3)])
+def test_returns_and_loss_grads_vs_oracle(pkg, cuda, A, T, B):
+    rng = np.random.default_rng(T * 10 + B)
+    logits = rng.normal(0, 1.5, (T, B, A)).astype(np.float32)
+    value = rng.normal(0, 1, (T, B)).astype(np.float32)
+    vboot = rng.normal(0, 1, B).astype(np.float32)
+    rew = rng.choice([-3.0, -1.0, 0.0, 0.5, 1.0, 7.0], (T, B)).astype(np.float32)
+    term = (rng.random((T, B)) < 0.25)
+    acts = rng.integers(0, A, (T, B)).astype(np.int32)
+    d = lambda x: torch.as_tensor(x, device=cuda)
+    R = torch.empty(T, B, device=cuda); dl = torch.empty(T, B, A, device=cuda)
+    dv = torch.empty(T, B, device=cuda); sums = torch.zeros(3, device=cuda)
+    scale = 1.0 / B
+    pkg._cabi.call("arl_returns_lossgrad", d(rew).data_ptr(), d(term.astype(np.uint8)).data_ptr(),
+                   d(acts).data_ptr(), d(logits).data_ptr(), d(value).data_ptr(),
+                   d(vboot).data_ptr(), R.data_ptr(), dl.data_ptr(), dv.data_ptr(),
+                   sums.data_ptr(), T, B, A, 0.99, 0.01, -1.0, 1.0, scale, pkg._cabi.stream_ptr())
+    torch.cuda.synchronize()
+    Rref = a3c.nstep_returns(a3c.clip_rewards(rew), term, vboot.astype(np.float64), 0.99)
+    lt = torch.tensor(logits.reshape(-1, A), dtype=torch.float64)
+    vt = torch.tensor(value.reshape(-1), dtype=torch.float64)
+    at = torch.tensor(acts.reshape(-1)); Rt = torch.tensor(Rref.reshape(-1))
+    dlr, dvr = a3c.analytic_head_grads(lt, vt, at, Rt, 0.01, scale)
+    tot, pl, vl = a3c.loss_per_sample(lt, vt, at, Rt, 0.01)
+    _, _, ent = a3c.policy_terms(lt)
+    errs = dict(R=rel_err(R.cpu(), Rref), dlogits=rel_err(dl.cpu().reshape(-1, A), dlr),
+                dvalue=rel_err(dv.cpu().reshape(-1), dvr),
+                sums=rel_err(sums.cpu(), [float(pl.sum()), float(vl.sum()), float(ent.sum())]))
+    print("returns/loss rel-err", errs)
+    assert max(errs.values()) <= REL_TOL, errs
+
+
+def _gpu_cycle_grads(pkg, cuda, net, hist, rew, term, acts, scale):
+    T, B = net.t_max, net.num_envs
+    d = lambda x: torch.as_tensor(x, device=cuda)
+    v_boot = net.bootstrap_value(hist)
+    net.compute_gradients(hist, d(rew.astype(np.float32)), d(term.astype(np.uint8)), v_boot,
+                          actions=d(acts.astype(np.int32).reshape(-1)), grad_scale=scale)
+    torch.cuda.synchronize()
+    return v_boot
+
+
+@pytest.mark.parametrize("A,B,T", [(6, 7, 5), (18, 3, 2)])
+def test_backward_gradients_vs_oracle(pkg, cuda, A, B, T):
+    """Whole backward (heads -> fc -> conv2 -> conv1) on a rollout, all 10 tensors, plus the
+    intermediate input-gradients checked layer by layer with float64 autograd."""
+    rng = np.random.default_rng(A + B)
+    params = make_params(A, seed=11, scale=2.0)
+    net = net_for(pkg, A, B, T, params)
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T})
+    hist = pkg.History(cfg, num_envs=B, device=cuda)
+    screens = rng.integers(0, 256, (T + 4, B, 84, 84), dtype=np.uint8)
+    for k in range(4):
+        hist.add(torch.as_tensor(screens[k], device=cuda))
+    for t in range(T):
+        net.forward(hist, t)
+        hist.add(torch.as_tensor(screens[4 + t], device=cuda))
+    acts = rng.integers(0, A, (T, B)); rew = rng.choice([-2.0, 0.0, 1.0], (T, B))
+    term = rng.random((T, B)) < 0.2
+    v_boot = _gpu_cycle_grads(pkg, cuda, net, hist, rew, term, acts, 1.0 / B)
+
+    stacks = a3c.stacks_from_screens(screens, T)
+    p64 = a3c.to_torch(params)
+    with torch.no_grad():
+        _, vb = a3c.forward(p64, stacks[T])
+    assert rel_err(v_boot.cpu(), vb) <= REL_TOL
+    R = a3c.nstep_returns(a3c.clip_rewards(rew), term, vb.numpy(), 0.99)
+    assert rel_err(net.R.cpu().reshape(T, B), R) <= REL_TOL
+    grads, aux = a3c.gradients(params, stacks[:T].reshape(T * B, 84, 84, 4), acts.reshape(-1),
+                               R.reshape(-1), 0.01, B)
+    errs = {k: rel_err(net.g[k].cpu(), grads[k]) for k in a3c.PARAM_NAMES}
+    print("grad rel-err", errs)
+    assert max(errs.values()) <= REL_TOL, errs
+    assert rel_err(net.policy_logits.cpu(), aux["logits"]) <= REL_TOL
+    assert rel_err(net.value.cpu(), aux["value"]) <= REL_TOL
+
+
+def test_backward_single_sample_and_zero_samples(pkg, cuda):
+    A, B, T = 6, 1, 1
+    params = make_params(A, seed=2, scale=2.0)
+    net = net_for(pkg, A, B, T, params)
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T})
+    hist = pkg.History(cfg, num_envs=B, device=cuda)
+    rng = np.random.default_rng(1)
+    screens = rng.integers(0, 256, (T + 4, B, 84, 84), dtype=np.uint8)
+    for k in range(4):
+        hist.add(torch.as_tensor(screens[k], device=cuda))
+    net.forward(hist, 0)
+    hist.add(torch.as_tensor(screens[4], device=cuda))
+    acts = np.array([[2]]); rew = np.array([[1.0]]); term = np.array([[False]])
+    _gpu_cycle_grads(pkg, cuda, net, hist, rew, term, acts, 1.0)
+    stacks = a3c.stacks_from_screens(screens, T)
+    with torch.no_grad():
+        _, vb = a3c.forward(a3c.to_torch(params), stacks[T])
+    R = a3c.nstep_returns(a3c.clip_rewards(rew), term, vb.numpy(), 0.99)
+    grads, _ = a3c.gradients(params, stacks[0], acts.reshape(-1), R.reshape(-1), 0.01, 1)
+    errs = {k: rel_err(net.g[k].cpu(), grads[k]) for k in a3c.PARAM_NAMES}
+    assert max(errs.values()) <= REL_TOL, errs
+    # zero samples: every backward entry point must zero its gradient slice and return OK
+    lib = pkg._cabi.load()
+    net.grads.fill_(5.0)
+    st = pkg._cabi.stream_ptr()
+    P = pkg._cabi.ptr
+    assert lib.arl_backward(P(net.params), A, P(hist.ring), 0, hist.ring_slots, 0, 1, P(net.l1),
+                            P(net.l2), P(net.l4), P(net.d_logits), P(net.d_value), P(net.d_l4),
+                            P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), st) == 0
+    torch.cuda.synchronize()
+    assert float(net.grads.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("A", [6, 18])
+def test_clip_rmsprop_vs_oracle(pkg, cuda, A):
+    rng = np.random.default_rng(A)
+    params = make_params(A, seed=4)
+    net = net_for(pkg, A, 2, 1, params)
+    shapes = a3c.param_shapes(A)
+    grads = {k: rng.normal(0, 1.0, s).astype(np.float32) for k, s in shapes.items()}
+    grads["l4_w"] *= 0.2                      # norm ~163 -> clipped; q_b norm ~1 -> untouched
+    grads["l1_b"] *= 100.0                    # norm ~400 -> clipped
+    rms0 = {k: rng.uniform(0.5, 2.0, s).astype(np.float32) for k, s in shapes.items()}
+    net.grads.copy_(torch.as_tensor(a3c.flatten_params(grads)))
+    net.rms.copy_(torch.as_tensor(a3c.flatten_params(rms0)))
+    lr = 0.0007
+    net.apply_gradients(lr)
+    torch.cuda.synchronize()
+    newp, newr = a3c.update(params, rms0, grads, lr)
+    for i, k in enumerate(a3c.PARAM_NAMES):
+        nrm = float(np.sqrt((grads[k].astype(np.float64) ** 2).sum()))
+        assert abs(float(net.grad_norms[i]) - nrm) <= 1e-4 * nrm
+        lo, hi = net.offsets[i], net.offsets[i + 1]
+        assert rel_err(net.rms[lo:hi].cpu().reshape(shapes[k]), newr[k]) <= 1e-5
+        step_ref = newp[k] - params[k].astype(np.float64)
+        step_gpu = net.w[k].cpu().numpy().astype(np.float64) - params[k].astype(np.float64)
+        assert rel_err(step_gpu, step_ref) <= REL_TOL, k       # the update itself, not just w
+
+
+def _run_trajectory(pkg, cuda, A, B, T, updates, seed=123):
+    params = make_params(A, seed=21, bias_std=0.0)
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T, "seed": seed})
+    env = pkg.GymEnvironment(cfg, env=pkg.SyntheticAtari(B, action_size=A, seed=seed, pool=T + 3,
+                                                         device=cuda, p_terminal=0.05,
+                                                         reward_scale=2.0), device=cuda)
+    agent = pkg.Agent(cfg, env, device=cuda)
+    agent.network.set_weights(params)
+    p_ref = {k: v.astype(np.float64) for k, v in params.items()}
+    r_ref = {k: np.ones_like(v, np.float64) for k, v in params.items()}
+    p0 = {k: v.copy() for k, v in p_ref.items()}
+    agent.before_train()
+    worst = dict(param=0.0, disp=0.0, grad=0.0)
+    for u in range(updates):
+        ring = agent.history
+        screens = []
+        first = ring.first_slot(0)
+        snap = ring.ring.cpu().numpy()
+        screens = [snap[:, (first + k) % ring.ring_slots] for k in range(4)]
+        step0 = agent.step
+        for t in range(T):
+            action = agent.predict()
+            scr, rew, term = env.act(action, is_training=True, fused=True)
+            agent.history.add(scr)
+            agent.batch_reward[t].copy_(rew)
+            agent.batch_terminal[t].copy_(term)
+            screens.append(agent.history.ring[:, agent.history.head].cpu().numpy())
+            agent.t += 1
+            agent.step += 1
+        agent.step -= 1                                          # lr uses the step of the last frame
+        agent.batch_update()
+        agent.step += 1
+        torch.cuda.synchronize()
+        acts = agent.batch_action.cpu().numpy()
+        p_ref, r_ref, aux = a3c.a3c_cycle(p_ref, r_ref, np.stack(screens), acts,
+                                          agent.batch_reward.cpu().numpy(),
+                                          agent.batch_terminal.cpu().numpy().astype(bool), step0,
+                                          num_envs=B)
+        for k in a3c.PARAM_NAMES:
+            w = agent.network.w[k].cpu().numpy().astype(np.float64)
+            worst["param"] = max(worst["param"], rel_err(w, p_ref[k]))
+            worst["grad"] = max(worst["grad"], rel_err(agent.network.g[k].cpu(), aux["grads"][k]))
+            if u == updates - 1:
+                worst["disp"] = max(worst["disp"], rel_err(w - p0[k], p_ref[k] - p0[k]))
+    return worst
+
+
+def test_agent_cycle_short_trajectory(pkg, cuda):
+    worst = _run_trajectory(pkg, cuda, A=6, B=16, T=5, updates=5)
+    print("5-update trajectory", worst)
+    assert worst["param"] <= REL_TOL and worst["grad"] <= 5 * REL_TOL and worst["disp"] <= 1e-2
+
+
+def test_rmsprop_trajectory_100_updates_config2(pkg, cuda):
+    """BASELINE config 2: 256 envs, history 4, t_max 5; parameters within 1e-3 of the float64
+    oracle trajectory over 100 updates (teacher-forced actions, independent parameter copies)."""
+    worst = _run_trajectory(pkg, cuda, A=6, B=256, T=5, updates=100)
+    print("100-update trajectory", worst)
+    assert worst["param"] <= REL_TOL, worst
+    assert worst["disp"] <= 2e-2, worst

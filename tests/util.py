@@ -1,0 +1,27 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+REL_TOL = 1e-3      # BASELINE.json north_star: rel-err <= 1e-3 for logits, values, returns, grads
+
+
+def rel_err(x, ref):
+    """max |x - ref| / max |ref|  (scale-relative max error; 0/0 -> 0)."""
+    x = np.asarray(x, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    d = float(np.abs(x - ref).max()) if x.size else 0.0
+    s = float(np.abs(ref).max()) if ref.size else 0.0
+    return d / s if s > 0 else d
+
+
+def norm_err(x, ref):
+    x = np.asarray(x, np.float64).ravel()
+    ref = np.asarray(ref, np.float64).ravel()
+    n = float(np.linalg.norm(ref))
+    return float(np.linalg.norm(x - ref)) / n if n > 0 else float(np.linalg.norm(x - ref))
+
+
+def golden_seq_frames(golden):
+    """The 10 sequence frames of the fixture (rolls of frame random0, see oracle/make_golden.py)."""
+    base = golden["frame_random0"]
+    return [np.roll(base, tuple(int(v) for v in s), axis=(0, 1)) for s in golden["seq_shifts"]]
