@@ -44,6 +44,7 @@ OTHER = {
     "arl_last_error": ([], ctypes.c_char_p),
     "arl_version": ([], c_int),
     "arl_backward_workspace_bytes": ([c_int], c_i64),
+    "arl_launch_count": ([c_int], c_i64),
 }
 EXPORTS = tuple(SIGNATURES) + tuple(OTHER)
 
@@ -117,6 +118,11 @@ def param_layout(action_size):
     off = (c_i64 * 11)()
     check(load().arl_param_layout(int(action_size), off), "arl_param_layout")
     return list(off)
+
+
+def launch_count(reset=False):
+    """Kernels launched by the library so far in this process."""
+    return int(load().arl_launch_count(1 if reset else 0))
 
 
 def workspace_bytes(action_size):

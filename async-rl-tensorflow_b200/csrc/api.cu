@@ -20,6 +20,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return ARL_ERR_CUDA;
 }
 
+static long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
+
 static int g_num_sms = 0;
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 
@@ -33,6 +36,11 @@ using namespace arl;
 
 extern "C" const char* arl_last_error(void) { return g_err; }
 extern "C" int arl_version(void) { return 100; }
+extern "C" int64_t arl_launch_count(int reset) {
+  const long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_launches, 0, __ATOMIC_RELAXED);
+  return (int64_t)v;
+}
 
 extern "C" int arl_init(int device) {
   int count = 0;

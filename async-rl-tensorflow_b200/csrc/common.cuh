@@ -12,6 +12,7 @@ namespace arl {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
+void count_launch();
 
 #define ARL_REQUIRE(cond, ...)                       \
   do {                                               \
@@ -31,6 +32,7 @@ int num_sms();
   do {                                                             \
     cudaError_t e__ = cudaGetLastError();                          \
     if (e__ != cudaSuccess) return arl::cuda_fail(e__, name);      \
+    arl::count_launch();                                           \
   } while (0)
 
 // flat parameter layout (floats)

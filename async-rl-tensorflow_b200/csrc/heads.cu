@@ -24,7 +24,7 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
   extern __shared__ __align__(16) float sm[];
   const int J = A + 1;
   float* wt = sm;                       // [J][257]
-  float* hs = wt + J * 257;             // [16][256]
+  float* hs = wt + ((J * 257 + 3) & ~3); // [16][256], 16-byte aligned
   float* zs = hs + kHfSamples * 256;    // [16][J]
   const int tid = threadIdx.x;
   for (int i = tid; i < 256 * A; i += kHfThreads) {
@@ -240,7 +240,7 @@ int heads_init() {
   const int J = ARL_MAX_ACTIONS + 1;
   ARL_CUDA(cudaFuncSetAttribute(
       heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-      (int)((J * 257 + kHfSamples * 256 + kHfSamples * J) * sizeof(float))));
+      (int)((((J * 257 + 3) & ~3) + kHfSamples * 256 + kHfSamples * J) * sizeof(float))));
   return ARL_OK;
 }
 
@@ -261,7 +261,8 @@ extern "C" int arl_heads_forward(const float* params, int action_size, const flo
   if (num_samples == 0) return ARL_OK;
   const ParamLayout L = param_layout(action_size);
   const int J = action_size + 1;
-  const size_t smem = (size_t)(J * 257 + kHfSamples * 256 + kHfSamples * J) * sizeof(float);
+  const size_t smem =
+      (size_t)(((J * 257 + 3) & ~3) + kHfSamples * 256 + kHfSamples * J) * sizeof(float);
   const int64_t tiles = (num_samples + kHfSamples - 1) / kHfSamples;
   const int grid = (int)(tiles < 4LL * num_sms() ? tiles : 4LL * num_sms());
   heads_fwd_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(

@@ -68,7 +68,12 @@ class SyntheticAtari(object):
         if self.host:
             self._frames = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
             self._frames.copy_(frames)
-            self._stage = torch.empty((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device)
+            # double-buffered staging: the upload of step i+1 overlaps the compute of step i
+            self._stage = [torch.empty((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device)
+                           for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ready = [None, None]
+            self._staged_for = [-1, -1]
             del frames
         else:
             self._frames = frames
@@ -78,12 +83,28 @@ class SyntheticAtari(object):
         self.action_space = _ActionSpace(self, int(action_size))
         self.h2d_bytes_per_step = B * FRAME_SHAPE[0] * FRAME_SHAPE[1] * FRAME_SHAPE[2] if host else 0
 
+    def _upload(self, i):
+        """Queue the pinned-host -> device copy of step i's frames on the copy stream.  The copy
+        first waits for everything already queued on the compute stream, which includes every
+        reader of the buffer's previous content (step i-2)."""
+        k = i & 1
+        if self._staged_for[k] == i:
+            return
+        self._copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[k].copy_(self._frames[i % self.pool], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._ready[k], self._staged_for[k] = ev, i
+
     def _frame(self, i):
-        f = self._frames[i % self.pool]
-        if self.host:
-            self._stage.copy_(f, non_blocking=True)
-            return self._stage
-        return f
+        if not self.host:
+            return self._frames[i % self.pool]
+        self._upload(i)
+        k = i & 1
+        torch.cuda.current_stream().wait_event(self._ready[k])
+        self._upload(i + 1)                                      # prefetch the next step
+        return self._stage[k]
 
     def reset(self, mask=None):
         return self._frame(self._i)

@@ -30,6 +30,7 @@ class History(object):
         self.ring = torch.zeros(self.num_envs, self.ring_slots, SCREEN, SCREEN,
                                 dtype=torch.uint8, device=self.device)   # history.py:10-11
         self.head = self.ring_slots - 1
+        self.timer = None
 
     # -- reference API ------------------------------------------------------------------
     def add(self, screen, replicate=1):
@@ -39,9 +40,12 @@ class History(object):
         if tuple(screen.shape[1:]) == FRAME_SHAPE:
             if screen.dtype != torch.uint8:
                 raise TypeError("frames must be uint8")
-            _cabi.call("arl_preprocess_push", _cabi.ptr(screen), _cabi.ptr(self.ring),
-                       self.num_envs, self.ring_slots, new_head, int(replicate),
-                       _cabi.stream_ptr())
+            args = ("arl_preprocess_push", _cabi.ptr(screen), _cabi.ptr(self.ring),
+                    self.num_envs, self.ring_slots, new_head, int(replicate), _cabi.stream_ptr())
+            if self.timer is not None:
+                self.timer(*args)                    # bench.py: event pair around K1
+            else:
+                _cabi.call(*args)
         elif tuple(screen.shape[1:]) == (SCREEN, SCREEN):
             for r in range(replicate):
                 self.ring[:, (new_head + r) % self.ring_slots].copy_(screen)

@@ -105,6 +105,7 @@ class Network(object):
         self.workspace = torch.empty(_cabi.workspace_bytes(A), dtype=torch.uint8, device=dev)
         self.loss_sums = torch.zeros(3, **f32)                # sum policy / value loss, entropy
         self.grad_norms = torch.zeros(len(PARAM_NAMES), **f32)
+        self.events = {}
 
     # -- parameters -----------------------------------------------------------------------
     def set_weights(self, weights):
@@ -125,14 +126,41 @@ class Network(object):
         B = self.num_envs
         return slice(t * B, (t + 1) * B)
 
+    # Optional per-entry timing (bench.py): ``timed`` is a set of C-ABI entry names (or {'*'});
+    # the composed arl_forward/arl_backward are then issued as their per-layer entries -- the
+    # same kernels in the same order -- with a CUDA-event pair around each selected entry.
+    timed = None
+
+    def _timed_call(self, name, *args):
+        if self.timed is not None and (name in self.timed or '*' in self.timed):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _cabi.call(name, *args)
+            e1.record()
+            self.events.setdefault(name, []).append((e0, e1))
+        else:
+            _cabi.call(name, *args)
+
+    def _forward_into(self, history, l1, l2, l4, logits, probs, value):
+        P, st = _cabi.ptr, _cabi.stream_ptr()
+        B, A = self.num_envs, self.action_size
+        if self.timed is None:
+            _cabi.call("arl_forward", P(self.params), A, P(history.ring), B, history.ring_slots,
+                       history.first_slot(0), 1, P(l1), P(l2), P(l4), P(logits), P(probs),
+                       P(value), st)
+            return
+        self._timed_call("arl_conv1_forward", P(self.params), P(history.ring), P(l1), B,
+                         history.ring_slots, history.first_slot(0), 1, st)
+        self._timed_call("arl_conv2_forward", P(self.params), P(l1), P(l2), B, st)
+        self._timed_call("arl_fc_forward", P(self.params), P(l2), P(l4), B, st)
+        self._timed_call("arl_heads_forward", P(self.params), A, P(l4), P(logits), P(probs),
+                         P(value), B, st)
+
     def forward(self, history, t):
         """Forward of the current stack into rollout slot ``t``; returns (logits, policy, value)."""
         r = self._rows(t)
-        _cabi.call("arl_forward", _cabi.ptr(self.params), self.action_size,
-                   _cabi.ptr(history.ring), self.num_envs, history.ring_slots,
-                   history.first_slot(0), 1, _cabi.ptr(self.l1[r]), _cabi.ptr(self.l2[r]),
-                   _cabi.ptr(self.l4[r]), _cabi.ptr(self.policy_logits[r]),
-                   _cabi.ptr(self.policy[r]), _cabi.ptr(self.value[r]), _cabi.stream_ptr())
+        self._forward_into(history, self.l1[r], self.l2[r], self.l4[r], self.policy_logits[r],
+                           self.policy[r], self.value[r])
         return self.policy_logits[r], self.policy[r], self.value[r]
 
     def sample(self, t, step, seed, env_id_base=0):
@@ -146,11 +174,7 @@ class Network(object):
     def bootstrap_value(self, history):
         """V(s_T) under the same theta (Algorithm 3: R = V(s_t, theta'_v))."""
         b = self._b
-        _cabi.call("arl_forward", _cabi.ptr(self.params), self.action_size,
-                   _cabi.ptr(history.ring), self.num_envs, history.ring_slots,
-                   history.first_slot(0), 1, _cabi.ptr(b['l1']), _cabi.ptr(b['l2']),
-                   _cabi.ptr(b['l4']), _cabi.ptr(b['logits']), _cabi.ptr(b['probs']),
-                   _cabi.ptr(b['value']), _cabi.stream_ptr())
+        self._forward_into(history, b['l1'], b['l2'], b['l4'], b['logits'], b['probs'], b['value'])
         return b['value']
 
     @property
@@ -181,11 +205,22 @@ class Network(object):
                    _cabi.ptr(v_boot), _cabi.ptr(self.R), _cabi.ptr(self.d_logits),
                    _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
                    self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
-        _cabi.call("arl_backward", _cabi.ptr(self.params), A, _cabi.ptr(history.ring), B,
-                   history.ring_slots, history.first_slot(T), T, _cabi.ptr(self.l1),
-                   _cabi.ptr(self.l2), _cabi.ptr(self.l4), _cabi.ptr(self.d_logits),
-                   _cabi.ptr(self.d_value), _cabi.ptr(self.d_l4), _cabi.ptr(self.d_l2),
-                   _cabi.ptr(self.d_l1), _cabi.ptr(self.grads), _cabi.ptr(self.workspace), st)
+        P = _cabi.ptr
+        if self.timed is None:
+            _cabi.call("arl_backward", P(self.params), A, P(history.ring), B, history.ring_slots,
+                       history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
+                       P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
+                       P(self.d_l1), P(self.grads), P(self.workspace), st)
+            return self.grads
+        N = T * B
+        self._timed_call("arl_heads_backward", P(self.params), A, P(self.l4), P(self.d_logits),
+                         P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, st)
+        self._timed_call("arl_fc_backward", P(self.params), P(self.l2), P(self.d_l4), P(self.d_l2),
+                         P(self.grads), P(self.workspace), N, st)
+        self._timed_call("arl_conv2_backward", P(self.params), P(self.l1), P(self.d_l2),
+                         P(self.d_l1), P(self.grads), P(self.workspace), N, st)
+        self._timed_call("arl_conv1_backward", P(history.ring), P(self.d_l1), P(self.grads),
+                         P(self.workspace), B, history.ring_slots, history.first_slot(T), T, st)
         return self.grads
 
     def apply_gradients(self, lr):

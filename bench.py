@@ -1,0 +1,323 @@
+"""bench.py -- env-frames/sec through preprocess + forward + backward + update.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one A3C cycle of the hot path: t_max env steps for every env of this rank
+(K1 preprocess+ring push, forward, action sampling), the bootstrap forward, n-step returns +
+loss gradients, the backward over the t_max*envs samples, [NCCL all-reduce of the gradient at
+N>1], per-tensor clip + RMSProp.  Workload at N=1: BASELINE.json configs[2]/[3] -- 4096 envs
+per GPU, 6-action head, t_max 5, synthetic 210x160x3 uint8 frames (weak scaling: 4096 per GPU).
+
+Prints ONE JSON line (contract in the task statement): value = device-resident throughput,
+e2e = the same cycle through the public API with frames in pinned HOST memory (H2D of every
+frame and D2H of the actions/loss inside the timed region), roofline = the dominant kernel
+timed live with CUDA events, cpu_baseline = the CPU port of the reference path on this box.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_frames_per_sec"
+UNIT = "frames/s"
+
+# algorithmic work per sample / frame (DESIGN.md kernel table)
+ENTRY_WORK = {
+    # entry: (kernel name, flop per sample, algorithmic bytes per sample)
+    "arl_preprocess_push": ("preprocess_kernel", 0.0, 80640 + 7056),
+    "arl_conv1_forward": ("conv1_fwd_kernel", 2.0 * 1638400, 28224 + 25600),
+    "arl_conv2_forward": ("conv2_fwd_kernel", 2.0 * 663552, 25600 + 10368),
+    "arl_fc_forward": ("fc forward", 2.0 * 663552, 10368 + 1024),
+    "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * 7, 1024 + 56),
+    "arl_heads_backward": ("heads_bwd_kernel", 4.0 * 256 * 7, 2048 + 28),
+    "arl_fc_backward": ("fc backward (dgrad+wgrad)", 4.0 * 663552, 2 * 10368 + 1024 + 10368),
+    "arl_conv2_backward": ("conv2 backward (wgrad+dgrad)", 4.0 * 663552, 2 * (25600 + 10368) + 25600),
+    "arl_conv1_backward": ("conv1_wgrad_kernel", 2.0 * 1638400, 28224 + 25600),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json; bf16 figure = sustained)")
+    return dict(hbm=6650.0, tensor=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        busy = [s for s in self.samples if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference(workers, t_max, actions, steps, warmup, cycles_per_step):
+    """The reference's CPU ps/worker path (oracle/cpu_ref.py port), in a subprocess tree."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_ref.py"), "--workers", str(workers),
+           "--t-max", str(t_max), "--actions", str(actions), "--steps", str(steps),
+           "--warmup", str(warmup), "--cycles-per-step", str(cycles_per_step)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("cpu_ref failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    cyc = args.ref_cycles_per_step
+    res = cpu_reference(cores, args.t_max, args.actions, args.steps, max(args.warmup, 1), cyc)
+    total_t = sum(res["step_seconds"])
+    value = res["frames_per_step"] * len(res["step_seconds"]) / total_t
+    sample = ("%d worker processes (1 env, 1 torch thread each, shared hogwild parameter block) x "
+              "%d cycles of t_max=%d frames per step" % (cores, cyc, args.t_max))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / len(res["step_seconds"]), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, ref=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, ref=False):
+    return {"workload": "A3C full update, %d envs/GPU, conv16-conv32-fc256, %d-action head, "
+                        "t_max %d, history 4, shared RMSProp (BASELINE.json configs[2]/[3])"
+                        % (args.envs, args.actions, args.t_max),
+            "envs_per_gpu": args.envs, "t_max": args.t_max, "action_size": args.actions,
+            "frame": "210x160x3 uint8", "frames_per_step_per_gpu": args.envs * args.t_max,
+            "l2_policy": "inputs larger than L2: each env step reads %d MB of fresh frames"
+                         % (args.envs * 100800 // 2 ** 20),
+            "parallelism": "dp%d (env-sharded, one NCCL all-reduce of the 2.7 MB gradient per step)"
+                           % args.gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--t-max", type=int, default=5)
+    ap.add_argument("--actions", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-cycles-per-step", type=int, default=40)
+    ap.add_argument("--profile-all", action="store_true", help="print per-entry times to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    # CPU baseline first (rank 0 at N=1 only), before this process touches CUDA
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        try:
+            res = cpu_reference(cores, args.t_max, args.actions, 2, 1, 40)
+            cpu_base = {"value": res["frames_per_sec"], "unit": UNIT, "cores": cores,
+                        "kind": "port",
+                        "sample": "%d workers x 2 timed steps x 40 cycles x t_max %d = %d frames "
+                                  "(%.1f s)" % (cores, args.t_max, 2 * res["frames_per_step"],
+                                                sum(res["step_seconds"]))}
+        except Exception as e:                                  # report, never fake
+            cpu_base = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "failed: %s" % str(e)[:200]}
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("async-rl-tensorflow_b200")
+    cabi = pkg._cabi
+    peaks = load_peaks()
+    B, T, A, K, W = args.envs, args.t_max, args.actions, args.steps, args.warmup
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T})
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def make_agent(host):
+        env = pkg.GymEnvironment(cfg, env=pkg.SyntheticAtari(B, A, seed=123 + rank, pool=T,
+                                                             device=dev, host=host), device=dev)
+        agent = pkg.Agent(cfg, env, device=dev)
+        agent.before_train()
+        return agent, env
+
+    def cycle(agent, env, d2h=None):
+        for _ in range(T):
+            action = agent.predict()
+            if d2h is not None:                                  # a host-side emulator needs them
+                d2h["actions"].copy_(action, non_blocking=True)
+            scr, rew, term = env.act(action, is_training=True, fused=True)
+            agent.observe(scr, rew, action, term)
+            agent.step += 1
+        if d2h is not None:
+            d2h["loss"].copy_(agent.network.loss_sums, non_blocking=True)
+            torch.cuda.current_stream().synchronize()           # the caller reads the loss
+
+    def timed(agent, env, d2h=None, sampler=None):
+        for _ in range(W):
+            cycle(agent, env, d2h)
+        barrier()
+        if sampler:
+            sampler.start()
+        cabi.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            cycle(agent, env, d2h)
+        e1.record()
+        barrier()
+        launches = cabi.launch_count()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    # ---- arm 1: inputs resident in HBM ----------------------------------------------------
+    agent, env = make_agent(host=False)
+    net = agent.network
+    # find the dominant entry with one event-timed cycle (untimed region)
+    net.timed, net.events = {"*"}, {}
+    k1_events = []
+
+    def k1_timer(name, *a):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(); cabi.call(name, *a); eb.record()
+        k1_events.append((ea, eb))
+    agent.history.timer = k1_timer
+    for _ in range(2):
+        cycle(agent, env)
+    torch.cuda.synchronize()
+    net.events, k1_events[:] = {}, []
+    cycle(agent, env)
+    torch.cuda.synchronize()
+    per_entry = {n: sum(a.elapsed_time(b) for a, b in ev) for n, ev in net.events.items()}
+    per_entry["arl_preprocess_push"] = sum(a.elapsed_time(b) for a, b in k1_events)
+    dominant = max(per_entry, key=per_entry.get)
+    if args.profile_all and rank == 0:
+        print("per-entry ms per step:", json.dumps({k: round(v, 4) for k, v in
+                                                    sorted(per_entry.items(), key=lambda x: -x[1])}),
+              file=sys.stderr)
+    # timed region: events only around the dominant entry
+    net.timed, net.events, k1_events[:] = {dominant}, {}, []
+    if dominant != "arl_preprocess_push":
+        agent.history.timer = None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches = timed(agent, env, sampler=sampler)
+    clocks = sampler.finish() if sampler else None
+    ev = k1_events if dominant == "arl_preprocess_push" else net.events.get(dominant, [])
+    ev = ev[-(len(ev) * K // (K + W)) if W else 0:] if ev else ev      # timed-region launches only
+    dom_ms = [a.elapsed_time(b) for a, b in ev]
+    value = world * B * T * K / (ms_total * 1e-3)
+    net.timed, agent.history.timer = None, None
+
+    kname, flop_per, bytes_per = ENTRY_WORK[dominant]
+    samples_per_launch = B * T if dominant.endswith("_backward") else B
+    avg_ms = sum(dom_ms) / len(dom_ms) if dom_ms else None
+    if dominant == "arl_preprocess_push":
+        bound, unit, peak = "hbm", "GB/s", peaks["hbm"]
+        achieved = bytes_per * samples_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else None
+    else:
+        bound, unit, peak = "tensor", "TFLOP/s", peaks["tensor"]
+        achieved = flop_per * samples_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms else None
+    roofline = {"kernel": kname, "entry": dominant, "bound": bound, "achieved": achieved,
+                "peak": peak, "unit": unit, "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": len(dom_ms),
+                "share_of_step": (per_entry[dominant] / sum(per_entry.values())),
+                "peak_source": peaks["source"]}
+    if bound == "tensor":
+        roofline["note"] = ("CUDA-core FFMA kernel this round; fp32 FFMA peak 148 SM x 128 x 2 x "
+                            "1.965 GHz = 74.4 TFLOP/s")
+        roofline["fp32_ffma_frac"] = (achieved / 74.4) if achieved else None
+    del agent, env, net
+    torch.cuda.empty_cache()
+
+    # ---- arm 2: end to end through the public API with HOST frames --------------------------
+    e2e = None
+    if not args.no_e2e:
+        agent, env = make_agent(host=True)
+        d2h = {"actions": torch.empty(B, dtype=torch.int32, pin_memory=True),
+               "loss": torch.empty(3, dtype=torch.float32, pin_memory=True)}
+        ms_e2e, _ = timed(agent, env, d2h=d2h)
+        e2e = {"value": world * B * T * K / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": T * B * 100800, "d2h_bytes_per_step": T * B * 4 + 12,
+               "ms_per_step": ms_e2e / K,
+               "note": "frames in pinned host memory, double-buffered upload; PCIe-bound"}
+        del agent, env
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,8 @@ typedef enum {
 /* Thread-local message of the last failing call on this thread. */
 ARL_API const char* arl_last_error(void);
 ARL_API int arl_version(void);
+/* Number of kernels this library has launched in this process (optionally reset to 0). */
+ARL_API int64_t arl_launch_count(int reset);
 
 /* One-time per-process set-up on `device`: derives the luma correction bitmap
  * (the 774 RGB triples where the reference's float64 luma truncates one below the
