@@ -28,6 +28,7 @@ SIGNATURES = {
     "arl_heads_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_forward": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                     c_vp, c_vp],
+    "arl_debug_gemm": [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_sample_actions": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_u64, c_vp],
     "arl_greedy_actions": [c_vp, c_vp, c_int, c_int, c_vp],
     "arl_returns_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,

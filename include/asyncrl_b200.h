@@ -105,6 +105,14 @@ ARL_API int arl_forward(const float* params, int action_size, const uint8_t* rin
                 int ring_slots, int first_slot, int steps, float* a1, float* a2, float* h,
                 float* logits, float* probs, float* value, void* stream);
 
+/* Test hook for the tcgen05 GEMM behind arl_fc_forward/backward (fp32 operands, bf16x3 split,
+ * fp32 accumulation in TMEM), on caller-chosen shapes.  N % 16 == 0, K % 8 == 0.
+ *   variant 0/1: D[M,N] = relu(A[M,K] . B[K,N] + extra[N])            (N tile 256 / 64)
+ *   variant 2  : D[M,N] = (A[M,K] . B[N,K]^T) where extra[M,N] > 0, else 0
+ *   variant 3  : D[z][M,N] = A[K,M]^T . B[K,N] over split-K slice z  (M % 8 == 0) */
+ARL_API int arl_debug_gemm(int variant, const float* A, const float* B, float* D, const float* extra,
+                           int M, int N, int K, int k_splits, void* stream);
+
 /* ---- K4: action sampling, returns, loss gradients -----------------------------------
  * network.py:72 batch_sample(policy) (undefined in the reference): Philox4x32-10 keyed
  * (seed; env_id_base + b, step), inverse CDF over the f32 running sum.  actions i32. */
