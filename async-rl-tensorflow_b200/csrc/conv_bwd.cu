@@ -12,201 +12,6 @@
 
 namespace arl {
 
-// =============================== conv1 forward ============================================
-// CTA = 256 threads, 3 samples per tile (80 threads each: oy 0..19 x half-row x co-half),
-// thread tile 10 ox x 8 co.  smem: 3 x 4 planes u8 (TMA bulk copies) + W1/255 + bias.
-constexpr int kC1Samples = 3;
-constexpr int kC1Threads = 256;
-struct __align__(16) Conv1FwdSmem {
-  uint8_t planes[kC1Samples][4][kPlane];   // 84 672 B
-  float w[8 * 8 * 4 * 16];                 // [kh][kw][c][co], pre-scaled by 1/255
-  float b[16];
-  uint64_t bar;
-};
-
-__global__ void __launch_bounds__(kC1Threads, 2)
-conv1_fwd_kernel(const float* __restrict__ params, const uint8_t* __restrict__ ring,
-                 float* __restrict__ a1, int num_envs, int ring_slots, int first_slot,
-                 int64_t num_samples) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  Conv1FwdSmem& sm = *reinterpret_cast<Conv1FwdSmem*>(smem_raw);
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 4096; i += kC1Threads) sm.w[i] = params[i] * (1.0f / 255.0f);
-  if (tid < 16) sm.b[tid] = params[4096 + tid];
-  if (tid == 0) {
-    mbar_init(&sm.bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int s = tid / 80, r = tid - s * 80;
-  const int oy = r >> 2, xh = (r >> 1) & 1, coh = r & 1;
-  const bool active = tid < 240;
-  const int64_t num_tiles = (num_samples + kC1Samples - 1) / kC1Samples;
-  uint32_t phase = 0;
-
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t n0 = tile * kC1Samples;
-    const int ns = (int)((num_samples - n0) < kC1Samples ? (num_samples - n0) : kC1Samples);
-    if (tid == 0) {
-      mbar_expect_tx(&sm.bar, (uint32_t)(ns * 4 * kPlane));
-      for (int j = 0; j < ns; ++j) {
-        const int64_t n = n0 + j;
-        const int t = (int)(n / num_envs), b = (int)(n - (int64_t)t * num_envs);
-        for (int k = 0; k < 4; ++k) {
-          const int slot = (first_slot + t + k) % ring_slots;
-          bulk_g2s(sm.planes[j][k], ring + ((size_t)b * ring_slots + slot) * kPlane, kPlane,
-                   &sm.bar);
-        }
-      }
-    }
-    mbar_wait(&sm.bar, phase);
-    phase ^= 1;
-
-    if (active && s < ns) {
-      float acc[10][8];
-#pragma unroll
-      for (int j = 0; j < 10; ++j)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = sm.b[coh * 8 + c];
-
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll 1
-        for (int kh = 0; kh < 8; ++kh) {
-          const uint32_t* row = reinterpret_cast<const uint32_t*>(
-              &sm.planes[s][c][(4 * oy + kh) * ARL_SCREEN + 40 * xh]);
-          uint32_t wd[11];
-#pragma unroll
-          for (int i = 0; i < 11; ++i) wd[i] = row[i];
-          const float* wp = &sm.w[((kh * 8) * 4 + c) * 16 + coh * 8];
-#pragma unroll
-          for (int kw = 0; kw < 8; ++kw) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 64);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + kw * 64 + 4);
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-              const int bi = 4 * j + kw;
-              const float x = (float)((wd[bi >> 2] >> (8 * (bi & 3))) & 0xFFu);
-              acc[j][0] = fmaf(x, w0.x, acc[j][0]);
-              acc[j][1] = fmaf(x, w0.y, acc[j][1]);
-              acc[j][2] = fmaf(x, w0.z, acc[j][2]);
-              acc[j][3] = fmaf(x, w0.w, acc[j][3]);
-              acc[j][4] = fmaf(x, w1.x, acc[j][4]);
-              acc[j][5] = fmaf(x, w1.y, acc[j][5]);
-              acc[j][6] = fmaf(x, w1.z, acc[j][6]);
-              acc[j][7] = fmaf(x, w1.w, acc[j][7]);
-            }
-          }
-        }
-      }
-      float* out = a1 + ((n0 + s) * 400 + oy * 20 + xh * 10) * 16 + coh * 8;
-#pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        float4 v0 = make_float4(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f),
-                                fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
-        float4 v1 = make_float4(fmaxf(acc[j][4], 0.f), fmaxf(acc[j][5], 0.f),
-                                fmaxf(acc[j][6], 0.f), fmaxf(acc[j][7], 0.f));
-        *reinterpret_cast<float4*>(out + j * 16) = v0;
-        *reinterpret_cast<float4*>(out + j * 16 + 4) = v1;
-      }
-    }
-    __syncthreads();   // planes are free for the next tile's bulk copies
-  }
-}
-
-// =============================== conv2 forward ============================================
-// CTA = 128 threads, 3 samples per tile (36 threads each: oy 0..8 x co-quarter),
-// thread tile 9 ox x 8 co.  a1 rows are padded to 321 floats in smem so that the
-// stride-2-rows access of the 8 oy-lanes of a warp hits distinct banks.
-constexpr int kC2Samples = 3;
-constexpr int kC2Threads = 128;
-constexpr int kA1Row = 321;                  // 20 px * 16 ch + 1 pad
-constexpr int kA1Smem = 20 * kA1Row;         // 6420 floats per sample
-struct __align__(16) Conv2FwdSmem {
-  float w[4 * 4 * 16 * 32];                  // 32 KB [kh][kw][c][co]
-  float a[kC2Samples][kA1Smem];              // 77 040 B
-  float b[32];
-};
-
-__global__ void __launch_bounds__(kC2Threads, 2)
-conv2_fwd_kernel(const float* __restrict__ params, const float* __restrict__ a1,
-                 float* __restrict__ a2, int64_t num_samples) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  Conv2FwdSmem& sm = *reinterpret_cast<Conv2FwdSmem*>(smem_raw);
-  const int tid = threadIdx.x;
-  const float* w2 = params + 4096 + 16;
-  for (int i = tid; i < 8192 / 4; i += kC2Threads)
-    reinterpret_cast<float4*>(sm.w)[i] = reinterpret_cast<const float4*>(w2)[i];
-  if (tid < 32) sm.b[tid] = w2[8192 + tid];
-
-  const int s = tid / 36, r = tid - s * 36;
-  const int oy = r >> 2, cq = r & 3;
-  const bool active = tid < 108;
-  const int64_t num_tiles = (num_samples + kC2Samples - 1) / kC2Samples;
-
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t n0 = tile * kC2Samples;
-    const int ns = (int)((num_samples - n0) < kC2Samples ? (num_samples - n0) : kC2Samples);
-    __syncthreads();   // previous tile fully consumed (also orders the weight fill)
-    const float4* src = reinterpret_cast<const float4*>(a1 + n0 * ARL_A1_ELEMS);
-    for (int i = tid; i < ns * (ARL_A1_ELEMS / 4); i += kC2Threads) {
-      const float4 v = src[i];
-      const int j = i / 1600, e = (i - j * 1600) * 4;      // element within the sample
-      const int row = e / 320, col = e - row * 320;
-      float* d = &sm.a[j][row * kA1Row + col];
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    __syncthreads();
-
-    if (active && s < ns) {
-      float acc[9][8];
-#pragma unroll
-      for (int j = 0; j < 9; ++j)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = sm.b[cq * 8 + c];
-
-#pragma unroll 1
-      for (int kh = 0; kh < 4; ++kh) {
-#pragma unroll 1
-        for (int c = 0; c < 16; ++c) {
-          const float* row = &sm.a[s][(2 * oy + kh) * kA1Row + c];
-          float in[20];
-#pragma unroll
-          for (int x = 0; x < 20; ++x) in[x] = row[x * 16];
-          const float* wp = &sm.w[((kh * 4) * 16 + c) * 32 + cq * 8];
-#pragma unroll
-          for (int kw = 0; kw < 4; ++kw) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 512);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + kw * 512 + 4);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-              const float x = in[2 * j + kw];
-              acc[j][0] = fmaf(x, w0.x, acc[j][0]);
-              acc[j][1] = fmaf(x, w0.y, acc[j][1]);
-              acc[j][2] = fmaf(x, w0.z, acc[j][2]);
-              acc[j][3] = fmaf(x, w0.w, acc[j][3]);
-              acc[j][4] = fmaf(x, w1.x, acc[j][4]);
-              acc[j][5] = fmaf(x, w1.y, acc[j][5]);
-              acc[j][6] = fmaf(x, w1.z, acc[j][6]);
-              acc[j][7] = fmaf(x, w1.w, acc[j][7]);
-            }
-          }
-        }
-      }
-      float* out = a2 + (n0 + s) * ARL_A2_ELEMS + (oy * 9) * 32 + cq * 8;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        *reinterpret_cast<float4*>(out + j * 32) =
-            make_float4(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f), fmaxf(acc[j][2], 0.f),
-                        fmaxf(acc[j][3], 0.f));
-        *reinterpret_cast<float4*>(out + j * 32 + 4) =
-            make_float4(fmaxf(acc[j][4], 0.f), fmaxf(acc[j][5], 0.f), fmaxf(acc[j][6], 0.f),
-                        fmaxf(acc[j][7], 0.f));
-      }
-    }
-  }
-}
-
 // =============================== conv1 weight gradient =====================================
 // dW1[kh][kw][c][co] = sum_{n,oy,ox} x[n][c][4oy+kh][4ox+kw]/255 * dy1[n][oy][ox][co]
 // (dy1 = gradient w.r.t. the conv1 pre-activation, i.e. already relu-masked).
@@ -544,10 +349,6 @@ int reduce_partials(const float* partials, float* out, int num_partials, int n,
 }
 
 int conv_init() {
-  ARL_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(Conv1FwdSmem)));
-  ARL_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(Conv2FwdSmem)));
   ARL_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(Conv1WgradSmem)));
   ARL_CUDA(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -564,40 +365,6 @@ int wgrad_grid() { return num_sms(); }
 using namespace arl;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-extern "C" int arl_conv1_forward(const float* params, const uint8_t* ring, float* a1, int num_envs,
-                                 int ring_slots, int first_slot, int steps, void* stream) {
-  ARL_REQUIRE(params && ring && a1, "arl_conv1_forward: null pointer");
-  ARL_REQUIRE(num_envs >= 0 && steps >= 0, "arl_conv1_forward: negative size");
-  ARL_REQUIRE(ring_slots >= steps + 3 && first_slot >= 0 && first_slot < ring_slots,
-              "arl_conv1_forward: ring_slots %d must be >= steps+3 (%d) and first_slot %d inside it",
-              ring_slots, steps + 3, first_slot);
-  ARL_REQUIRE(aligned16(params) && aligned16(ring) && aligned16(a1),
-              "arl_conv1_forward: pointers must be 16-byte aligned");
-  const int64_t N = (int64_t)num_envs * steps;
-  if (N == 0) return ARL_OK;
-  const int64_t tiles = (N + kC1Samples - 1) / kC1Samples;
-  const int grid = (int)(tiles < 2LL * num_sms() ? tiles : 2LL * num_sms());
-  conv1_fwd_kernel<<<grid, kC1Threads, sizeof(Conv1FwdSmem), (cudaStream_t)stream>>>(
-      params, ring, a1, num_envs, ring_slots, first_slot, N);
-  ARL_LAUNCH_CHECK("conv1_fwd_kernel");
-  return ARL_OK;
-}
-
-extern "C" int arl_conv2_forward(const float* params, const float* a1, float* a2,
-                                 int64_t num_samples, void* stream) {
-  ARL_REQUIRE(params && a1 && a2, "arl_conv2_forward: null pointer");
-  ARL_REQUIRE(num_samples >= 0, "arl_conv2_forward: negative size");
-  ARL_REQUIRE(aligned16(params) && aligned16(a1) && aligned16(a2),
-              "arl_conv2_forward: pointers must be 16-byte aligned");
-  if (num_samples == 0) return ARL_OK;
-  const int64_t tiles = (num_samples + kC2Samples - 1) / kC2Samples;
-  const int grid = (int)(tiles < 2LL * num_sms() ? tiles : 2LL * num_sms());
-  conv2_fwd_kernel<<<grid, kC2Threads, sizeof(Conv2FwdSmem), (cudaStream_t)stream>>>(
-      params, a1, a2, num_samples);
-  ARL_LAUNCH_CHECK("conv2_fwd_kernel");
-  return ARL_OK;
-}
 
 extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads,
                                   void* workspace, int num_envs, int ring_slots, int first_slot,

@@ -26,34 +26,32 @@ __global__ void colsum256_kernel(const float* __restrict__ X, float* __restrict_
   partials[(size_t)blockIdx.x * 256 + col] = s0 + s1;
 }
 
-constexpr int kKB = 32;
-
-static int desc_swap_flag() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ARL_DESC_SWAP");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
-
+// KB per variant: 8 stages must fit in 227 KB (N tile 256 -> KB 16, N tile 64 -> KB 32)
 int fc_gemm(int variant, const float* A, const float* B, float* D, const float* extra, int M, int N,
             int K, int64_t lda, int64_t ldb, int64_t ldd, int k_splits, cudaStream_t st) {
   tc::GemmArgs g;
   g.A = A; g.B = B; g.D = D; g.extra = extra;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  const int n_tile = variant == 1 ? 64 : 256, kb = variant == 1 ? 32 : 16;
   if (k_splits < 1) k_splits = 1;
-  int k_chunk = ((K + k_splits - 1) / k_splits + kKB - 1) / kKB * kKB;
-  g.k_chunk = k_chunk;
-  g.k_splits = (K + k_chunk - 1) / k_chunk;
-  g.desc_swap = desc_swap_flag();
+  g.k_chunk = ((K + k_splits - 1) / k_splits + kb - 1) / kb * kb;
+  g.k_splits = (K + g.k_chunk - 1) / g.k_chunk;
+  g.m_tiles = (M + tc::kTileM - 1) / tc::kTileM;
+  g.n_tiles = (N + n_tile - 1) / n_tile;
+  const int items = g.m_tiles * g.n_tiles * g.k_splits;
   switch (variant) {
-    case 0: return tc::launch_gemm<256, kKB, 4, false, true, tc::EPI_BIAS_RELU>(g, st);
-    case 1: return tc::launch_gemm<64, kKB, 6, false, true, tc::EPI_BIAS_RELU>(g, st);
-    case 2: return tc::launch_gemm<256, kKB, 4, false, false, tc::EPI_MASK>(g, st);
-    case 3: return tc::launch_gemm<256, kKB, 4, true, true, tc::EPI_PLAIN>(g, st);
+    case 0: return tc::launch<tc::GemmPolicy<256, 16, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
+    case 1: return tc::launch<tc::GemmPolicy<64, 32, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
+    case 2: return tc::launch<tc::GemmPolicy<256, 16, false, false, tc::EPI_MASK>>(g, items, st);
+    case 3: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN>>(g, items, st);
     default: set_error("fc_gemm: unknown variant %d", variant); return ARL_ERR_INVALID;
   }
+}
+
+// number of split-K slices fc_gemm(variant 3) produces for K samples and a request of `want`
+int fc_wgrad_splits(int K, int want) {
+  const int k_chunk = ((K + want - 1) / want + 15) / 16 * 16;
+  return (K + k_chunk - 1) / k_chunk;
 }
 
 }  // namespace arl
@@ -119,8 +117,7 @@ extern "C" int arl_fc_backward(const float* params, const float* a2, const float
   float* part = (float*)workspace;
   rc = fc_gemm(3, a2, d_h, part, nullptr, ARL_A2_ELEMS, ARL_FC, M, ARL_A2_ELEMS, ARL_FC, ARL_FC, 7, st);
   if (rc) return rc;
-  const int k_chunk = ((M + 6) / 7 + kKB - 1) / kKB * kKB;
-  const int splits = (M + k_chunk - 1) / k_chunk;
+  const int splits = fc_wgrad_splits(M, 7);
   rc = reduce_partials(part, gW, splits, ARL_A2_ELEMS * ARL_FC, st);
   if (rc) return rc;
   // bias grad

@@ -77,7 +77,16 @@ def to_torch(params, dtype=torch.float64, requires_grad=False):
                        for k, v in params.items())
 
 
-def forward(p, s_nhwc, keep=False):
+def _relu(x, mask):
+    """relu, or -- when ``mask`` is given -- x * mask.  Forcing the activation pattern observed
+    on the device removes the one discontinuity of the net from a parity comparison: a
+    pre-activation within rounding distance of 0 would otherwise flip a whole gradient column."""
+    if mask is None:
+        return F.relu(x)
+    return x * torch.as_tensor(mask).to(x.dtype)
+
+
+def forward(p, s_nhwc, keep=False, masks=None):
     """Trunk + heads.  ``s_nhwc``: [N,84,84,4] holding u8 values (any real dtype),
     channel k=0 oldest ... 3 newest (history.py:20-24).
 
@@ -90,10 +99,12 @@ def forward(p, s_nhwc, keep=False):
     """
     dt = p["l1_w"].dtype
     x = torch.as_tensor(s_nhwc).to(dt).permute(0, 3, 1, 2) / 255.0
-    a1 = F.relu(F.conv2d(x, p["l1_w"].permute(3, 2, 0, 1), p["l1_b"], stride=4))
-    a2 = F.relu(F.conv2d(a1, p["l2_w"].permute(3, 2, 0, 1), p["l2_b"], stride=2))
-    flat = a2.permute(0, 2, 3, 1).reshape(a2.shape[0], -1)
-    h = F.relu(flat @ p["l4_w"] + p["l4_b"])
+    m = masks or {}
+    m1 = None if "a1" not in m else torch.as_tensor(m["a1"]).permute(0, 3, 1, 2)
+    a1 = _relu(F.conv2d(x, p["l1_w"].permute(3, 2, 0, 1), p["l1_b"], stride=4), m1)
+    a2 = F.conv2d(a1, p["l2_w"].permute(3, 2, 0, 1), p["l2_b"], stride=2)
+    flat = _relu(a2.permute(0, 2, 3, 1).reshape(a2.shape[0], -1), m.get("a2"))
+    h = _relu(flat @ p["l4_w"] + p["l4_b"], m.get("h"))
     logits = h @ p["p_w"] + p["p_b"]
     value = (h @ p["q_w"] + p["q_b"]).reshape(-1)
     if keep:
@@ -158,13 +169,14 @@ def analytic_head_grads(logits, value, actions, R, beta=0.01, scale=1.0):
     return dlogits * scale, dv * scale
 
 
-def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=torch.float64):
+def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=torch.float64,
+              masks=None):
     """Gradient of  sum_t mean_env total_loss   w.r.t. every
     parameter, by autograd of the loss expression (agent.py:317 compute_gradients).
     stacks [N,84,84,4] (N = T*B, t-major), actions [N], R [N].
     ``num_envs`` = B of the mean (global env count); None -> pure sum."""
     p = to_torch(params_np, dtype, requires_grad=True)
-    logits, value = forward(p, stacks)
+    logits, value = forward(p, stacks, masks=masks)
     Rt = torch.as_tensor(np.asarray(R), dtype=dtype)
     at = torch.as_tensor(np.asarray(actions))
     total, pl, vl = loss_per_sample(logits, value, at, Rt, beta)
@@ -220,7 +232,7 @@ def stacks_from_screens(screens, t_max):
 
 def a3c_cycle(params, rms, screens, actions, rewards, terminals, step, *,
               beta=0.01, gamma=0.99, num_envs=None, max_step=80000000, base_lr=0.0007,
-              reduce_mean=True):
+              reduce_mean=True, masks=None):
     """One REF-A3C cycle (SURVEY §8 normative order, steps 2-10) with the actions
     given (teacher forcing: sampling parity is tested separately on identical probs).
 
@@ -236,7 +248,8 @@ def a3c_cycle(params, rms, screens, actions, rewards, terminals, step, *,
     R = nstep_returns(r, np.asarray(terminals), v_boot.numpy(), gamma)
     n_env = (num_envs if num_envs is not None else B) if reduce_mean else None
     grads, aux = gradients(params, stacks[:T].reshape((T * B,) + stacks.shape[2:]),
-                           np.asarray(actions).reshape(-1), R.reshape(-1), beta, n_env)
+                           np.asarray(actions).reshape(-1), R.reshape(-1), beta, n_env,
+                           masks=masks)
     lr = learning_rate(step, max_step, base_lr)
     new_p, new_r = update(params, rms, grads, lr)
     aux.update(R=R, v_boot=v_boot.numpy(), grads=grads, lr=lr)
