@@ -44,6 +44,7 @@ int fc_gemm(int variant, const float* A, const float* B, float* D, const float* 
     case 1: return tc::launch<tc::GemmPolicy<64, 32, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
     case 2: return tc::launch<tc::GemmPolicy<256, 16, false, false, tc::EPI_MASK>>(g, items, st);
     case 3: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN>>(g, items, st);
+    case 4: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN, true>>(g, items, st);
     default: set_error("fc_gemm: unknown variant %d", variant); return ARL_ERR_INVALID;
   }
 }
@@ -67,12 +68,12 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int arl_debug_gemm(int variant, const float* A, const float* B, float* D,
                               const float* extra, int M, int N, int K, int k_splits, void* stream) {
   ARL_REQUIRE(A && B && D, "arl_debug_gemm: null pointer");
-  ARL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 16 == 0 && (variant == 3 || K % 8 == 0),
+  ARL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 16 == 0 && (variant >= 3 || K % 8 == 0),
               "arl_debug_gemm: need M,N,K > 0, N %% 16 == 0, K %% 8 == 0");
-  ARL_REQUIRE(variant != 3 || M % 8 == 0, "arl_debug_gemm: variant 3 needs M %% 8 == 0");
-  const int64_t lda = variant == 3 ? M : K;
+  ARL_REQUIRE(variant < 3 || M % 8 == 0, "arl_debug_gemm: variants 3/4 need M %% 8 == 0");
+  const int64_t lda = variant >= 3 ? M : K;
   const int64_t ldb = variant == 2 ? K : N;
-  return fc_gemm(variant, A, B, D, extra, M, N, K, lda, ldb, N, variant == 3 ? k_splits : 1,
+  return fc_gemm(variant, A, B, D, extra, M, N, K, lda, ldb, N, variant >= 3 ? k_splits : 1,
                  (cudaStream_t)stream);
 }
 

@@ -10,9 +10,9 @@
 //
 // One persistent CTA per SM, 416 threads:
 //   warps 0-3   epilogue : tcgen05.ld (TMEM lane quadrant = warp id) -> Policy::store -> HBM
-//   warps 4-11  producers: producer warp w owns smem stage w (8 stages): it fills k-blocks
-//                          w, w+8, ... so 8 independent load->convert->store chains are in
-//                          flight; fence.proxy.async + mbarrier arrive hand the stage over
+//   warps 4-11  producers: 8/STAGES warps own each smem stage and fill it independently of the
+//                          other stages (STAGES load->convert->store chains in flight);
+//                          fence.proxy.async + mbarrier arrive hand the stage to the MMA warp
 //   warp 12     MMA      : one thread issues tcgen05.mma (cta_group::1, kind::f16, M=128,
 //                          N=N_TILE, K=16); tcgen05.commit frees the stage / publishes the
 //                          accumulator (2 TMEM accumulator stages); owns tcgen05.alloc/dealloc
@@ -28,7 +28,7 @@
 namespace arl {
 namespace tc {
 
-constexpr int kEpiWarps = 4, kProdWarps = 8, kStages = kProdWarps;
+constexpr int kEpiWarps = 4, kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kThreads = (kEpiWarps + kProdWarps + 1) * 32;   // 416
 constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 12
@@ -84,16 +84,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kTileM >> 4) << 24);
+// instruction descriptor: bf16 x bf16 -> f32, M=128; operands K-major unless *_mn
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
-// shared-memory matrix descriptor: SWIZZLE_NONE, K-major; LBO = byte distance between the two
-// 8-element K chunks of one MMA, SBO = byte distance between 8-row groups
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes) {
+// shared-memory matrix descriptor, SWIZZLE_NONE.  The operand images in this file place the 16-B
+// vector of (index r of the 16-B-strided axis, chunk c of the other axis) at c*PLANE + r*16.
+//   K-major operand : r = row (M/N), c = k/8   -> LBO = PLANE (next K chunk), SBO = 128
+//   MN-major operand: r = k,         c = row/8 -> LBO = 128 (next 8 k), SBO = PLANE (next 8 rows)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                               uint32_t sbo_bytes = 128) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 
 template <int ROWS, int KB>
@@ -190,52 +193,49 @@ __device__ __forceinline__ void load_tile_f32(uint8_t* hi_img, uint8_t* lo_img,
 
 struct TileCoord {
   int mt, nt, ks;        // tile indices (meaning is the policy's)
-  int k_begin, k_end;    // reduction range of this work item
+  int k_begin, k_end;    // reduction range of this work item (meaning is the policy's)
 };
 
 // A Policy provides:
-//   Args; N_TILE; KB; A_HAS_LO; B_RESIDENT; B_RES_K (K extent of a resident B); B_RES_SETS
+//   Args; STAGES (4 or 8); STAGE_BYTES; RES_BYTES (resident smem, e.g. converted weights);
+//   ACC_COLS (TMEM columns of one accumulator set, multiple of 16)
 //   static __device__ int num_items(const Args&)
 //   static __device__ TileCoord coord(const Args&, int item)
-//   static __device__ void load_A(const Args&, const TileCoord&, int k0, uint8_t* hi, uint8_t* lo, int lane)
-//   static __device__ void load_B(const Args&, const TileCoord&, int k0, uint8_t* hi, uint8_t* lo, int lane)   (staged B)
-//   static __device__ void load_B_resident(const Args&, uint8_t* base, int ptid)   (resident B; all 256 producer threads)
-//   static __device__ int b_set(const Args&, const TileCoord&)                      (which resident B)
+//   static __device__ int num_stages(const Args&, const TileCoord&)          stages per item
+//   static __device__ void load_resident(const Args&, uint8_t* res, int ptid)   (256 threads)
+//   static __device__ void load_stage(const Args&, const TileCoord&, int s, uint8_t* stage,
+//                                     int glane, int gsize)     lanes of the stage's warp group
+//   static __device__ void issue(const Args&, const TileCoord&, int s, uint32_t stage_addr,
+//                                uint32_t res_addr, uint32_t d_tmem)   all MMAs of stage s
+//                                (s == 0 must start with accumulate = 0)
 //   static __device__ void store(const Args&, const TileCoord&, int row, int col, const float (&v)[16])
 template <class P>
 struct Smem {
-  using TA = OperandTile<kTileM, P::KB>;
-  using TBs = OperandTile<P::N_TILE, P::KB>;
-  using TBr = OperandTile<P::N_TILE, P::B_RES_K>;
-  static constexpr int A_STAGE = (P::A_HAS_LO ? 2 : 1) * TA::BYTES;
-  static constexpr int B_STAGE = P::B_RESIDENT ? 0 : 2 * TBs::BYTES;
-  static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int B_RES_ONE = 2 * TBr::BYTES;
-  static constexpr int B_RES = P::B_RESIDENT ? B_RES_ONE * P::B_RES_SETS : 0;
-  static constexpr int BAR_OFF = kStages * STAGE + B_RES;
+  static constexpr int BAR_OFF = P::STAGES * P::STAGE_BYTES + P::RES_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 
 template <class P>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
   using S = Smem<P>;
-  using TA = typename S::TA;
-  constexpr int N_TILE = P::N_TILE, KB = P::KB;
+  constexpr int STAGES = P::STAGES, WPS = kProdWarps / STAGES;     // producer warps per stage
+  static_assert(STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* bres = smem + kStages * S::STAGE;
+  uint8_t* res = smem + STAGES * P::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty = full + kStages;
-  uint64_t* tfull = empty + kStages;     // [2]
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;      // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t kTmemCols = 2 * N_TILE <= 32 ? 32 : 2 * N_TILE <= 64 ? 64
-                               : 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
+  constexpr uint32_t kTmemCols = 2 * P::ACC_COLS <= 32 ? 32 : 2 * P::ACC_COLS <= 64 ? 64
+                               : 2 * P::ACC_COLS <= 128 ? 128 : 2 * P::ACC_COLS <= 256 ? 256 : 512;
+  static_assert(2 * P::ACC_COLS <= 512 && P::ACC_COLS % 16 == 0, "TMEM budget");
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 32);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 32 * WPS);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_base_slot, kTmemCols);
-  if (P::B_RESIDENT && warp >= kEpiWarps && warp < kMmaWarp) {
-    P::load_B_resident(g, bres, tid - kEpiWarps * 32);
+  if (P::RES_BYTES > 0 && warp >= kEpiWarps && warp < kMmaWarp) {
+    P::load_resident(g, res, tid - kEpiWarps * 32);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -256,61 +256,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
   const int items = P::num_items(g);
 
   if (warp >= kEpiWarps && warp < kMmaWarp) {
-    // ===================== producers: warp pw owns stage pw =====================
+    // ===================== producers: warp group pg owns stage pg =====================
     const int pw = warp - kEpiWarps;
-    uint8_t* st = smem + pw * S::STAGE;
-    int i = 0;                                         // running k-block index over all items
+    const int pg = pw / WPS, glane = (pw % WPS) * 32 + lane;
+    uint8_t* st = smem + pg * P::STAGE_BYTES;
+    int i = 0;                                         // running stage index over all items
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const TileCoord tc = P::coord(g, item);
-      for (int k0 = tc.k_begin; k0 < tc.k_end; k0 += KB, ++i) {
-        if ((i & (kStages - 1)) != pw) continue;
-        mbar_wait(&empty[pw], ((i >> 3) & 1) ^ 1);
-        P::load_A(g, tc, k0, st, st + TA::BYTES, lane);
-        if (!P::B_RESIDENT)
-          P::load_B(g, tc, k0, st + S::A_STAGE, st + S::A_STAGE + S::TBs::BYTES, lane);
+      const int ns = P::num_stages(g, tc);
+      for (int s = 0; s < ns; ++s, ++i) {
+        if (i % STAGES != pg) continue;
+        mbar_wait(&empty[pg], ((i / STAGES) & 1) ^ 1);
+        P::load_stage(g, tc, s, st, glane, 32 * WPS);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(&full[pw]);
+        mbar_arrive(&full[pg]);
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(N_TILE);
       int i = 0;
       uint32_t acc = 0, acc_phase = 0;
+      const uint32_t res_addr = smem_u32(res);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const TileCoord tc = P::coord(g, item);
+        const int ns = P::num_stages(g, tc);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        uint32_t accumulate = 0;
-        for (int k0 = tc.k_begin; k0 < tc.k_end; k0 += KB, ++i) {
-          const int stage = i & (kStages - 1);
-          mbar_wait(&full[stage], (i >> 3) & 1);
+        const uint32_t d_tmem = tmem_base + acc * P::ACC_COLS;
+        for (int s = 0; s < ns; ++s, ++i) {
+          const int stage = i % STAGES;
+          mbar_wait(&full[stage], (i / STAGES) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * S::STAGE), a_lo = a_hi + TA::BYTES;
-          uint32_t b_hi, b_lo, b_lbo;
-          if (P::B_RESIDENT) {
-            b_lbo = S::TBr::LBO;
-            b_hi = smem_u32(bres) + P::b_set(g, tc) * S::B_RES_ONE +
-                   ((k0 - P::res_k_origin(g, tc)) >> 3) * S::TBr::LBO;
-            b_lo = b_hi + S::TBr::BYTES;
-          } else {
-            b_lbo = S::TBs::LBO;
-            b_hi = a_hi + S::A_STAGE;
-            b_lo = b_hi + S::TBs::BYTES;
-          }
-#pragma unroll
-          for (int k16 = 0; k16 < KB / 16; ++k16) {
-            const uint32_t ao = k16 * 2 * TA::LBO, bo = k16 * 2 * b_lbo;
-            const uint64_t da_hi = make_sdesc(a_hi + ao, TA::LBO);
-            const uint64_t db_hi = make_sdesc(b_hi + bo, b_lbo);
-            const uint64_t db_lo = make_sdesc(b_lo + bo, b_lbo);
-            umma_f16(d_tmem, da_hi, db_hi, idesc, accumulate);
-            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-            if (P::A_HAS_LO) umma_f16(d_tmem, make_sdesc(a_lo + ao, TA::LBO), db_hi, idesc, 1u);
-            accumulate = 1u;
-          }
+          P::issue(g, tc, s, smem_u32(smem + stage * P::STAGE_BYTES), res_addr, d_tmem);
           umma_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
         }
         umma_commit(&tfull[acc]);            // accumulator ready for the epilogue
@@ -326,9 +304,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N_TILE;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * P::ACC_COLS;
 #pragma unroll 1
-      for (int c = 0; c < N_TILE; c += 16) {
+      for (int c = 0; c < P::ACC_COLS; c += 16) {
         float v[16];
         tmem_ld16(taddr + c, v);
         P::store(g, tc, row, c, v);
@@ -352,8 +330,6 @@ template <class P>
 int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   using S = Smem<P>;
   static_assert(S::TOTAL <= 227 * 1024, "smem budget");
-  static_assert(P::N_TILE % 16 == 0 && P::N_TILE >= 16 && P::N_TILE <= 256, "UMMA N");
-  static_assert(P::KB % 16 == 0, "KB");
   auto kern = tc_kernel<P>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -381,12 +357,23 @@ struct GemmArgs {
   int m_tiles, n_tiles;
 };
 
-template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI>
+// MN=false: both operand images K-major (sample-major sources are transposed in registers).
+// MN=true : requires A_TRANS && B_TRANS; the images are MN-major (the natural layout of
+//           sample-major sources: 8 consecutive rows of one k form the 16-B vector).
+template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI, bool MN = false>
 struct GemmPolicy {
   using Args = GemmArgs;
-  static constexpr int N_TILE = N_TILE_, KB = KB_;
-  static constexpr bool A_HAS_LO = true, B_RESIDENT = false;
-  static constexpr int B_RES_K = KB_, B_RES_SETS = 1;
+  static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = 8, ACC_COLS = N_TILE_;
+  using TA = OperandTile<kTileM, KB>;
+  using TB = OperandTile<N_TILE, KB>;
+  // MN-major images: plane = 8 rows x KB k  -> (KB+1)*16 bytes per plane, ROWS/8 planes
+  static constexpr int PLANE_MN = (KB + 1) * 16;
+  static constexpr int A_BYTES = MN ? (kTileM / 8) * PLANE_MN : TA::BYTES;     // one image
+  static constexpr int B_BYTES = MN ? (N_TILE / 8) * PLANE_MN : TB::BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int RES_BYTES = 0;
+  static_assert(!MN || (A_TRANS && B_TRANS), "MN-major images need sample-major sources");
+
   static __device__ __forceinline__ int num_items(const Args& g) {
     return g.m_tiles * g.n_tiles * g.k_splits;
   }
@@ -399,17 +386,62 @@ struct GemmPolicy {
     t.k_end = min(g.K, t.k_begin + g.k_chunk);
     return t;
   }
-  static __device__ __forceinline__ void load_A(const Args& g, const TileCoord& t, int k0,
-                                                uint8_t* hi, uint8_t* lo, int lane) {
-    load_tile_f32<kTileM, KB, A_TRANS>(hi, lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, lane);
+  static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
+    return (t.k_end - t.k_begin + KB - 1) / KB;
   }
-  static __device__ __forceinline__ void load_B(const Args& g, const TileCoord& t, int k0,
-                                                uint8_t* hi, uint8_t* lo, int lane) {
-    load_tile_f32<N_TILE, KB, B_TRANS>(hi, lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, lane);
+  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int) {}
+
+  // MN-major image of a sample-major source: vector (k, row group rg) at rg*PLANE_MN + k*16
+  template <int ROWS>
+  static __device__ __forceinline__ void load_mn(uint8_t* hi, uint8_t* lo, const float* src,
+                                                 int64_t ld, int r0, int rmax, int k0, int kmax,
+                                                 int lane) {
+    for (int c = lane; c < (ROWS / 8) * KB; c += 32) {
+      const int rg = c % (ROWS / 8), kk = c / (ROWS / 8);
+      const int r = r0 + rg * 8, k = k0 + kk;
+      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (r < rmax && k < kmax) {
+        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)k * ld + r);
+        const float4 x0 = p[0], x1 = p[1];
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
+        x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+      }
+      store_chunk_split(hi, lo, rg * PLANE_MN + kk * 16, x);
+    }
   }
-  static __device__ __forceinline__ void load_B_resident(const Args&, uint8_t*, int) {}
-  static __device__ __forceinline__ int b_set(const Args&, const TileCoord&) { return 0; }
-  static __device__ __forceinline__ int res_k_origin(const Args&, const TileCoord&) { return 0; }
+  static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
+                                                    uint8_t* st, int lane, int) {
+    const int k0 = t.k_begin + s * KB;
+    uint8_t* a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = b_hi + B_BYTES;
+    if (MN) {
+      load_mn<kTileM>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, lane);
+      load_mn<N_TILE>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, lane);
+    } else {
+      load_tile_f32<kTileM, KB, A_TRANS>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, lane);
+      load_tile_f32<N_TILE, KB, B_TRANS>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, lane);
+    }
+  }
+  static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s,
+                                               uint32_t st, uint32_t, uint32_t d_tmem) {
+    constexpr uint32_t idesc = make_idesc(N_TILE, MN, MN);
+    const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+    for (int k16 = 0; k16 < KB / 16; ++k16) {
+      uint64_t da_hi, da_lo, db_hi, db_lo;
+      if (MN) {
+        const uint32_t o = k16 * 256;                 // 16 k rows of 16 B
+        da_hi = make_sdesc(a_hi + o, 128, PLANE_MN); da_lo = make_sdesc(a_lo + o, 128, PLANE_MN);
+        db_hi = make_sdesc(b_hi + o, 128, PLANE_MN); db_lo = make_sdesc(b_lo + o, 128, PLANE_MN);
+      } else {
+        const uint32_t ao = k16 * 2 * TA::LBO, bo = k16 * 2 * TB::LBO;
+        da_hi = make_sdesc(a_hi + ao, TA::LBO); da_lo = make_sdesc(a_lo + ao, TA::LBO);
+        db_hi = make_sdesc(b_hi + bo, TB::LBO); db_lo = make_sdesc(b_lo + bo, TB::LBO);
+      }
+      umma_f16(d_tmem, da_hi, db_hi, idesc, (s | k16) != 0 ? 1u : 0u);
+      umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+      umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+    }
+  }
   static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
                                                const float (&v)[16]) {
     const int m = t.mt * kTileM + row, n = t.nt * N_TILE + c;

@@ -29,7 +29,7 @@ def _run(pkg, variant, M, N, K, k_splits=1, seed=0):
                    extra.data_ptr() if extra is not None else None, M, N, K, k_splits,
                    pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
-    if variant == 3:
+    if variant >= 3:
         kb = 16
         per = (K + k_splits - 1) // k_splits
         k_chunk = (per + kb - 1) // kb * kb
@@ -52,8 +52,9 @@ def test_gemm_variants_vs_float64(pkg, cuda, variant, M, N, K):
 @pytest.mark.parametrize("M,N,K,splits", [(128, 256, 32, 1), (2592, 256, 1280, 7),
                                           (2592, 256, 77, 7), (264, 256, 5000, 3)])
 def test_gemm_wgrad_splitk_vs_float64(pkg, cuda, M, N, K, splits):
-    # K need not be a multiple of 8 for the transposed (sample-major) operands
-    K8 = K
-    e = _run(pkg, 3, M, N, K8, k_splits=splits)
-    print("gemm wgrad %dx%dx%d/%d rel-err %.3e" % (M, N, K, splits, e))
-    assert e <= 2e-5
+    # K need not be a multiple of 8 for the sample-major operands; variant 3 transposes them in
+    # registers into K-major images, variant 4 uses MN-major images (the conv wgrad path)
+    for variant in (3, 4):
+        e = _run(pkg, variant, M, N, K, k_splits=splits)
+        print("gemm wgrad v%d %dx%dx%d/%d rel-err %.3e" % (variant, M, N, K, splits, e))
+        assert e <= 2e-5
