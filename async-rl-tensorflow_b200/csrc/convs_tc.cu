@@ -83,14 +83,14 @@ struct Conv1Fwd {
   using Args = Conv1FwdArgs;
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one k-chunk
-  static constexpr int STAGES = 8, STAGE_BYTES = 8 * PL;      // hi only
+  static constexpr int PROD_WARPS = 16, STAGES = 8, STAGE_BYTES = 8 * PL;      // hi only
   static constexpr int PLB = 17 * 16, B_IMG = 32 * PLB, RES_BYTES = 2 * B_IMG;
   static constexpr int ACC_COLS = 16;
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
-  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid) {
-    for (int ch = ptid; ch < 16 * 32; ch += tc::kProdThreads) {
+  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
+    for (int ch = ptid; ch < 16 * 32; ch += nthr) {
       const int co = ch & 15, kc = ch >> 4;                    // kc = tap*8 + c*2 + h
       const int tap = kc >> 3, c = (kc >> 1) & 3, h = kc & 1, a = tap >> 1, b = tap & 1;
       float x[8];
@@ -167,15 +167,15 @@ struct Conv2Fwd {
   using Args = Conv2FwdArgs;
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
   static constexpr int PL = (TROWS + 1) * 16, IMG = 8 * PL;   // 2256, 18048
-  static constexpr int STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
+  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
   static constexpr int PLB = 33 * 16, B_IMG = 32 * PLB, RES_BYTES = 2 * B_IMG;
   static constexpr int ACC_COLS = 32;
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
-  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid) {
+  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
     const float* w2 = g.params + 4112;
-    for (int ch = ptid; ch < 32 * 32; ch += tc::kProdThreads) {
+    for (int ch = ptid; ch < 32 * 32; ch += nthr) {
       const int co = ch & 31, kc = ch >> 5;                    // kc = tap*8 + (i*2+j)*2 + chalf
       const int tap = kc >> 3, ij = (kc >> 1) & 3, chalf = kc & 1;
       const int kh = 2 * (tap >> 1) + (ij >> 1), kw = 2 * (tap & 1) + (ij & 1);
@@ -252,15 +252,15 @@ struct Conv2Dgrad {
   using Args = Conv2DgradArgs;
   static constexpr int GW = 11, GROWS = 121, TROWS = 140;
   static constexpr int PL = (TROWS + 1) * 16, IMG = 4 * PL;   // 32 co = 4 chunks
-  static constexpr int STAGES = 8, STAGE_BYTES = 2 * IMG;
+  static constexpr int PROD_WARPS = 16, STAGES = 8, STAGE_BYTES = 2 * IMG;
   static constexpr int PLB = 17 * 16, B_IMG = 16 * PLB, B_CLS = 2 * B_IMG, RES_BYTES = 4 * B_CLS;
   static constexpr int ACC_COLS = 64;                         // 4 parity classes x 16 channels
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
-  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid) {
+  static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
     const float* w2 = g.params + 4112;
-    for (int ch = ptid; ch < 4 * 16 * 16; ch += tc::kProdThreads) {
+    for (int ch = ptid; ch < 4 * 16 * 16; ch += nthr) {
       const int c = ch & 15, kc = (ch >> 4) & 15, cls = ch >> 8;   // kc = tap*4 + co8
       const int tap = kc >> 2, co8 = kc & 3;
       const int kh = (cls >> 1) + 2 * (tap >> 1), kw = (cls & 1) + 2 * (tap & 1);
@@ -351,7 +351,7 @@ struct Conv2Wgrad {
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
   static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // 2 shifted copies x 8 ch groups
   static constexpr int PLB = 129 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
-  static constexpr int STAGES = 2, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
+  static constexpr int PROD_WARPS = 16, STAGES = 2, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
   static constexpr int ACC_COLS = 64;                              // tap a in {0,1} x 32 co
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
@@ -360,7 +360,7 @@ struct Conv2Wgrad {
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
     return (t.k_end - t.k_begin + 127) / 128;
   }
-  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int) {}
+  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
                                                     uint8_t* st, int glane, int gsize) {
     const int64_t p0 = (int64_t)t.k_begin + (int64_t)s * 128;
@@ -440,7 +440,7 @@ struct Conv1Wgrad {
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // exact bf16: hi only
   static constexpr int PLB = 129 * 16, B_IMG = 2 * PLB;            // dy1z: 2 co groups
-  static constexpr int STAGES = 4, STAGE_BYTES = A_IMG + 2 * B_IMG, RES_BYTES = 0;
+  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = A_IMG + 2 * B_IMG, RES_BYTES = 0;
   static constexpr int ACC_COLS = 32;                              // tap a in {0,1} x 16 co
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
@@ -449,7 +449,7 @@ struct Conv1Wgrad {
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
     return (t.k_end - t.k_begin + 127) / 128;
   }
-  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int) {}
+  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
                                                     uint8_t* st, int glane, int gsize) {
     const int64_t p0 = (int64_t)t.k_begin + (int64_t)s * 128;

@@ -116,7 +116,7 @@ extern "C" int arl_fc_backward(const float* params, const float* a2, const float
   if (rc) return rc;
   // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles = 147 work items
   float* part = (float*)workspace;
-  rc = fc_gemm(3, a2, d_h, part, nullptr, ARL_A2_ELEMS, ARL_FC, M, ARL_A2_ELEMS, ARL_FC, ARL_FC, 7, st);
+  rc = fc_gemm(4, a2, d_h, part, nullptr, ARL_A2_ELEMS, ARL_FC, M, ARL_A2_ELEMS, ARL_FC, ARL_FC, 7, st);
   if (rc) return rc;
   const int splits = fc_wgrad_splits(M, 7);
   rc = reduce_partials(part, gW, splits, ARL_A2_ELEMS * ARL_FC, st);

@@ -28,11 +28,11 @@
 namespace arl {
 namespace tc {
 
-constexpr int kEpiWarps = 4, kProdWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kThreads = (kEpiWarps + kProdWarps + 1) * 32;   // 416
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 12
+constexpr int kEpiWarps = 4;
 constexpr int kTileM = 128;
+// per policy: PROD_WARPS producer warps (8 or 16); warp layout = [4 epilogue | producers | MMA]
+template <class P> __host__ __device__ constexpr int prod_threads() { return P::PROD_WARPS * 32; }
+template <class P> __host__ __device__ constexpr int cta_threads() { return (kEpiWarps + P::PROD_WARPS + 1) * 32; }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -197,12 +197,12 @@ struct TileCoord {
 };
 
 // A Policy provides:
-//   Args; STAGES (4 or 8); STAGE_BYTES; RES_BYTES (resident smem, e.g. converted weights);
+//   Args; PROD_WARPS (8 or 16); STAGES (2, 4 or 8); STAGE_BYTES; RES_BYTES (resident smem, e.g. converted weights);
 //   ACC_COLS (TMEM columns of one accumulator set, multiple of 16)
 //   static __device__ int num_items(const Args&)
 //   static __device__ TileCoord coord(const Args&, int item)
 //   static __device__ int num_stages(const Args&, const TileCoord&)          stages per item
-//   static __device__ void load_resident(const Args&, uint8_t* res, int ptid)   (256 threads)
+//   static __device__ void load_resident(const Args&, uint8_t* res, int ptid, int nthreads)
 //   static __device__ void load_stage(const Args&, const TileCoord&, int s, uint8_t* stage,
 //                                     int glane, int gsize)     lanes of the stage's warp group
 //   static __device__ void issue(const Args&, const TileCoord&, int s, uint32_t stage_addr,
@@ -216,9 +216,11 @@ struct Smem {
 };
 
 template <class P>
-__global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
+__global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Args g) {
   using S = Smem<P>;
-  constexpr int STAGES = P::STAGES, WPS = kProdWarps / STAGES;     // producer warps per stage
+  constexpr int STAGES = P::STAGES, WPS = P::PROD_WARPS / STAGES;  // producer warps per stage
+  constexpr int kMmaWarp = kEpiWarps + P::PROD_WARPS;
+  static_assert(P::PROD_WARPS % STAGES == 0, "producer warps must divide evenly over the stages");
   static_assert(STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* res = smem + STAGES * P::STAGE_BYTES;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(typename P::Args g) {
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_base_slot, kTmemCols);
   if (P::RES_BYTES > 0 && warp >= kEpiWarps && warp < kMmaWarp) {
-    P::load_resident(g, res, tid - kEpiWarps * 32);
+    P::load_resident(g, res, tid - kEpiWarps * 32, prod_threads<P>());
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -338,7 +340,7 @@ int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   }
   if (items <= 0) return ARL_OK;
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kThreads, S::TOTAL, stream>>>(g);
+  kern<<<grid, cta_threads<P>(), S::TOTAL, stream>>>(g);
   ARL_LAUNCH_CHECK("tc_kernel");
   return ARL_OK;
 }
@@ -364,6 +366,7 @@ template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI, bool MN = f
 struct GemmPolicy {
   using Args = GemmArgs;
   static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = 8, ACC_COLS = N_TILE_;
+  static constexpr int PROD_WARPS = (MN || (!A_TRANS && !B_TRANS)) ? 16 : 8;   // register budget
   using TA = OperandTile<kTileM, KB>;
   using TB = OperandTile<N_TILE, KB>;
   // MN-major images: plane = 8 rows x KB k  -> (KB+1)*16 bytes per plane, ROWS/8 planes
@@ -389,7 +392,7 @@ struct GemmPolicy {
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
     return (t.k_end - t.k_begin + KB - 1) / KB;
   }
-  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int) {}
+  static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
 
   // MN-major image of a sample-major source: vector (k, row group rg) at rg*PLANE_MN + k*16
   template <int ROWS>
