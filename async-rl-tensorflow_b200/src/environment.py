@@ -45,12 +45,16 @@ class SyntheticAtari(object):
     """
 
     def __init__(self, num_envs, action_size=6, seed=123, pool=8, device='cuda', host=False,
-                 p_terminal=0.01, reward_scale=1.0, structured=False, lives=3):
+                 p_terminal=0.01, reward_scale=1.0, structured=False, lives=3, shard=None):
         self.num_envs, self.device, self.host = int(num_envs), torch.device(device), bool(host)
         self.pool = int(pool)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed))
-        B, P = self.num_envs, self.pool
+        # shard=(rank, world): draw the pool for the world*num_envs GLOBAL envs from the one seed
+        # and keep this rank's slice, so an N-rank run sees exactly the single-process data
+        # (multi-GPU parity tests; benchmarks use per-rank seeds instead -- no extra memory)
+        rank, world = shard if shard is not None else (0, 1)
+        B, P = self.num_envs * int(world), self.pool
         shape = (P, B) + FRAME_SHAPE
         if structured:   # few colours, large flat regions (Atari-like)
             pal = torch.randint(0, 256, (16, 3), device=self.device, dtype=torch.uint8,
@@ -65,6 +69,13 @@ class SyntheticAtari(object):
         self._rewards = (torch.where(u < 0.05, -1.0, torch.where(u > 0.95, 1.0, 0.0))
                          * reward_scale).float()
         self._terminals = torch.rand(P, B, device=self.device, generator=self._gen) < p_terminal
+        if shard is not None:
+            lo, hi = rank * self.num_envs, (rank + 1) * self.num_envs
+            frames = frames[:, lo:hi].contiguous()
+            self._rewards = self._rewards[:, lo:hi].contiguous()
+            self._terminals = self._terminals[:, lo:hi].contiguous()
+            B = self.num_envs
+            shape = (P, B) + FRAME_SHAPE
         if self.host:
             self._frames = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
             self._frames.copy_(frames)
