@@ -35,40 +35,192 @@ __device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
   x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
   x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
 }
-__device__ __forceinline__ void zero8(float (&x)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = 0.f;
-}
 __device__ __forceinline__ TileCoord row_tile(int item) {
   TileCoord t;
   t.mt = item; t.nt = 0; t.ks = 0; t.k_begin = 0; t.k_end = 0;
   return t;
 }
 
-// ---- gather of one space-to-depth row ---------------------------------------------------------
-// conv1: X row (n, y', x') -> 8 chunks; chunk kc = c*2 + h holds channels ch = (c*4+i)*4+j for
+// ---- pixel-contiguous fp32 tensors scattered onto a padded row grid --------------------------
+// A tensor [samples][PH*PW pixels][4*CF4 floats] (dy1, dy2) is laid on a per-sample grid of
+// GROWS = rows of width GW with the pixel (py,px) at grid row (py+OFF)*GW + (px+OFF); the other
+// grid rows are zero.  A stage needs the grid rows [z0, z0+ROWS).  The pixels that land there are
+// ONE contiguous range of the tensor, so the producers stream that range with warp-contiguous
+// float4 loads (lane = 16 consecutive bytes) and scatter each float4 to its image position;
+// a second small pass zero-fills the rows no pixel maps to.  All row/pixel indices fit in int32
+// (checked by the entry points).
+template <int GW, int GROWS, int PH, int PW, int OFF, int CF4>
+struct PixelGrid {
+  static constexpr int PP = PH * PW, WIDTH = PW;
+  // a pixel index that is <= the first pixel whose grid row is >= z
+  static __device__ __forceinline__ int lower_pixel(int z) {
+    const int n = z / GROWS, rem = z - n * GROWS, gy = rem / GW, gx = rem - gy * GW;
+    const int py = min(max(gy - OFF, 0), PH - 1), px = min(max(gx - OFF, 0), PW - 1);
+    return n * PP + max(py * PW + px - PW, 0);
+  }
+  static __device__ __forceinline__ int grid_of_pixel(int pix) {
+    const int n = pix / PP, rem = pix - n * PP, py = rem / PW, px = rem - py * PW;
+    return n * GROWS + (py + OFF) * GW + (px + OFF);
+  }
+  static __device__ __forceinline__ bool row_has_pixel(int z, int num_samples) {
+    const int n = z / GROWS, rem = z - n * GROWS, gy = rem / GW, gx = rem - gy * GW;
+    return n < num_samples && gy >= OFF && gy < PH + OFF && gx >= OFF && gx < PW + OFF;
+  }
+};
+
+// Streams the pixels of grid rows [z0, z0+ROWS) (rows >= z_end count as zero) into a hi/lo image
+// pair whose 16-B vector (row r, chunk kc) sits at kc*PL + r*16.  U float4 loads are in flight per
+// lane before the first one is consumed (U * gsize >= the whole window => one latency per stage).
+// acc (optional) accumulates the column sums of what was stored: a lane owns floats
+// (glane % CF4)*4 .. +3 of every pixel it touches.
+template <class G, int CF4, int ROWS, int PL, int U, bool ACC>
+__device__ __forceinline__ void stream_pixels(uint8_t* hi, uint8_t* lo, const float* __restrict__ src,
+                                              int z0, int z_end, int num_samples, int glane,
+                                              int gsize, float (&acc)[4]) {
+  const int p0 = G::lower_pixel(z0);
+  const int p_total = num_samples * G::PP;
+  constexpr int SPAN = ROWS + 2 * G::WIDTH + 2;              // lower_pixel undershoots by <= 2*PW
+  constexpr int TOTAL = SPAN * CF4;
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (int64_t)p0 * CF4;
+  const int q = glane % CF4;                                 // gsize % CF4 == 0
+  for (int f0 = glane; f0 < TOTAL; f0 += U * gsize) {
+    float4 x[U];
+    int rr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int f = f0 + u * gsize;
+      const int pix = p0 + f / CF4;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rr[u] = -1;
+      if (f < TOTAL && pix < p_total) {
+        const int z = G::grid_of_pixel(pix);
+        if (z >= z0 && z < z0 + ROWS) {
+          rr[u] = z - z0;
+          if (z < z_end) x[u] = __ldg(s4 + f);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (rr[u] < 0) continue;
+      tc::store_half_split(hi, lo, (q >> 1) * PL + rr[u] * 16 + (q & 1) * 8, x[u]);
+      if (ACC) { acc[0] += x[u].x; acc[1] += x[u].y; acc[2] += x[u].z; acc[3] += x[u].w; }
+    }
+  }
+  // rows of the window that no pixel maps to (grid padding, beyond the last sample)
+  for (int r = glane; r < ROWS; r += gsize) {
+    if (!G::row_has_pixel(z0 + r, num_samples)) {
+#pragma unroll
+      for (int kc = 0; kc < CF4 / 2; ++kc) {
+        *reinterpret_cast<uint4*>(hi + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(lo + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+}
+
+using GridDy1 = PixelGrid<21, 441, 20, 20, 0, 4>;     // dy1 [N,400,16] on the conv1 X grid
+using GridDy2 = PixelGrid<10, 100, 9, 9, 0, 8>;       // dy2 [N,81,32] on the conv2 X2 grid
+using GridZ   = PixelGrid<11, 121, 9, 9, 1, 8>;       // dy2 zero-padded by one (transposed conv)
+
+// ---- conv2 A operand: space-to-depth rows of a1 ------------------------------------------------
+// X2 row (n, yp, xp) = a1[n][2yp..2yp+1][2xp..2xp+1][16] -> 8 chunks kc = (i*2+j)*2 + chalf.  The
+// 10 X2 rows of one (n, yp) are the 2560 contiguous bytes a1[n][2yp..2yp+1][:][:], and consecutive
+// (n, yp) follow each other, so a window of X2 rows is one contiguous float4 range of a1.
+// SHIFTED: also store the copy shifted by one row into planes 8..15 (tap b = 1 of the wgrad).
+template <int ROWS, int PL, int U, bool SHIFTED>
+__device__ __forceinline__ void stream_x2(uint8_t* hi, uint8_t* lo, const float* __restrict__ a1,
+                                          int xr0, int num_samples, int glane, int gsize) {
+  const int Y0 = xr0 / 10;
+  const int nY = (xr0 + ROWS - 1) / 10 - Y0 + 1;
+  const int Yrem = num_samples * 10 - Y0;                    // (n, yp) pairs that exist from Y0 on
+  const float4* s4 = reinterpret_cast<const float4*>(a1) + (int64_t)Y0 * 160;
+  const int total = nY * 160;
+  const int rbase = Y0 * 10 - xr0;                           // row of (Y0, xp = 0) in the window
+  for (int f0 = glane; f0 < total; f0 += U * gsize) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int f = f0 + u * gsize;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < total && f / 160 < Yrem) x[u] = __ldg(s4 + f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int f = f0 + u * gsize;
+      if (f >= total) break;
+      const int Yl = f / 160, w = f - Yl * 160, i = w >= 80 ? 1 : 0, wp = w - 80 * i;
+      const int pix = wp >> 2, q4 = wp & 3, xp = pix >> 1, j = pix & 1;
+      const int r = rbase + Yl * 10 + xp;
+      if (r < 0 || r >= ROWS) continue;
+      const int kc = (i * 2 + j) * 2 + (q4 >> 1);
+      const int off = kc * PL + r * 16 + (q4 & 1) * 8;
+      uint2 h, l;
+      tc::split2(x[u].x, x[u].y, h.x, l.x);
+      tc::split2(x[u].z, x[u].w, h.y, l.y);
+      *reinterpret_cast<uint2*>(hi + off) = h;
+      *reinterpret_cast<uint2*>(lo + off) = l;
+      if (SHIFTED && r > 0) {
+        *reinterpret_cast<uint2*>(hi + off + 8 * PL - 16) = h;
+        *reinterpret_cast<uint2*>(lo + off + 8 * PL - 16) = l;
+      }
+    }
+  }
+}
+
+// ---- conv1 A operand: space-to-depth rows of the u8 ring ---------------------------------------
+// X row (n, y', x') -> 8 chunks; chunk kc = c*2 + h holds channels ch = (c*4+i)*4+j for
 // i in {2h, 2h+1}, j in 0..3 = frame rows 4y'+2h, 4y'+2h+1, columns 4x'..4x'+3 of plane c.
+// Work unit = (row, plane c): four 4-byte loads -> two 16-B chunks.  Lanes run along the rows of
+// one plane (consecutive x' = consecutive 4-byte words); U units (4U loads) are in flight per lane.
+// SHIFTED: also store the copy shifted by one row into planes 8..15 (tap b = 1 of the wgrad).
 struct RingGeo {
   const uint8_t* ring;
   int num_envs, ring_slots, first_slot;
 };
-__device__ __forceinline__ void conv1_x_row(const RingGeo& g, int n, int yp, int xp, uint4 (&out)[8]) {
-  const int tt = n / g.num_envs, b = n - tt * g.num_envs;
+template <int ROWS, int PL, int U, bool SHIFTED>
+__device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr0, int num_samples,
+                                          int glane, int gsize) {
+  constexpr int GW = 21, GROWS = 441, TOTAL = ROWS * 4;
+  const int n0 = xr0 / GROWS, q0 = xr0 - n0 * GROWS;
+  const int tt0 = n0 / g.num_envs, b0 = n0 - tt0 * g.num_envs;
+  for (int u0 = glane; u0 < TOTAL; u0 += U * gsize) {
+    uint32_t w[U][4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int slot = (g.first_slot + tt + c) % g.ring_slots;
-    const uint8_t* src = g.ring + ((size_t)b * g.ring_slots + slot) * kPlane + (4 * yp) * ARL_SCREEN + 4 * xp;
-    uint32_t w[4];
+    for (int u = 0; u < U; ++u) {
+      const int un = u0 + u * gsize;
+      const int c = un / ROWS, r = un - c * ROWS;
+      int q = q0 + r, n = n0, tt = tt0, b = b0;
+      if (q >= GROWS) {                                      // ROWS < GROWS: at most one wrap
+        q -= GROWS; ++n; ++b;
+        if (b == g.num_envs) { b = 0; ++tt; }
+      }
+      w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
+      if (un < TOTAL && n < num_samples) {
+        const int yp = q / GW, xp = q - yp * GW;
+        int slot = g.first_slot + tt + c;
+        slot -= slot >= g.ring_slots ? g.ring_slots : 0;
+        slot -= slot >= g.ring_slots ? g.ring_slots : 0;
+        const uint8_t* src = g.ring + ((size_t)b * g.ring_slots + slot) * kPlane + (4 * yp) * ARL_SCREEN + 4 * xp;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(src + i * ARL_SCREEN));
-    out[2 * c] = tc::bytes8_to_bf16(w[0], w[1]);
-    out[2 * c + 1] = tc::bytes8_to_bf16(w[2], w[3]);
+        for (int i = 0; i < 4; ++i) w[u][i] = __ldg(reinterpret_cast<const uint32_t*>(src + i * ARL_SCREEN));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int un = u0 + u * gsize;
+      if (un >= TOTAL) break;
+      const int c = un / ROWS, r = un - c * ROWS;
+      const uint4 lo2 = tc::bytes8_to_bf16(w[u][0], w[u][1]), hi2 = tc::bytes8_to_bf16(w[u][2], w[u][3]);
+      uint8_t* d = img + (2 * c) * PL + r * 16;
+      *reinterpret_cast<uint4*>(d) = lo2;
+      *reinterpret_cast<uint4*>(d + PL) = hi2;
+      if (SHIFTED && r > 0) {
+        *reinterpret_cast<uint4*>(d + 8 * PL - 16) = lo2;
+        *reinterpret_cast<uint4*>(d + 9 * PL - 16) = hi2;
+      }
+    }
   }
-}
-// conv2: X2 row (n, y', x') chunk kc = (i*2+j)*2 + chalf <- a1[n][2y'+i][2x'+j][chalf*8 ..]
-__device__ __forceinline__ const float* conv2_x_chunk(const float* a1, int n, int yp, int xp, int kc) {
-  const int ij = kc >> 1, i = ij >> 1, j = ij & 1;
-  return a1 + (int64_t)n * ARL_A1_ELEMS + ((2 * yp + i) * 20 + 2 * xp + j) * 16 + (kc & 1) * 8;
 }
 
 // =================================== conv1 forward ============================================
@@ -79,13 +231,15 @@ struct Conv1FwdArgs {
   int64_t rows;          // 441 * num_samples (grid rows)
   int num_samples;
 };
-struct Conv1Fwd {
+struct Conv1Fwd : tc::PolicyBase {
   using Args = Conv1FwdArgs;
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one k-chunk
   static constexpr int PROD_WARPS = 16, STAGES = 8, STAGE_BYTES = 8 * PL;      // hi only
-  static constexpr int PLB = 17 * 16, B_IMG = 32 * PLB, RES_BYTES = 2 * B_IMG;
-  static constexpr int ACC_COLS = 16;
+  // resident W1 image: rows = [16 co hi | 16 co lo] (N = 32), 32 k-chunk planes
+  static constexpr int PLB = 33 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
+  static constexpr int ACC_COLS = 32, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
+  static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
@@ -99,29 +253,16 @@ struct Conv1Fwd {
         const int i = 2 * h + (e >> 2), j = e & 3;
         x[e] = g.params[(((4 * a + i) * 8 + 4 * b + j) * 4 + c) * 16 + co];
       }
-      tc::store_chunk_split(res, res + B_IMG, kc * PLB + co * 16, x);
+      tc::store_chunk_split(res, res + 16 * 16, kc * PLB + co * 16, x);
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
-                                                    uint8_t* st, int glane, int gsize) {
-    for (int r = glane; r < TROWS; r += gsize) {
-      const int64_t xr = (int64_t)t.mt * 128 + r;
-      const int n = (int)(xr / GROWS);
-      uint4 ch[8];
-      if (n < g.num_samples) {
-        const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-        conv1_x_row(g.geo, n, yp, xp, ch);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ch[k] = make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(st + k * PL + r * 16) = ch[k];
-    }
+                                                    uint8_t* st, int glane, int gsize, Prod&) {
+    stream_x1<TROWS, PL, 10, false>(st, g.geo, t.mt * 128, g.num_samples, glane, gsize);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(16);
+    constexpr uint32_t idesc = tc::make_idesc(32);                 // x . [w_hi | w_lo]
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
       const uint32_t a0 = st + ((tap >> 1) * GW + (tap & 1)) * 16;
@@ -130,28 +271,22 @@ struct Conv1Fwd {
         const uint64_t da = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
         const uint32_t b0 = res + (tap * 8 + 2 * k16) * PLB;
         tc::umma_f16(d, da, tc::make_sdesc(b0, PLB), idesc, (tap | k16) != 0 ? 1u : 0u);
-        tc::umma_f16(d, da, tc::make_sdesc(b0 + B_IMG, PLB), idesc, 1u);
       }
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int,
-                                               const float (&v)[16]) {
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int64_t xr = (int64_t)t.mt * 128 + row;
     const int n = (int)(xr / GROWS);
     const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-    if (n >= g.num_samples || yp >= 20 || xp >= 20) return;
-    const float* bias = g.params + 4096;
-    float* d = g.a1 + ((int64_t)n * 400 + yp * 20 + xp) * 16;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * k);
-      float4 o;
-      o.x = fmaxf(fmaf(v[4 * k], 1.0f / 255.0f, bb.x), 0.f);
-      o.y = fmaxf(fmaf(v[4 * k + 1], 1.0f / 255.0f, bb.y), 0.f);
-      o.z = fmaxf(fmaf(v[4 * k + 2], 1.0f / 255.0f, bb.z), 0.f);
-      o.w = fmaxf(fmaf(v[4 * k + 3], 1.0f / 255.0f, bb.w), 0.f);
-      *reinterpret_cast<float4*>(d + 4 * k) = o;
-    }
+    if (n >= g.num_samples || yp >= 20 || xp >= 20) return nullptr;
+    return g.a1 + ((int64_t)n * 400 + yp * 20 + xp) * 16;
+  }
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col) {
+    return tc::ldg4(g.params + 4096 + col);
+  }
+  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 bb) {
+    return make_float4(fmaxf(fmaf(v.x, 1.0f / 255.0f, bb.x), 0.f), fmaxf(fmaf(v.y, 1.0f / 255.0f, bb.y), 0.f),
+                       fmaxf(fmaf(v.z, 1.0f / 255.0f, bb.z), 0.f), fmaxf(fmaf(v.w, 1.0f / 255.0f, bb.w), 0.f));
   }
 };
 
@@ -163,13 +298,15 @@ struct Conv2FwdArgs {
   int64_t rows;          // 100 * num_samples
   int num_samples;
 };
-struct Conv2Fwd {
+struct Conv2Fwd : tc::PolicyBase {
   using Args = Conv2FwdArgs;
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PL = (TROWS + 1) * 16, IMG = 8 * PL;   // 2256, 18048
+  static constexpr int PL = 146 * 16, IMG = 8 * PL;           // plane rows = 2 (mod 8): 8-B stores conflict-free
   static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
-  static constexpr int PLB = 33 * 16, B_IMG = 32 * PLB, RES_BYTES = 2 * B_IMG;
-  static constexpr int ACC_COLS = 32;
+  // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
+  static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
+  static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
+  static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
@@ -182,27 +319,16 @@ struct Conv2Fwd {
       float x[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) x[e] = w2[((kh * 4 + kw) * 16 + chalf * 8 + e) * 32 + co];
-      tc::store_chunk_split(res, res + B_IMG, kc * PLB + co * 16, x);
+      tc::store_chunk_split(res, res + 32 * 16, kc * PLB + co * 16, x);
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
-                                                    uint8_t* st, int glane, int gsize) {
-    for (int r = glane; r < TROWS; r += gsize) {
-      const int64_t xr = (int64_t)t.mt * 128 + r;
-      const int n = (int)(xr / GROWS);
-      const bool ok = n < g.num_samples;
-      const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-#pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        float x[8];
-        if (ok) load8(conv2_x_chunk(g.a1, n, yp, xp, kc), x); else zero8(x);
-        tc::store_chunk_split(st, st + IMG, kc * PL + r * 16, x);
-      }
-    }
+                                                    uint8_t* st, int glane, int gsize, Prod&) {
+    stream_x2<TROWS, PL, 10, false>(st, st + IMG, g.a1, t.mt * 128, g.num_samples, glane, gsize);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(32);
+    constexpr uint32_t idesc64 = tc::make_idesc(64), idesc32 = tc::make_idesc(32);
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
       const uint32_t a0 = st + ((tap >> 1) * GW + (tap & 1)) * 16;
@@ -210,32 +336,25 @@ struct Conv2Fwd {
       for (int k16 = 0; k16 < 4; ++k16) {
         const uint64_t da_hi = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
         const uint64_t da_lo = tc::make_sdesc(a0 + IMG + 2 * k16 * PL, PL);
-        const uint32_t b0 = res + (tap * 8 + 2 * k16) * PLB;
-        const uint64_t db_hi = tc::make_sdesc(b0, PLB), db_lo = tc::make_sdesc(b0 + B_IMG, PLB);
-        tc::umma_f16(d, da_hi, db_hi, idesc, (tap | k16) != 0 ? 1u : 0u);
-        tc::umma_f16(d, da_hi, db_lo, idesc, 1u);
-        tc::umma_f16(d, da_lo, db_hi, idesc, 1u);
+        const uint64_t db = tc::make_sdesc(res + (tap * 8 + 2 * k16) * PLB, PLB);
+        tc::umma_f16(d, da_hi, db, idesc64, (tap | k16) != 0 ? 1u : 0u);   // x_hi . [w_hi | w_lo]
+        tc::umma_f16(d, da_lo, db, idesc32, 1u);                            // x_lo . w_hi
       }
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
-                                               const float (&v)[16]) {
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int64_t xr = (int64_t)t.mt * 128 + row;
     const int n = (int)(xr / GROWS);
     const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-    if (n >= g.num_samples || yp >= 9 || xp >= 9) return;
-    const float* bias = g.params + 4112 + 8192 + c;
-    float* d = g.a2 + ((int64_t)n * 81 + yp * 9 + xp) * 32 + c;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * k);
-      float4 o;
-      o.x = fmaxf(v[4 * k] + bb.x, 0.f);
-      o.y = fmaxf(v[4 * k + 1] + bb.y, 0.f);
-      o.z = fmaxf(v[4 * k + 2] + bb.z, 0.f);
-      o.w = fmaxf(v[4 * k + 3] + bb.w, 0.f);
-      *reinterpret_cast<float4*>(d + 4 * k) = o;
-    }
+    if (n >= g.num_samples || yp >= 9 || xp >= 9) return nullptr;
+    return g.a2 + ((int64_t)n * 81 + yp * 9 + xp) * 32;
+  }
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col) {
+    return tc::ldg4(g.params + 4112 + 8192 + col);
+  }
+  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 bb) {
+    return make_float4(fmaxf(v.x + bb.x, 0.f), fmaxf(v.y + bb.y, 0.f), fmaxf(v.z + bb.z, 0.f),
+                       fmaxf(v.w + bb.w, 0.f));
   }
 };
 
@@ -248,13 +367,16 @@ struct Conv2DgradArgs {
   int64_t rows;          // 121 * num_samples
   int num_samples;
 };
-struct Conv2Dgrad {
+struct Conv2Dgrad : tc::PolicyBase {
   using Args = Conv2DgradArgs;
   static constexpr int GW = 11, GROWS = 121, TROWS = 140;
-  static constexpr int PL = (TROWS + 1) * 16, IMG = 4 * PL;   // 32 co = 4 chunks
-  static constexpr int PROD_WARPS = 16, STAGES = 8, STAGE_BYTES = 2 * IMG;
-  static constexpr int PLB = 17 * 16, B_IMG = 16 * PLB, B_CLS = 2 * B_IMG, RES_BYTES = 4 * B_CLS;
-  static constexpr int ACC_COLS = 64;                         // 4 parity classes x 16 channels
+  static constexpr int PL = 146 * 16, IMG = 4 * PL;           // 32 co = 4 chunks
+  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = 2 * IMG;
+  // resident W2^T image: rows = part*64 + cls*16 + c (N = 128: the 4 parity classes share the A
+  // tile of a tap, and lo follows hi), 16 k-chunk planes (tap*4 + co8)
+  static constexpr int PLB = 129 * 16, RES_BYTES = 16 * PLB;
+  static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 64, SEG = 32;   // 4 classes x 16 ch
+  static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
@@ -266,66 +388,51 @@ struct Conv2Dgrad {
       const int kh = (cls >> 1) + 2 * (tap >> 1), kw = (cls & 1) + 2 * (tap & 1);
       float x[8];
       load8(w2 + ((kh * 4 + kw) * 16 + c) * 32 + co8 * 8, x);
-      uint8_t* base = res + cls * B_CLS;
-      tc::store_chunk_split(base, base + B_IMG, kc * PLB + c * 16, x);
+      tc::store_chunk_split(res, res + 64 * 16, kc * PLB + (cls * 16 + c) * 16, x);
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
-                                                    uint8_t* st, int glane, int gsize) {
-    for (int r = glane; r < TROWS; r += gsize) {
-      const int64_t zr = (int64_t)t.mt * 128 + r;
-      const int n = (int)(zr / GROWS);
-      const int q = (int)(zr - (int64_t)n * GROWS), zy = q / GW, zx = q - zy * GW;
-      const bool ok = n < g.num_samples && zy >= 1 && zy <= 9 && zx >= 1 && zx <= 9;
-      const float* src = g.dy2 + (int64_t)n * ARL_A2_ELEMS + ((zy - 1) * 9 + (zx - 1)) * 32;
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        float x[8];
-        if (ok) load8(src + kc * 8, x); else zero8(x);
-        tc::store_chunk_split(st, st + IMG, kc * PL + r * 16, x);
-      }
-    }
+                                                    uint8_t* st, int glane, int gsize, Prod&) {
+    float unused[4];
+    const int z0 = t.mt * 128;
+    stream_pixels<GridZ, 8, TROWS, PL, 10, false>(st, st + IMG, g.dy2, z0, z0 + TROWS, g.num_samples,
+                                                  glane, gsize, unused);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(16);
-#pragma unroll 1
-    for (int cls = 0; cls < 4; ++cls) {
+    constexpr uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
 #pragma unroll
-      for (int tap = 0; tap < 4; ++tap) {
-        // output (yy,xx) of this class reads Z row P + 12 - 11*dkh - dkw
-        const uint32_t a0 = st + (12 - 11 * (tap >> 1) - (tap & 1)) * 16;
+    for (int tap = 0; tap < 4; ++tap) {
+      // output (yy,xx) of every class reads Z row P + 12 - 11*dkh - dkw
+      const uint32_t a0 = st + (12 - 11 * (tap >> 1) - (tap & 1)) * 16;
 #pragma unroll
-        for (int k16 = 0; k16 < 2; ++k16) {
-          const uint64_t da_hi = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
-          const uint64_t da_lo = tc::make_sdesc(a0 + IMG + 2 * k16 * PL, PL);
-          const uint32_t b0 = res + cls * B_CLS + (tap * 4 + 2 * k16) * PLB;
-          const uint64_t db_hi = tc::make_sdesc(b0, PLB), db_lo = tc::make_sdesc(b0 + B_IMG, PLB);
-          tc::umma_f16(d + cls * 16, da_hi, db_hi, idesc, (tap | k16) != 0 ? 1u : 0u);
-          tc::umma_f16(d + cls * 16, da_hi, db_lo, idesc, 1u);
-          tc::umma_f16(d + cls * 16, da_lo, db_hi, idesc, 1u);
-        }
+      for (int k16 = 0; k16 < 2; ++k16) {
+        const uint64_t da_hi = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
+        const uint64_t da_lo = tc::make_sdesc(a0 + IMG + 2 * k16 * PL, PL);
+        const uint64_t db = tc::make_sdesc(res + (tap * 4 + 2 * k16) * PLB, PLB);
+        tc::umma_f16(d, da_hi, db, idesc128, (tap | k16) != 0 ? 1u : 0u);  // z_hi . [wT_hi | wT_lo]
+        tc::umma_f16(d, da_lo, db, idesc64, 1u);                            // z_lo . wT_hi
       }
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
-                                               const float (&v)[16]) {
+  // row (yy, xx) on the 11-wide grid -> the 2x2 block of dy1 pixels (2yy+dy, 2xx+dx); segment dy =
+  // parity classes (dy,0),(dy,1) = two adjacent pixels = 32 contiguous floats
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int64_t pr = (int64_t)t.mt * 128 + row;
     const int n = (int)(pr / GROWS);
     const int q = (int)(pr - (int64_t)n * GROWS), yy = q / GW, xx = q - yy * GW;
-    if (n >= g.num_samples || yy >= 10 || xx >= 10) return;
-    const int cls = c >> 4, y = 2 * yy + (cls >> 1), x = 2 * xx + (cls & 1);
-    const int64_t off = (int64_t)n * ARL_A1_ELEMS + (y * 20 + x) * 16;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(g.a1 + off) + k);
-      float4 o;
-      o.x = m.x > 0.f ? v[4 * k] : 0.f;
-      o.y = m.y > 0.f ? v[4 * k + 1] : 0.f;
-      o.z = m.z > 0.f ? v[4 * k + 2] : 0.f;
-      o.w = m.w > 0.f ? v[4 * k + 3] : 0.f;
-      *(reinterpret_cast<float4*>(g.dy1 + off) + k) = o;
-    }
+    if (n >= g.num_samples || yy >= 10 || xx >= 10) return nullptr;
+    return g.dy1 + (int64_t)n * ARL_A1_ELEMS + ((2 * yy) * 20 + 2 * xx) * 16;
+  }
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int dy) {
+    return dy * 20 * 16;
+  }
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float* dst, int) {
+    return tc::ldg4(g.a1 + (dst - g.dy1));
+  }
+  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 m) {
+    return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f,
+                       m.w > 0.f ? v.w : 0.f);
   }
 };
 
@@ -338,21 +445,37 @@ __device__ __forceinline__ TileCoord range_tile(int item, int64_t rows, int k_ch
   t.k_end = (int)(b + k_chunk < rows ? b + k_chunk : rows);
   return t;
 }
+// per-lane bias sums (4 floats of every CF4-th float4) -> per-warp partial row of CF4*4 floats
+template <int CF4>
+__device__ __forceinline__ void bias_partial_store(float* dst_row, float (&acc)[4], int lane) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int o = 16; o >= CF4; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  }
+  if (lane < CF4)
+    *reinterpret_cast<float4*>(dst_row + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
 
 struct Conv2WgradArgs {
   const float* a1;
   const float* dy2;
   float* partials;       // [items][8192]
+  float* bias_partials;  // [items * PROD_WARPS][32]  column sums of dy2 (= db2), per producer warp
   int64_t rows;          // 100 * num_samples
   int num_samples, k_chunk, items;
 };
-struct Conv2Wgrad {
+struct Conv2Wgrad : tc::PolicyBase {
   using Args = Conv2WgradArgs;
+  struct Prod { float acc[4]; };    // running column sums of dy2 (bias gradient)
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // 2 shifted copies x 8 ch groups
-  static constexpr int PLB = 129 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
+  static constexpr int PLA = 146 * 16, A_IMG = 16 * PLA;           // 2 shifted copies x 8 ch groups
+  static constexpr int PLB = 130 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
   static constexpr int PROD_WARPS = 16, STAGES = 2, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
-  static constexpr int ACC_COLS = 64;                              // tap a in {0,1} x 32 co
+  // accumulator columns: a*64 + part*32 + co (the lo image of dy2 follows its hi image, so one
+  // N = 64 MMA covers both)
+  static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 32, SEG = 32;
+  static __device__ __forceinline__ int acc_col(int c) { return (c >> 5) * 64 + (c & 31); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
     return range_tile(item, g.rows, g.k_chunk);
@@ -361,87 +484,70 @@ struct Conv2Wgrad {
     return (t.k_end - t.k_begin + 127) / 128;
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
+  static __device__ __forceinline__ void prod_begin(Prod& ps) {
+    ps.acc[0] = ps.acc[1] = ps.acc[2] = ps.acc[3] = 0.f;
+  }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int gsize) {
-    const int64_t p0 = (int64_t)t.k_begin + (int64_t)s * 128;
+                                                    uint8_t* st, int glane, int gsize, Prod& ps) {
+    const int p0 = t.k_begin + s * 128;
     uint8_t* a_hi = st, *a_lo = st + A_IMG, *b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
-    // A: X2 rows p0 .. p0+139; copy 0 holds row r at r*16, copy 1 (ch groups 8..15) holds row r
-    // at (r-1)*16, i.e. copy 1 is the image shifted by one row (tap b = 1)
-    for (int c = glane; c < TROWS * 8; c += gsize) {
-      const int r = c % TROWS, kc = c / TROWS;
-      const int64_t xr = p0 + r;
-      const int n = (int)(xr / GROWS);
-      const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-      float x[8];
-      if (n < g.num_samples) load8(conv2_x_chunk(g.a1, n, yp, xp, kc), x); else zero8(x);
-      uint4 h, l;
-      tc::split2(x[0], x[1], h.x, l.x); tc::split2(x[2], x[3], h.y, l.y);
-      tc::split2(x[4], x[5], h.z, l.z); tc::split2(x[6], x[7], h.w, l.w);
-      *reinterpret_cast<uint4*>(a_hi + kc * PLA + r * 16) = h;
-      *reinterpret_cast<uint4*>(a_lo + kc * PLA + r * 16) = l;
-      if (r > 0) {
-        *reinterpret_cast<uint4*>(a_hi + (8 + kc) * PLA + (r - 1) * 16) = h;
-        *reinterpret_cast<uint4*>(a_lo + (8 + kc) * PLA + (r - 1) * 16) = l;
-      }
-    }
+    // A: X2 rows p0 .. p0+139; planes 0..7 hold row r at r*16, planes 8..15 the same image shifted
+    // by one row (tap b = 1)
+    stream_x2<TROWS, PLA, 10, true>(a_hi, a_lo, g.a1, p0, g.num_samples, glane, gsize);
     // B: dy2 on the 10-wide grid, zero at y'=9 / x'=9 and outside [k_begin, k_end)
-    for (int c = glane; c < 128 * 4; c += gsize) {
-      const int r = c & 127, kc = c >> 7;
-      const int64_t pr = p0 + r;
-      const int n = (int)(pr / GROWS);
-      const int q = (int)(pr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-      float x[8];
-      if (pr < t.k_end && n < g.num_samples && yp < 9 && xp < 9)
-        load8(g.dy2 + (int64_t)n * ARL_A2_ELEMS + (yp * 9 + xp) * 32 + kc * 8, x);
-      else
-        zero8(x);
-      tc::store_chunk_split(b_hi, b_lo, kc * PLB + r * 16, x);
-    }
+    stream_pixels<GridDy2, 8, 128, PLB, 5, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
+                                                 gsize, ps.acc);
+  }
+  static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
+                                                  int lane) {
+    bias_partial_store<8>(g.bias_partials + ((size_t)t.ks * PROD_WARPS + pw) * 32, ps.acc, lane);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(32, true, true);
-    const uint32_t a_hi = st, a_lo = st + A_IMG, b_hi = st + 2 * A_IMG, b_lo = b_hi + B_IMG;
+    constexpr uint32_t idesc64 = tc::make_idesc(64, true, true), idesc32 = tc::make_idesc(32, true, true);
+    const uint32_t a_hi = st, a_lo = st + A_IMG, b_hi = st + 2 * A_IMG;   // b_lo = b_hi + B_IMG
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
 #pragma unroll
       for (int k16 = 0; k16 < 8; ++k16) {
         const uint32_t ao = (a * GW + k16 * 16) * 16, bo = k16 * 256;
         const uint64_t da_hi = tc::make_sdesc(a_hi + ao, 128, PLA), da_lo = tc::make_sdesc(a_lo + ao, 128, PLA);
-        const uint64_t db_hi = tc::make_sdesc(b_hi + bo, 128, PLB), db_lo = tc::make_sdesc(b_lo + bo, 128, PLB);
-        tc::umma_f16(d + a * 32, da_hi, db_hi, idesc, (s | k16) != 0 ? 1u : 0u);
-        tc::umma_f16(d + a * 32, da_hi, db_lo, idesc, 1u);
-        tc::umma_f16(d + a * 32, da_lo, db_hi, idesc, 1u);
+        const uint64_t db = tc::make_sdesc(b_hi + bo, 128, PLB);           // 8 co groups: hi | lo
+        tc::umma_f16(d + a * 64, da_hi, db, idesc64, (s | k16) != 0 ? 1u : 0u);
+        tc::umma_f16(d + a * 64, da_lo, db, idesc32, 1u);
       }
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
-                                               const float (&v)[16]) {
-    // row = b*64 + ch, ch = (i*2+j)*16 + cin ; column c = a*32 + co
+  // row = b*64 + ch, ch = (i*2+j)*16 + cin ; segment a = 32 co of tap (kh = 2a+i, kw = 2b+j)
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int b = row >> 6, ch = row & 63, ij = ch >> 4, cin = ch & 15;
-    const int a = c >> 5, co = c & 31;
-    const int kh = 2 * a + (ij >> 1), kw = 2 * b + (ij & 1);
-    float* d = g.partials + (size_t)t.ks * 8192 + ((kh * 4 + kw) * 16 + cin) * 32 + co;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      *reinterpret_cast<float4*>(d + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    const int kh = ij >> 1, kw = 2 * b + (ij & 1);
+    return g.partials + (size_t)t.ks * 8192 + ((kh * 4 + kw) * 16 + cin) * 32;
   }
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int a) {
+    return a * 2 * 4 * 16 * 32;
+  }
+
 };
 
 struct Conv1WgradArgs {
   RingGeo geo;
   const float* dy1;
   float* partials;       // [items][4096]
+  float* bias_partials;  // [items * PROD_WARPS][16]  column sums of dy1 (= db1), per producer warp
   int64_t rows;          // 441 * num_samples
   int num_samples, k_chunk, items;
 };
-struct Conv1Wgrad {
+struct Conv1Wgrad : tc::PolicyBase {
   using Args = Conv1WgradArgs;
+  struct Prod { float acc[4]; };    // running column sums of dy1 (bias gradient)
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // exact bf16: hi only
-  static constexpr int PLB = 129 * 16, B_IMG = 2 * PLB;            // dy1z: 2 co groups
+  static constexpr int PLB = 132 * 16, B_IMG = 2 * PLB;            // dy1z: 2 co groups
   static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = A_IMG + 2 * B_IMG, RES_BYTES = 0;
-  static constexpr int ACC_COLS = 32;                              // tap a in {0,1} x 16 co
+  // accumulator columns: a*32 + part*16 + co
+  static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 16, SEG = 16;
+  static __device__ __forceinline__ int acc_col(int c) { return (c >> 4) * 32 + (c & 15); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
     return range_tile(item, g.rows, g.k_chunk);
@@ -450,89 +556,51 @@ struct Conv1Wgrad {
     return (t.k_end - t.k_begin + 127) / 128;
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
+  static __device__ __forceinline__ void prod_begin(Prod& ps) {
+    ps.acc[0] = ps.acc[1] = ps.acc[2] = ps.acc[3] = 0.f;
+  }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int gsize) {
-    const int64_t p0 = (int64_t)t.k_begin + (int64_t)s * 128;
+                                                    uint8_t* st, int glane, int gsize, Prod& ps) {
+    const int p0 = t.k_begin + s * 128;
     uint8_t* a_img = st, *b_hi = st + A_IMG, *b_lo = b_hi + B_IMG;
-    for (int r = glane; r < TROWS; r += gsize) {
-      const int64_t xr = p0 + r;
-      const int n = (int)(xr / GROWS);
-      uint4 ch[8];
-      if (n < g.num_samples) {
-        const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-        conv1_x_row(g.geo, n, yp, xp, ch);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ch[k] = make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        *reinterpret_cast<uint4*>(a_img + k * PLA + r * 16) = ch[k];
-        if (r > 0) *reinterpret_cast<uint4*>(a_img + (8 + k) * PLA + (r - 1) * 16) = ch[k];
-      }
-    }
-    for (int c = glane; c < 128 * 2; c += gsize) {
-      const int r = c & 127, kc = c >> 7;
-      const int64_t pr = p0 + r;
-      const int n = (int)(pr / GROWS);
-      const int q = (int)(pr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
-      float x[8];
-      if (pr < t.k_end && n < g.num_samples && yp < 20 && xp < 20)
-        load8(g.dy1 + ((int64_t)n * 400 + yp * 20 + xp) * 16 + kc * 8, x);
-      else
-        zero8(x);
-      tc::store_chunk_split(b_hi, b_lo, kc * PLB + r * 16, x);
-    }
+    // A: X rows p0 .. p0+149 (exact in bf16: one image); planes 8..15 = shifted copy (tap b = 1)
+    stream_x1<TROWS, PLA, 5, true>(a_img, g.geo, p0, g.num_samples, glane, gsize);
+    // B: dy1 on the 21-wide grid, zero at y'=20 / x'=20 and outside [k_begin, k_end)
+    stream_pixels<GridDy1, 4, 128, PLB, 6, true>(b_hi, b_lo, g.dy1, p0, t.k_end, g.num_samples, glane,
+                                                 gsize, ps.acc);
+  }
+  static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
+                                                  int lane) {
+    bias_partial_store<4>(g.bias_partials + ((size_t)t.ks * PROD_WARPS + pw) * 16, ps.acc, lane);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(16, true, true);
-    const uint32_t a_img = st, b_hi = st + A_IMG, b_lo = b_hi + B_IMG;
+    constexpr uint32_t idesc = tc::make_idesc(32, true, true);     // x . [dy_hi | dy_lo]
+    const uint32_t a_img = st, b_hi = st + A_IMG;                  // b_lo = b_hi + B_IMG
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
 #pragma unroll
       for (int k16 = 0; k16 < 8; ++k16) {
         const uint64_t da = tc::make_sdesc(a_img + (a * GW + k16 * 16) * 16, 128, PLA);
-        tc::umma_f16(d + a * 16, da, tc::make_sdesc(b_hi + k16 * 256, 128, PLB), idesc,
+        tc::umma_f16(d + a * 32, da, tc::make_sdesc(b_hi + k16 * 256, 128, PLB), idesc,
                      (s | k16) != 0 ? 1u : 0u);
-        tc::umma_f16(d + a * 16, da, tc::make_sdesc(b_lo + k16 * 256, 128, PLB), idesc, 1u);
       }
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
-                                               const float (&v)[16]) {
-    // row = b*64 + ch, ch = (cin*4 + i)*4 + j ; column c = a*16 + co
+  // row = b*64 + ch, ch = (cin*4 + i)*4 + j ; segment a = 16 co of tap (kh = 4a+i, kw = 4b+j)
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int b = row >> 6, ch = row & 63, cin = ch >> 4, i = (ch >> 2) & 3, j = ch & 3;
-    const int a = c >> 4;
-    const int kh = 4 * a + i, kw = 4 * b + j;
-    float* d = g.partials + (size_t)t.ks * 4096 + ((kh * 8 + kw) * 4 + cin) * 16;
+    const int kw = 4 * b + j;
+    return g.partials + (size_t)t.ks * 4096 + ((i * 8 + kw) * 4 + cin) * 16;
+  }
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int a) {
+    return a * 4 * 8 * 4 * 16;
+  }
+  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4) {
     const float s = 1.0f / 255.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      *reinterpret_cast<float4*>(d + 4 * k) =
-          make_float4(v[4 * k] * s, v[4 * k + 1] * s, v[4 * k + 2] * s, v[4 * k + 3] * s);
+    return make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
   }
 };
-
-// partial column sums of X [rows, COLS] (COLS = 16 or 32): block b owns rows b, b+grid, ...
-template <int COLS>
-__global__ void colsum_small_kernel(const float* __restrict__ X, float* __restrict__ partials,
-                                    int64_t rows) {
-  __shared__ float red[256];
-  const int col = threadIdx.x % COLS, sub = threadIdx.x / COLS;
-  constexpr int SUBS = 256 / COLS;
-  float s = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * SUBS + sub; r < rows; r += (int64_t)gridDim.x * SUBS)
-    s += X[r * COLS + col];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  if (sub == 0) {
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < SUBS; ++k) v += red[k * COLS + col];
-    partials[(size_t)blockIdx.x * COLS + col] = v;
-  }
-}
 
 int split_rows(int64_t rows, int want, int* k_chunk) {
   int64_t per = (rows + want - 1) / want;
@@ -599,15 +667,13 @@ extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float*
   g.rows = N * 441;
   g.num_samples = (int)N;
   g.items = split_rows(g.rows, num_sms(), &g.k_chunk);
+  g.bias_partials = (float*)workspace + (size_t)g.items * 4096;
   int rc = tc::launch<Conv1Wgrad>(g, g.items, st);
   if (rc) return rc;
   rc = reduce_partials(g.partials, grads, g.items, 4096, st);                    // l1_w
   if (rc) return rc;
-  float* part = (float*)workspace + (size_t)g.items * 4096;
-  const int grid = num_sms();
-  colsum_small_kernel<16><<<grid, 256, 0, st>>>(d_a1, part, N * 400);
-  ARL_LAUNCH_CHECK("colsum_small_kernel<16>");
-  return reduce_partials(part, grads + 4096, grid, 16, st);                      // l1_b
+  // l1_b = column sums of d_a1, accumulated by the wgrad producers while they stream d_a1
+  return reduce_partials(g.bias_partials, grads + 4096, g.items * Conv1Wgrad::PROD_WARPS, 16, st);
 }
 
 extern "C" int arl_conv2_backward(const float* params, const float* a1, const float* d_a2,
@@ -632,15 +698,13 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
   w.rows = num_samples * 100;
   w.num_samples = (int)num_samples;
   w.items = split_rows(w.rows, num_sms(), &w.k_chunk);
+  w.bias_partials = (float*)workspace + (size_t)w.items * 8192;
   int rc = tc::launch<Conv2Wgrad>(w, w.items, st);
   if (rc) return rc;
   rc = reduce_partials(w.partials, g2, w.items, 8192, st);
   if (rc) return rc;
-  float* part = (float*)workspace + (size_t)w.items * 8192;
-  const int grid = num_sms();
-  colsum_small_kernel<32><<<grid, 256, 0, st>>>(d_a2, part, num_samples * 81);
-  ARL_LAUNCH_CHECK("colsum_small_kernel<32>");
-  rc = reduce_partials(part, g2 + 8192, grid, 32, st);
+  // l2_b = column sums of d_a2, accumulated by the wgrad producers while they stream d_a2
+  rc = reduce_partials(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, st);
   if (rc) return rc;
   Conv2DgradArgs d{params, a1, d_a2, d_a1, num_samples * 121, (int)num_samples};
   return tc::launch<Conv2Dgrad>(d, (int)((d.rows + 127) / 128), st);

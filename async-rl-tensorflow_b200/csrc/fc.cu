@@ -43,8 +43,8 @@ int fc_gemm(int variant, const float* A, const float* B, float* D, const float* 
     case 0: return tc::launch<tc::GemmPolicy<256, 16, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
     case 1: return tc::launch<tc::GemmPolicy<64, 32, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
     case 2: return tc::launch<tc::GemmPolicy<256, 16, false, false, tc::EPI_MASK>>(g, items, st);
-    case 3: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN>>(g, items, st);
-    case 4: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN, true>>(g, items, st);
+    case 3:   // (was: K-major images transposed in registers; now identical to 4)
+    case 4: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN>>(g, items, st);
     default: set_error("fc_gemm: unknown variant %d", variant); return ARL_ERR_INVALID;
   }
 }

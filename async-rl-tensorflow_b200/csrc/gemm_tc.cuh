@@ -18,8 +18,14 @@
 //                          accumulator (2 TMEM accumulator stages); owns tcgen05.alloc/dealloc
 //
 // smem operand image (bf16): element (row r, k) of a [ROWS x KB] tile sits at
-//   (k/8)*LBO + r*16 + (k%8)*2,  LBO = (ROWS+1)*16 (one 16-B pad keeps st.shared conflict-free),
-//   SBO = 128 (the 8 rows of a core matrix are contiguous).
+//   (k/8)*LBO + r*16 + (k%8)*2,  LBO = (ROWS+pad)*16, SBO = 128 (the 8 rows of a core matrix are
+//   contiguous).  Producers read HBM with WARP-CONTIGUOUS float4 loads (lane = 16 consecutive
+//   bytes, a warp instruction = 512 contiguous bytes = 4 full lines) and store the converted
+//   half-chunk (4 bf16 = 8 B) of hi and lo; `pad` is chosen per policy so that those 8-byte
+//   stores are bank-conflict-free.
+//
+// Epilogue: TMEM -> registers (lane = row) -> per-warp smem staging -> coalesced float4 stores
+// (SEG/4 lanes per row), so an instruction writes full 128-B lines instead of 32 x 16 B.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -84,6 +90,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column loads in flight, one wait; v += w (hi-part + lo-part accumulators)
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr_a, uint32_t taddr_b, float (&v)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,"
+      "%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_a)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,"
+      "%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]),
+        "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]),
+        "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr_b)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+}
+
 // instruction descriptor: bf16 x bf16 -> f32, M=128; operands K-major unless *_mn
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -98,13 +128,6 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-
-template <int ROWS, int KB>
-struct OperandTile {
-  static constexpr int KC = KB / 8;
-  static constexpr int LBO = (ROWS + 1) * 16;
-  static constexpr int BYTES = KC * LBO;          // one image (hi or lo)
-};
 
 // ---- chunk helpers (a chunk = 8 consecutive k of one row = 16 B of bf16) ---------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -124,6 +147,18 @@ __device__ __forceinline__ void store_chunk_split(uint8_t* hi_img, uint8_t* lo_i
   *reinterpret_cast<uint4*>(hi_img + off) = h;
   *reinterpret_cast<uint4*>(lo_img + off) = l;
 }
+// 4 consecutive k of one row: 8 B of hi and 8 B of lo
+__device__ __forceinline__ void store_half_split(uint8_t* hi_img, uint8_t* lo_img, int off,
+                                                 const float4& x) {
+  uint2 h, l;
+  split2(x.x, x.y, h.x, l.x);
+  split2(x.z, x.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi_img + off) = h;
+  *reinterpret_cast<uint2*>(lo_img + off) = l;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
 // 8 bytes (two u32 words) -> 8 exact bf16
 __device__ __forceinline__ uint32_t bytes2bf16x2(uint32_t w, int sel_lo, int sel_hi) {
   // 0x4B000000 | byte = 8388608 + byte as fp32; subtracting 8388608 is exact
@@ -142,77 +177,67 @@ __device__ __forceinline__ uint4 bytes8_to_bf16(uint32_t w0, uint32_t w1) {
   return o;
 }
 
-// Generic fp32 operand tile loader used by several policies, one WARP fills the tile.
-// TRANS=false: element (r,k) at src[r*ld + k] (k contiguous; r < rmax checked per row,
-//              k < kmax per 8-chunk).  TRANS=true: element (r,k) at src[k*ld + r] (r contiguous;
-//              r checked per 8-row group, k per element).
-template <int ROWS, int KB, bool TRANS>
-__device__ __forceinline__ void load_tile_f32(uint8_t* hi_img, uint8_t* lo_img,
-                                              const float* __restrict__ src, int64_t ld, int r0,
-                                              int rmax, int k0, int kmax, int lane) {
-  using T = OperandTile<ROWS, KB>;
-  if (!TRANS) {
-#pragma unroll 2
-    for (int c = lane; c < ROWS * T::KC; c += 32) {
-      const int row = c % ROWS, kc = c / ROWS;
-      const int r = r0 + row, k = k0 + kc * 8;
-      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (r < rmax && k < kmax) {
-        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * ld + k);
-        const float4 x0 = p[0], x1 = p[1];
-        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
-        x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
-      }
-      store_chunk_split(hi_img, lo_img, kc * T::LBO + row * 16, x);
-    }
-  } else {
-    // 8 (rows) x 8 (k) blocks, lanes along the k-chunks (pad in LBO => conflict-free stores)
-    for (int b = lane; b < (ROWS / 8) * T::KC; b += 32) {
-      const int kc = b % T::KC, rg = b / T::KC;
-      const int r = r0 + rg * 8, k = k0 + kc * 8;
-      float v[8][8];                                  // [k][row]
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        if (r < rmax && k + kk < kmax) {
-          const float4* p = reinterpret_cast<const float4*>(src + (int64_t)(k + kk) * ld + r);
-          x0 = p[0];
-          x1 = p[1];
-        }
-        v[kk][0] = x0.x; v[kk][1] = x0.y; v[kk][2] = x0.z; v[kk][3] = x0.w;
-        v[kk][4] = x1.x; v[kk][5] = x1.y; v[kk][6] = x1.z; v[kk][7] = x1.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x[8] = {v[0][i], v[1][i], v[2][i], v[3][i], v[4][i], v[5][i], v[6][i], v[7][i]};
-        store_chunk_split(hi_img, lo_img, kc * T::LBO + (rg * 8 + i) * 16, x);
-      }
-    }
-  }
-}
-
 struct TileCoord {
   int mt, nt, ks;        // tile indices (meaning is the policy's)
   int k_begin, k_end;    // reduction range of this work item (meaning is the policy's)
 };
 
-// A Policy provides:
+// Per-thread producer state that lives across the stages of one work item (e.g. the running
+// column sums of the operand a producer streams through its registers anyway = a bias gradient).
+struct PolicyBase {
+  struct Prod {};
+  static __device__ __forceinline__ void prod_begin(Prod&) {}
+  template <class Args>
+  static __device__ __forceinline__ void prod_end(const Args&, const TileCoord&, Prod&, int, int) {}
+  template <class Args>
+  static __device__ __forceinline__ bool seg_valid(const Args&, const TileCoord&, int) { return true; }
+  template <class Args>
+  static __device__ __forceinline__ bool col_valid(const Args&, const TileCoord&, int) { return true; }
+  template <class Args>
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int) { return 0; }
+  template <class Args>
+  static __device__ __forceinline__ float4 aux_load(const Args&, const TileCoord&, const float*, int) {
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  template <class Args>
+  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4) { return v; }
+};
+
+// A Policy (derived from PolicyBase) provides:
 //   Args; PROD_WARPS (8 or 16); STAGES (2, 4 or 8); STAGE_BYTES; RES_BYTES (resident smem, e.g. converted weights);
 //   ACC_COLS (TMEM columns of one accumulator set, multiple of 16)
+//   OUT_COLS (logical output columns), acc_col(c) (TMEM column of output column c, c % 16 == 0),
+//   LO_DELTA (> 0: output = acc[acc_col(c)] + acc[acc_col(c) + LO_DELTA]; the bf16 lo-part of the
+//   B operand is CONCATENATED to its hi-part along N so that one MMA of width 2N replaces two of
+//   width N -- the A tile is read from shared memory once instead of twice, which is what bounds
+//   the narrow-N (16/32) convolutions: see DESIGN.md "L1 data pipe")
 //   static __device__ int num_items(const Args&)
 //   static __device__ TileCoord coord(const Args&, int item)
 //   static __device__ int num_stages(const Args&, const TileCoord&)          stages per item
 //   static __device__ void load_resident(const Args&, uint8_t* res, int ptid, int nthreads)
 //   static __device__ void load_stage(const Args&, const TileCoord&, int s, uint8_t* stage,
-//                                     int glane, int gsize)     lanes of the stage's warp group
+//                                     int glane, int gsize, Prod&)   lanes of the stage's warp group
+//   optional: Prod, prod_begin(Prod&), prod_end(Args, TileCoord, Prod&, producer warp, lane)
+//             called by every producer thread before the first / after the last stage of an item
 //   static __device__ void issue(const Args&, const TileCoord&, int s, uint32_t stage_addr,
 //                                uint32_t res_addr, uint32_t d_tmem)   all MMAs of stage s
 //                                (s == 0 must start with accumulate = 0)
-//   static __device__ void store(const Args&, const TileCoord&, int row, int col, const float (&v)[16])
+//   epilogue: SEG (16 or 32 floats: contiguous output run of one row), NSEG = OUT_COLS / SEG,
+//     static __device__ float* row_ptr(const Args&, const TileCoord&, int row)   nullptr = skip row
+//     static __device__ bool seg_valid(const Args&, const TileCoord&, int sg)    (warp-uniform)
+//     static __device__ int64_t seg_offset(const Args&, const TileCoord&, int sg) floats from row_ptr
+//     static __device__ bool col_valid(const Args&, const TileCoord&, int col)
+//     static __device__ float4 aux_load(const Args&, const TileCoord&, const float* dst, int col)
+//     static __device__ float4 finish(const Args&, float4 acc, float4 aux)
+//       col = sg*SEG + 4*j: the float4's first logical output column; aux = what the finishing
+//       op needs from HBM (bias, relu mask), loaded ahead of the accumulator read-out
 template <class P>
 struct Smem {
   static constexpr int BAR_OFF = P::STAGES * P::STAGE_BYTES + P::RES_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256;
+  static constexpr int EPI_OFF = BAR_OFF + 256;
+  static constexpr int EPI_ROW = (P::SEG + 4) * 4;              // staged row, padded: conflict-free
+  static constexpr int EPI_WARP = 32 * EPI_ROW + 32 * 8;        // staging + 32 row pointers
+  static constexpr int TOTAL = EPI_OFF + kEpiWarps * EPI_WARP;
 };
 
 template <class P>
@@ -266,13 +291,16 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const TileCoord tc = P::coord(g, item);
       const int ns = P::num_stages(g, tc);
+      typename P::Prod ps;
+      P::prod_begin(ps);
       for (int s = 0; s < ns; ++s, ++i) {
         if (i % STAGES != pg) continue;
         mbar_wait(&empty[pg], ((i / STAGES) & 1) ^ 1);
-        P::load_stage(g, tc, s, st, glane, 32 * WPS);
+        P::load_stage(g, tc, s, st, glane, 32 * WPS, ps);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
         mbar_arrive(&full[pg]);
       }
+      P::prod_end(g, tc, ps, pw, lane);
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
@@ -300,18 +328,67 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     }
   } else {
     // ===================== epilogue =====================
+    constexpr int SEG = P::SEG, NSEG = P::OUT_COLS / SEG, LPR = SEG / 4, RPI = 32 / LPR;
+    static_assert((SEG == 16 || SEG == 32) && P::OUT_COLS % SEG == 0, "SEG");
+    uint8_t* ep = smem + S::EPI_OFF + warp * S::EPI_WARP;
+    float* stg = reinterpret_cast<float*>(ep);
+    float** rowp = reinterpret_cast<float**>(ep + 32 * S::EPI_ROW);
     uint32_t acc = 0, acc_phase = 0;
+    constexpr int NI = 32 / RPI;
+    const int c4 = lane % LPR, rsub = lane / LPR;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const TileCoord tc = P::coord(g, item);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int row = warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * P::ACC_COLS;
+      __syncwarp();
+      rowp[lane] = P::row_ptr(g, tc, warp * 32 + lane);
+      __syncwarp();
+      bool waited = false;
 #pragma unroll 1
-      for (int c = 0; c < P::ACC_COLS; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + c, v);
-        P::store(g, tc, row, c, v);
+      for (int sg = 0; sg < NSEG; ++sg) {
+        if (!P::seg_valid(g, tc, sg)) continue;
+        // (1) destination of every float4 this lane will write + the operand its finishing op
+        //     needs from HBM (relu mask / bias): issued BEFORE the accumulator is waited for, so
+        //     the load latency hides behind the MMAs (first segment) / the TMEM read-out
+        const int64_t soff = P::seg_offset(g, tc, sg);
+        float* dstp[NI];
+        float4 aux[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          float* base = rowp[i * RPI + rsub];
+          dstp[i] = base != nullptr ? base + soff + c4 * 4 : nullptr;
+          aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (dstp[i] != nullptr && !P::col_valid(g, tc, sg * SEG + c4 * 4)) dstp[i] = nullptr;
+          if (dstp[i] != nullptr) aux[i] = P::aux_load(g, tc, dstp[i], sg * SEG + c4 * 4);
+        }
+        if (!waited) {
+          mbar_wait(&tfull[acc], acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * P::ACC_COLS;
+        // (2) TMEM -> registers (lane = row) -> staging
+#pragma unroll
+        for (int h = 0; h < SEG / 16; ++h) {
+          float v[16];
+          const uint32_t ta = taddr + P::acc_col(sg * SEG + h * 16);
+          if (P::LO_DELTA > 0) tmem_ld16_sum(ta, ta + P::LO_DELTA, v);
+          else tmem_ld16(ta, v);
+          float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __syncwarp();
+        // (3) coalesced finish: LPR lanes cover one row's SEG floats, RPI rows per instruction
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const float4 val = *reinterpret_cast<const float4*>(stg + (i * RPI + rsub) * (SEG + 4) + c4 * 4);
+          if (dstp[i] != nullptr)
+            *reinterpret_cast<float4*>(dstp[i]) = P::finish(g, val, aux[i]);
+        }
+        __syncwarp();
+      }
+      if (!waited) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -359,23 +436,26 @@ struct GemmArgs {
   int m_tiles, n_tiles;
 };
 
-// MN=false: both operand images K-major (sample-major sources are transposed in registers).
-// MN=true : requires A_TRANS && B_TRANS; the images are MN-major (the natural layout of
-//           sample-major sources: 8 consecutive rows of one k form the 16-B vector).
-template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI, bool MN = false>
-struct GemmPolicy {
+// Operand images follow the SOURCE layout, so no transposition ever happens in registers:
+//   X_TRANS=false (element (r,k) at src[r*ld + k], k contiguous) -> K-major image
+//   X_TRANS=true  (element (r,k) at src[k*ld + r], r contiguous) -> MN-major image
+// (the instruction descriptor carries one major-ness bit per operand).
+template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI>
+struct GemmPolicy : PolicyBase {
   using Args = GemmArgs;
   static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = 8, ACC_COLS = N_TILE_;
-  static constexpr int PROD_WARPS = (MN || (!A_TRANS && !B_TRANS)) ? 16 : 8;   // register budget
-  using TA = OperandTile<kTileM, KB>;
-  using TB = OperandTile<N_TILE, KB>;
-  // MN-major images: plane = 8 rows x KB k  -> (KB+1)*16 bytes per plane, ROWS/8 planes
+  static constexpr int OUT_COLS = N_TILE_, LO_DELTA = 0, SEG = 32;
+  static constexpr int PROD_WARPS = 16;
+  static __device__ __forceinline__ int acc_col(int c) { return c; }
+  // K-major image: plane (8 k) = (ROWS + KPAD) rows of 16 B; MN-major image: plane (8 rows) =
+  // (KB + 1) k of 16 B.  Pads make the producers' 8-byte stores bank-conflict-free.
+  static constexpr int KPAD = KB == 16 ? 4 : 2;
+  static constexpr int LBO_A = (kTileM + KPAD) * 16, LBO_B = (N_TILE + KPAD) * 16;
   static constexpr int PLANE_MN = (KB + 1) * 16;
-  static constexpr int A_BYTES = MN ? (kTileM / 8) * PLANE_MN : TA::BYTES;     // one image
-  static constexpr int B_BYTES = MN ? (N_TILE / 8) * PLANE_MN : TB::BYTES;
+  static constexpr int A_BYTES = A_TRANS ? (kTileM / 8) * PLANE_MN : (KB / 8) * LBO_A;   // one image
+  static constexpr int B_BYTES = B_TRANS ? (N_TILE / 8) * PLANE_MN : (KB / 8) * LBO_B;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int RES_BYTES = 0;
-  static_assert(!MN || (A_TRANS && B_TRANS), "MN-major images need sample-major sources");
 
   static __device__ __forceinline__ int num_items(const Args& g) {
     return g.m_tiles * g.n_tiles * g.k_splits;
@@ -394,77 +474,91 @@ struct GemmPolicy {
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
 
-  // MN-major image of a sample-major source: vector (k, row group rg) at rg*PLANE_MN + k*16
-  template <int ROWS>
-  static __device__ __forceinline__ void load_mn(uint8_t* hi, uint8_t* lo, const float* src,
+  // one operand tile [ROWS x KB]; every lane moves float4s, a warp instruction reads 512
+  // contiguous bytes (TRANS) or (KB/4)-lane row segments (K-major); 4 loads in flight per lane
+  template <int ROWS, bool TRANS, int LBO>
+  static __device__ __forceinline__ void load_op(uint8_t* hi, uint8_t* lo, const float* __restrict__ src,
                                                  int64_t ld, int r0, int rmax, int k0, int kmax,
-                                                 int lane) {
-    for (int c = lane; c < (ROWS / 8) * KB; c += 32) {
-      const int rg = c % (ROWS / 8), kk = c / (ROWS / 8);
-      const int r = r0 + rg * 8, k = k0 + kk;
-      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (r < rmax && k < kmax) {
-        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)k * ld + r);
-        const float4 x0 = p[0], x1 = p[1];
-        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
-        x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+                                                 int glane, int gsize) {
+    constexpr int Q = TRANS ? ROWS / 4 : KB / 4;            // float4 per contiguous run
+    constexpr int TOTAL = TRANS ? KB * Q : ROWS * Q;
+    constexpr int U = 8;
+    for (int f0 = glane; f0 < TOTAL; f0 += U * gsize) {
+      float4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int f = f0 + u * gsize;
+        const int a = f / Q, b = f % Q;                      // TRANS: (k, r4)   else: (row, k4)
+        const int r = r0 + (TRANS ? b * 4 : a), k = k0 + (TRANS ? a : b * 4);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < TOTAL && r < rmax && k < kmax)
+          x[u] = ldg4(TRANS ? src + (int64_t)k * ld + r : src + (int64_t)r * ld + k);
       }
-      store_chunk_split(hi, lo, rg * PLANE_MN + kk * 16, x);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int f = f0 + u * gsize;
+        if (f >= TOTAL) break;
+        const int a = f / Q, b = f % Q;
+        const int off = TRANS ? (b >> 1) * PLANE_MN + a * 16 + (b & 1) * 8
+                              : (b >> 1) * LBO + a * 16 + (b & 1) * 8;
+        store_half_split(hi, lo, off, x[u]);
+      }
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int lane, int) {
+                                                    uint8_t* st, int glane, int gsize, Prod&) {
     const int k0 = t.k_begin + s * KB;
     uint8_t* a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = b_hi + B_BYTES;
-    if (MN) {
-      load_mn<kTileM>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, lane);
-      load_mn<N_TILE>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, lane);
-    } else {
-      load_tile_f32<kTileM, KB, A_TRANS>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, lane);
-      load_tile_f32<N_TILE, KB, B_TRANS>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, lane);
-    }
+    load_op<kTileM, A_TRANS, LBO_A>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, glane, gsize);
+    load_op<N_TILE, B_TRANS, LBO_B>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, glane, gsize);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s,
                                                uint32_t st, uint32_t, uint32_t d_tmem) {
-    constexpr uint32_t idesc = make_idesc(N_TILE, MN, MN);
+    constexpr uint32_t idesc = make_idesc(N_TILE, A_TRANS, B_TRANS);
     const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
     for (int k16 = 0; k16 < KB / 16; ++k16) {
-      uint64_t da_hi, da_lo, db_hi, db_lo;
-      if (MN) {
-        const uint32_t o = k16 * 256;                 // 16 k rows of 16 B
-        da_hi = make_sdesc(a_hi + o, 128, PLANE_MN); da_lo = make_sdesc(a_lo + o, 128, PLANE_MN);
-        db_hi = make_sdesc(b_hi + o, 128, PLANE_MN); db_lo = make_sdesc(b_lo + o, 128, PLANE_MN);
-      } else {
-        const uint32_t ao = k16 * 2 * TA::LBO, bo = k16 * 2 * TB::LBO;
-        da_hi = make_sdesc(a_hi + ao, TA::LBO); da_lo = make_sdesc(a_lo + ao, TA::LBO);
-        db_hi = make_sdesc(b_hi + bo, TB::LBO); db_lo = make_sdesc(b_lo + bo, TB::LBO);
-      }
+      const uint32_t ao = A_TRANS ? k16 * 256 : k16 * 2 * LBO_A;
+      const uint32_t bo = B_TRANS ? k16 * 256 : k16 * 2 * LBO_B;
+      const uint64_t da_hi = A_TRANS ? make_sdesc(a_hi + ao, 128, PLANE_MN) : make_sdesc(a_hi + ao, LBO_A);
+      const uint64_t da_lo = A_TRANS ? make_sdesc(a_lo + ao, 128, PLANE_MN) : make_sdesc(a_lo + ao, LBO_A);
+      const uint64_t db_hi = B_TRANS ? make_sdesc(b_hi + bo, 128, PLANE_MN) : make_sdesc(b_hi + bo, LBO_B);
+      const uint64_t db_lo = B_TRANS ? make_sdesc(b_lo + bo, 128, PLANE_MN) : make_sdesc(b_lo + bo, LBO_B);
       umma_f16(d_tmem, da_hi, db_hi, idesc, (s | k16) != 0 ? 1u : 0u);
       umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
       umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
     }
   }
-  static __device__ __forceinline__ void store(const Args& g, const TileCoord& t, int row, int c,
-                                               const float (&v)[16]) {
-    const int m = t.mt * kTileM + row, n = t.nt * N_TILE + c;
-    if (m >= g.M || n >= g.N) return;
-    float* d = g.D + (int64_t)t.ks * g.M * g.ldd + (int64_t)m * g.ldd + n;
-    const float* x = EPI == EPI_MASK ? g.extra + (int64_t)m * g.ldd + n : g.extra + n;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      if (EPI == EPI_BIAS_RELU) {
-        const float4 bb = *reinterpret_cast<const float4*>(x + 4 * q);
-        o.x = fmaxf(o.x + bb.x, 0.f); o.y = fmaxf(o.y + bb.y, 0.f);
-        o.z = fmaxf(o.z + bb.z, 0.f); o.w = fmaxf(o.w + bb.w, 0.f);
-      } else if (EPI == EPI_MASK) {
-        const float4 mm = *reinterpret_cast<const float4*>(x + 4 * q);
-        o.x = mm.x > 0.f ? o.x : 0.f; o.y = mm.y > 0.f ? o.y : 0.f;
-        o.z = mm.z > 0.f ? o.z : 0.f; o.w = mm.w > 0.f ? o.w : 0.f;
-      }
-      *reinterpret_cast<float4*>(d + 4 * q) = o;
+  // ---- epilogue: row m of the tile is N_TILE contiguous floats of D
+  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
+    const int m = t.mt * kTileM + row;
+    if (m >= g.M) return nullptr;
+    return g.D + (int64_t)t.ks * g.M * g.ldd + (int64_t)m * g.ldd + t.nt * N_TILE;
+  }
+  static __device__ __forceinline__ bool seg_valid(const Args& g, const TileCoord& t, int sg) {
+    return t.nt * N_TILE + sg * SEG < g.N;
+  }
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int sg) {
+    return sg * SEG;
+  }
+  static __device__ __forceinline__ bool col_valid(const Args& g, const TileCoord& t, int col) {
+    return t.nt * N_TILE + col < g.N;
+  }
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord& t, const float* dst,
+                                                    int col) {
+    if (EPI == EPI_BIAS_RELU) return ldg4(g.extra + t.nt * N_TILE + col);
+    if (EPI == EPI_MASK) return ldg4(g.extra + (dst - g.D));
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  static __device__ __forceinline__ float4 finish(const Args&, float4 o, float4 x) {
+    if (EPI == EPI_BIAS_RELU) {
+      o.x = fmaxf(o.x + x.x, 0.f); o.y = fmaxf(o.y + x.y, 0.f);
+      o.z = fmaxf(o.z + x.z, 0.f); o.w = fmaxf(o.w + x.w, 0.f);
+    } else if (EPI == EPI_MASK) {
+      o.x = x.x > 0.f ? o.x : 0.f; o.y = x.y > 0.f ? o.y : 0.f;
+      o.z = x.z > 0.f ? o.z : 0.f; o.w = x.w > 0.f ? o.w : 0.f;
     }
+    return o;
   }
 };
 
