@@ -3,9 +3,9 @@
 // expression, truncated) -> cv2 INTER_LINEAR 84x84 (fixed point) -> ring slot.
 //
 // Layout / data flow per frame (one persistent CTA per SM, 2-stage TMA pipeline):
-//   HBM --cp.async.bulk (84 x 960 B: the 168 source rows cv2 actually reads)--> smem raw[stage]
-//   raw --luma, 8 px / thread-iteration, dp4a--> smem Y [168][160] u8
-//   Y   --2x2 fixed-point taps--> smem out [84*84] u8 --cp.async.bulk--> ring[b][slot]
+//   HBM --cp.async.bulk (43 copies: the 168 source rows cv2 actually reads)--> smem raw[stage]
+//   raw --luma, 8 px / lane-iteration, dp4a--> smem Y [168][160] u8 (8 rows private to a warp)
+//   Y   --2x2 fixed-point taps--> smem out[ob] [84*84] u8 --cp.async.bulk--> ring[b][slot]
 // Algorithmic HBM bytes per frame: 80 640 read + 7 056 written (x replicate).
 //
 // Luma: the reference computes (0.2126*R + 0.7152*G) + 0.0722*B in float64 and truncates.
@@ -26,11 +26,10 @@ constexpr int kRawBytes = kS * kPairBytes;        // 80640 per frame
 constexpr int kYBytes = 2 * kS * kW;              // 26880
 constexpr int kFrameBytes = kH * kW * 3;          // 100800
 constexpr int kBitmapWords = 65536 / 32;          // 2048
-constexpr int kThreads = 512;
 
 struct TapTables {
   uint32_t x[kS];      // sx | c0 << 8 | c1 << 20
-  uint32_t y[kS];      // sy | b0 << 8 | b1 << 20
+  uint32_t y[kS];      // sy | b0 << 8 | b1 << 20   (sy must be 0,3,5,8,...: checked at init)
 };
 __constant__ TapTables c_taps;
 __device__ uint32_t g_luma_fix[kBitmapWords];
@@ -67,14 +66,25 @@ static void linear_taps(int src, int dst, uint32_t* packed) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------
+// One persistent CTA per SM: 21 compute warps + 1 copy warp, no block-wide barrier in the loop.
+//   copy warp   : per frame 43 cp.async.bulk loads (the 168 source rows cv2 reads: rows 5k+2 are
+//                 never touched; rows 5k+3 .. 5k+6 are contiguous, so one 1920-B copy feeds two
+//                 output rows) into raw[stage]; later the 7056-B plane store(s) out[ob] -> ring.
+//   compute warp w owns output rows 4w .. 4w+3: luma of its 8 source rows (160 groups of 8 px =
+//                 5 full warp iterations) into its private Y slice, then the 4 x 84 outputs with
+//                 the x taps of its 3 columns held in registers.  Hand-offs are mbarriers:
+//                 full/empty per raw stage, out_full/out_empty per output buffer.
+constexpr int kComputeWarps = kS / 4;                       // 21
+constexpr int kK1Threads = (kComputeWarps + 1) * 32;        // 704
+constexpr int kCopies = 43;
+
 struct __align__(16) K1Smem {
   uint8_t raw[2][kRawBytes];
   uint8_t Y[kYBytes];
-  uint8_t out[kPlane];
+  uint8_t out[2][kPlane];
   uint32_t fix[kBitmapWords];
-  uint32_t xtab[kS];
   uint32_t ytab[kS];
-  uint64_t full[2];
+  uint64_t full[2], empty[2], out_full[2], out_empty[2];
 };
 
 __device__ __forceinline__ uint32_t luma8(uint32_t px /* R | G<<8 | B<<16 */, const uint32_t* fix) {
@@ -87,90 +97,116 @@ __device__ __forceinline__ uint32_t luma8(uint32_t px /* R | G<<8 | B<<16 */, co
   return q;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kK1Threads, 1)
 preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring, int num_envs,
                   int ring_slots, int slot, int replicate) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < kBitmapWords; i += kThreads) sm.fix[i] = g_luma_fix[i];
-  if (tid < kS) {
-    sm.xtab[tid] = c_taps.x[tid];
-    sm.ytab[tid] = c_taps.y[tid];
-  }
+  for (int i = tid; i < kBitmapWords; i += kK1Threads) sm.fix[i] = g_luma_fix[i];
+  if (tid < kS) sm.ytab[tid] = c_taps.y[tid];
   if (tid == 0) {
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&sm.full[k], 1);
+      mbar_init(&sm.empty[k], kComputeWarps);
+      mbar_init(&sm.out_full[k], kComputeWarps);
+      mbar_init(&sm.out_empty[k], 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
+  const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  // producer: warp 0 issues the 84 row-pair copies of one frame
-  auto issue = [&](int env, int stage) {
-    if (tid < 32) {
-      if (tid == 0) mbar_expect_tx(&sm.full[stage], kRawBytes);
-      __syncwarp();
-      const uint8_t* src = frames + (size_t)env * kFrameBytes;
-      for (int dy = tid; dy < kS; dy += 32) {
-        const uint32_t sy = sm.ytab[dy] & 0xFFu;
-        bulk_g2s(&sm.raw[stage][dy * kPairBytes], src + sy * kRowBytes, kPairBytes, &sm.full[stage]);
+  if (warp == kComputeWarps) {
+    // ===================== copy warp =====================
+    for (int f = 0; f <= frames_here; ++f) {
+      if (f < frames_here) {                                 // loads of frame f
+        const int stage = f & 1;
+        mbar_wait(&sm.empty[stage], ((f >> 1) & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(&sm.full[stage], kRawBytes);
+        __syncwarp();
+        const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
+        uint8_t* dst = sm.raw[stage];
+        for (int m = lane; m < kCopies; m += 32) {
+          // m = 0: rows 0,1 (dy 0);  m = 1..41: rows 5m-2 .. 5m+1 (dy 2m-1, 2m);  m = 42: rows 208,209
+          const int row = m == 0 ? 0 : 5 * m - 2, dy = m == 0 ? 0 : 2 * m - 1;
+          const uint32_t bytes = (m == 0 || m == kCopies - 1) ? kPairBytes : 2 * kPairBytes;
+          bulk_g2s(dst + dy * kPairBytes, src + row * kRowBytes, bytes, &sm.full[stage]);
+        }
       }
+      if (f >= 1 && lane == 0) {                             // store of frame f-1
+        const int g = f - 1, ob = g & 1;
+        mbar_wait(&sm.out_full[ob], (g >> 1) & 1);
+        uint8_t* dst = ring + ((size_t)(blockIdx.x + (size_t)g * gridDim.x) * ring_slots) * kPlane;
+        for (int r = 0; r < replicate; ++r) {
+          int sl = slot + r;
+          if (sl >= ring_slots) sl -= ring_slots;
+          bulk_s2g(dst + (size_t)sl * kPlane, sm.out[ob], kPlane);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();                                 // smem has been read: buffer reusable
+        mbar_arrive(&sm.out_empty[ob]);
+      }
+      __syncwarp();
     }
-  };
+    if (lane == 0) bulk_wait<0>();
+    return;
+  }
 
-  int it = 0;
-  if ((int)blockIdx.x < num_envs) issue(blockIdx.x, 0);
-  for (int env = blockIdx.x; env < num_envs; env += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int next = env + gridDim.x;
-    if (next < num_envs) issue(next, stage ^ 1);             // stage^1 was drained last iteration
-    mbar_wait(&sm.full[stage], (it >> 1) & 1);
-
-    // phase 1: luma of the 168 x 160 staged pixels, 8 pixels (24 B) per thread-iteration
-    const uint2* raw2 = reinterpret_cast<const uint2*>(sm.raw[stage]);
-    for (int g = tid; g < kYBytes / 8; g += kThreads) {
-      const uint2 a = raw2[3 * g], b = raw2[3 * g + 1], c = raw2[3 * g + 2];
+  // ===================== compute warps =====================
+  uint32_t xt[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) xt[p] = c_taps.x[min(p * 32 + lane, kS - 1)];
+  uint8_t* Yw = sm.Y + warp * (8 * kW);
+  for (int f = 0; f < frames_here; ++f) {
+    const int stage = f & 1, ob = f & 1;
+    mbar_wait(&sm.full[stage], (f >> 1) & 1);
+    // phase A: luma of this warp's 8 source rows, 8 pixels (24 B) per lane-iteration
+    const uint2* raw2 = reinterpret_cast<const uint2*>(sm.raw[stage] + warp * (4 * kPairBytes));
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int u = it * 32 + lane;
+      const uint2 a = raw2[3 * u], b = raw2[3 * u + 1], c = raw2[3 * u + 2];
       const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y, w4 = c.x, w5 = c.y;
       uint32_t y0, y1;
       y0 = luma8(w0 & 0x00FFFFFFu, sm.fix);
       y0 |= luma8(__byte_perm(w0, w1, 0x4543), sm.fix) << 8;    // bytes 3,4,5
-      y0 |= luma8(__byte_perm(w1, w2, 0x4432), sm.fix) << 16;   // bytes 6,7,8   (w1.2,w1.3,w2.0)
+      y0 |= luma8(__byte_perm(w1, w2, 0x4432), sm.fix) << 16;   // bytes 6,7,8
       y0 |= luma8(w2 >> 8, sm.fix) << 24;                       // bytes 9,10,11
       y1 = luma8(w3 & 0x00FFFFFFu, sm.fix);                     // bytes 12,13,14
       y1 |= luma8(__byte_perm(w3, w4, 0x4543), sm.fix) << 8;    // bytes 15,16,17
       y1 |= luma8(__byte_perm(w4, w5, 0x4432), sm.fix) << 16;   // bytes 18,19,20
       y1 |= luma8(w5 >> 8, sm.fix) << 24;                       // bytes 21,22,23
-      reinterpret_cast<uint2*>(sm.Y)[g] = make_uint2(y0, y1);
+      reinterpret_cast<uint2*>(Yw)[u] = make_uint2(y0, y1);
     }
-    if (tid == 0) bulk_wait_read<0>();                          // previous store has read sm.out
-    __syncthreads();
-
-    // phase 2: cv2 fixed-point bilinear, one output pixel per thread-iteration
-    for (int idx = tid; idx < kPlane; idx += kThreads) {
-      const int dy = idx / kS, dx = idx - dy * kS;
-      const uint32_t xt = sm.xtab[dx], yt = sm.ytab[dy];
-      const int sx = xt & 0xFF, c0 = (xt >> 8) & 0xFFF, c1 = xt >> 20;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);               // raw[stage] may be refilled
+    // phase B: cv2 fixed-point bilinear for output rows 4*warp .. 4*warp+3
+    mbar_wait(&sm.out_empty[ob], ((f >> 1) & 1) ^ 1);
+    uint8_t* out = sm.out[ob];
+#pragma unroll
+    for (int ry = 0; ry < 4; ++ry) {
+      const int dy = warp * 4 + ry;
+      const uint32_t yt = sm.ytab[dy];
       const int b0 = (yt >> 8) & 0xFFF, b1 = yt >> 20;
-      const uint8_t* r0 = sm.Y + (2 * dy) * kW + sx;
-      const int h0 = r0[0] * c0 + r0[1] * c1;
-      const int h1 = r0[kW] * c0 + r0[kW + 1] * c1;
-      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      sm.out[idx] = (uint8_t)v;
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      uint8_t* dst = ring + ((size_t)env * ring_slots) * kPlane;
-      for (int r = 0; r < replicate; ++r) {
-        int s = slot + r;
-        if (s >= ring_slots) s -= ring_slots;
-        bulk_s2g(dst + (size_t)s * kPlane, sm.out, kPlane);
+      const uint8_t* row = Yw + (2 * ry) * kW;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const int dx = p * 32 + lane;
+        if (dx < kS) {
+          const int sx = xt[p] & 0xFF, c0 = (xt[p] >> 8) & 0xFFF, c1 = xt[p] >> 20;
+          const uint8_t* r0 = row + sx;
+          const int h0 = r0[0] * c0 + r0[1] * c1;
+          const int h1 = r0[kW] * c0 + r0[kW + 1] * c1;
+          out[dy * kS + dx] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+        }
       }
-      bulk_commit();
     }
+    fence_proxy_async_smem();                                   // generic writes -> bulk store
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.out_full[ob]);
   }
-  if (tid == 0) bulk_wait<0>();
 }
 
 // ---- History.get / reset -----------------------------------------------------------------
@@ -212,6 +248,13 @@ int preprocess_init(int device) {
       return ARL_ERR_UNSUPPORTED;
     }
   }
+  for (int d = 0; d < kS; ++d) {
+    // the copy warp relies on sy(d) = 5*(d/2) + 3*(d%2): rows 5k+2 unused, 5k+3..5k+6 contiguous
+    if ((int)(t.y[d] & 0xFF) != 5 * (d / 2) + 3 * (d % 2)) {
+      set_error("arl_init: unexpected vertical tap pattern at row %d", d);
+      return ARL_ERR_UNSUPPORTED;
+    }
+  }
   ARL_CUDA(cudaMemcpyToSymbol(c_taps, &t, sizeof(t)));
   void* fix = nullptr;
   ARL_CUDA(cudaGetSymbolAddress(&fix, g_luma_fix));
@@ -244,7 +287,7 @@ extern "C" int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num
               "arl_preprocess_push: frames and ring must be 16-byte aligned");
   if (num_envs == 0) return ARL_OK;
   const int grid = num_envs < num_sms() ? num_envs : num_sms();
-  preprocess_kernel<<<grid, kThreads, sizeof(K1Smem), (cudaStream_t)stream>>>(
+  preprocess_kernel<<<grid, kK1Threads, sizeof(K1Smem), (cudaStream_t)stream>>>(
       frames, ring, num_envs, ring_slots, slot, replicate);
   ARL_LAUNCH_CHECK("preprocess_kernel");
   return ARL_OK;
