@@ -239,6 +239,7 @@ struct Conv1Fwd : tc::PolicyBase {
   // resident W1 image: rows = [16 co hi | 16 co lo] (N = 32), 32 k-chunk planes
   static constexpr int PLB = 33 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
   static constexpr int ACC_COLS = 32, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
+  static constexpr bool HAS_AUX = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -306,6 +307,7 @@ struct Conv2Fwd : tc::PolicyBase {
   // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
   static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
+  static constexpr bool HAS_AUX = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -324,7 +326,7 @@ struct Conv2Fwd : tc::PolicyBase {
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
                                                     uint8_t* st, int glane, int gsize, Prod&) {
-    stream_x2<TROWS, PL, 10, false>(st, st + IMG, g.a1, t.mt * 128, g.num_samples, glane, gsize);
+    stream_x2<TROWS, PL, 8, false>(st, st + IMG, g.a1, t.mt * 128, g.num_samples, glane, gsize);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
@@ -371,11 +373,14 @@ struct Conv2Dgrad : tc::PolicyBase {
   using Args = Conv2DgradArgs;
   static constexpr int GW = 11, GROWS = 121, TROWS = 140;
   static constexpr int PL = 146 * 16, IMG = 4 * PL;           // 32 co = 4 chunks
-  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = 2 * IMG;
+  // the relu-mask epilogue waits on HBM: two epilogue sets; 8 producer warps (17 warps in all ->
+  // 96 registers per thread, 8 float4 mask loads in flight per epilogue lane)
+  static constexpr int EPI_SETS = 2, PROD_WARPS = 8, STAGES = 4, STAGE_BYTES = 2 * IMG;
   // resident W2^T image: rows = part*64 + cls*16 + c (N = 128: the 4 parity classes share the A
   // tile of a tap, and lo follows hi), 16 k-chunk planes (tap*4 + co8)
   static constexpr int PLB = 129 * 16, RES_BYTES = 16 * PLB;
   static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 64, SEG = 32;   // 4 classes x 16 ch
+  static constexpr bool HAS_AUX = true, AUX_ROW_INVARIANT = false;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -395,7 +400,7 @@ struct Conv2Dgrad : tc::PolicyBase {
                                                     uint8_t* st, int glane, int gsize, Prod&) {
     float unused[4];
     const int z0 = t.mt * 128;
-    stream_pixels<GridZ, 8, TROWS, PL, 10, false>(st, st + IMG, g.dy2, z0, z0 + TROWS, g.num_samples,
+    stream_pixels<GridZ, 8, TROWS, PL, 7, false>(st, st + IMG, g.dy2, z0, z0 + TROWS, g.num_samples,
                                                   glane, gsize, unused);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
@@ -493,7 +498,7 @@ struct Conv2Wgrad : tc::PolicyBase {
     uint8_t* a_hi = st, *a_lo = st + A_IMG, *b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
     // A: X2 rows p0 .. p0+139; planes 0..7 hold row r at r*16, planes 8..15 the same image shifted
     // by one row (tap b = 1)
-    stream_x2<TROWS, PLA, 10, true>(a_hi, a_lo, g.a1, p0, g.num_samples, glane, gsize);
+    stream_x2<TROWS, PLA, 5, true>(a_hi, a_lo, g.a1, p0, g.num_samples, glane, gsize);
     // B: dy2 on the 10-wide grid, zero at y'=9 / x'=9 and outside [k_begin, k_end)
     stream_pixels<GridDy2, 8, 128, PLB, 5, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
                                                  gsize, ps.acc);

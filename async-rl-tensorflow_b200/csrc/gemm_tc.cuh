@@ -34,11 +34,13 @@
 namespace arl {
 namespace tc {
 
-constexpr int kEpiWarps = 4;
 constexpr int kTileM = 128;
-// per policy: PROD_WARPS producer warps (8 or 16); warp layout = [4 epilogue | producers | MMA]
+// per policy: EPI_SETS sets of 4 epilogue warps (set e drains accumulator stage e when there are
+// two: the read-outs of consecutive tiles overlap, which hides the HBM latency of a mask-reading
+// epilogue), PROD_WARPS producer warps; warp layout = [epilogue | producers | MMA]
+template <class P> __host__ __device__ constexpr int epi_warps() { return 4 * P::EPI_SETS; }
 template <class P> __host__ __device__ constexpr int prod_threads() { return P::PROD_WARPS * 32; }
-template <class P> __host__ __device__ constexpr int cta_threads() { return (kEpiWarps + P::PROD_WARPS + 1) * 32; }
+template <class P> __host__ __device__ constexpr int cta_threads() { return (epi_warps<P>() + P::PROD_WARPS + 1) * 32; }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -90,6 +92,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// hi-part + lo-part accumulators, 8 columns: two loads in flight, one wait
+__device__ __forceinline__ void tmem_ld8_sum(uint32_t taddr_a, uint32_t taddr_b, float (&v)[8]) {
+  uint32_t r[8], q[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr_a)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]),
+                 "=r"(q[7])
+               : "r"(taddr_b)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+}
 // two 16-column loads in flight, one wait; v += w (hi-part + lo-part accumulators)
 __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr_a, uint32_t taddr_b, float (&v)[16]) {
   uint32_t r[16], q[16];
@@ -185,6 +215,9 @@ struct TileCoord {
 // Per-thread producer state that lives across the stages of one work item (e.g. the running
 // column sums of the operand a producer streams through its registers anyway = a bias gradient).
 struct PolicyBase {
+  static constexpr int EPI_SETS = 1;
+  static constexpr bool HAS_AUX = false;       // finish() needs an operand from HBM (bias, relu mask)
+  static constexpr bool AUX_ROW_INVARIANT = true;   // ... that depends on the column only (bias)
   struct Prod {};
   static __device__ __forceinline__ void prod_begin(Prod&) {}
   template <class Args>
@@ -237,13 +270,14 @@ struct Smem {
   static constexpr int EPI_OFF = BAR_OFF + 256;
   static constexpr int EPI_ROW = (P::SEG + 4) * 4;              // staged row, padded: conflict-free
   static constexpr int EPI_WARP = 32 * EPI_ROW + 32 * 8;        // staging + 32 row pointers
-  static constexpr int TOTAL = EPI_OFF + kEpiWarps * EPI_WARP;
+  static constexpr int TOTAL = EPI_OFF + epi_warps<P>() * EPI_WARP;
 };
 
 template <class P>
 __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Args g) {
   using S = Smem<P>;
   constexpr int STAGES = P::STAGES, WPS = P::PROD_WARPS / STAGES;  // producer warps per stage
+  constexpr int kEpiWarps = epi_warps<P>();
   constexpr int kMmaWarp = kEpiWarps + P::PROD_WARPS;
   static_assert(P::PROD_WARPS % STAGES == 0, "producer warps must divide evenly over the stages");
   static_assert(STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
@@ -267,7 +301,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], kEpiWarps * 32);
+      mbar_init(&tempty[a], 128);
     }
     fence_mbar_init();
   }
@@ -305,12 +339,12 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int i = 0;
-      uint32_t acc = 0, acc_phase = 0;
+      int i = 0, k = 0;                                  // k = this CTA's running tile count
       const uint32_t res_addr = smem_u32(res);
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
         const TileCoord tc = P::coord(g, item);
         const int ns = P::num_stages(g, tc);
+        const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * P::ACC_COLS;
@@ -322,8 +356,6 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           umma_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
         }
         umma_commit(&tfull[acc]);            // accumulator ready for the epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -333,13 +365,15 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     uint8_t* ep = smem + S::EPI_OFF + warp * S::EPI_WARP;
     float* stg = reinterpret_cast<float*>(ep);
     float** rowp = reinterpret_cast<float**>(ep + 32 * S::EPI_ROW);
-    uint32_t acc = 0, acc_phase = 0;
     constexpr int NI = 32 / RPI;
-    const int c4 = lane % LPR, rsub = lane / LPR;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int c4 = lane % LPR, rsub = lane / LPR, quad = warp & 3, set = warp >> 2;
+    int k = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+      if (P::EPI_SETS == 2 && (k & 1) != set) continue;
+      const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
       const TileCoord tc = P::coord(g, item);
       __syncwarp();
-      rowp[lane] = P::row_ptr(g, tc, warp * 32 + lane);
+      rowp[lane] = P::row_ptr(g, tc, quad * 32 + lane);
       __syncwarp();
       bool waited = false;
 #pragma unroll 1
@@ -348,41 +382,47 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
         // (1) destination of every float4 this lane will write + the operand its finishing op
         //     needs from HBM (relu mask / bias): issued BEFORE the accumulator is waited for, so
         //     the load latency hides behind the MMAs (first segment) / the TMEM read-out
-        const int64_t soff = P::seg_offset(g, tc, sg);
-        float* dstp[NI];
+        const int64_t soff = P::seg_offset(g, tc, sg) + c4 * 4;
+        const bool cok = P::col_valid(g, tc, sg * SEG + c4 * 4);
         float4 aux[NI];
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-          float* base = rowp[i * RPI + rsub];
-          dstp[i] = base != nullptr ? base + soff + c4 * 4 : nullptr;
+          const float* base = rowp[i * RPI + rsub];
           aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (dstp[i] != nullptr && !P::col_valid(g, tc, sg * SEG + c4 * 4)) dstp[i] = nullptr;
-          if (dstp[i] != nullptr) aux[i] = P::aux_load(g, tc, dstp[i], sg * SEG + c4 * 4);
+          if (P::HAS_AUX && !P::AUX_ROW_INVARIANT && cok && base != nullptr)
+            aux[i] = P::aux_load(g, tc, base + soff, sg * SEG + c4 * 4);
+        }
+        if (P::HAS_AUX && P::AUX_ROW_INVARIANT && cok) {         // e.g. a bias: one load serves all rows
+          const float4 a = P::aux_load(g, tc, nullptr, sg * SEG + c4 * 4);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) aux[i] = a;
         }
         if (!waited) {
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
           waited = true;
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * P::ACC_COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * P::ACC_COLS;
         // (2) TMEM -> registers (lane = row) -> staging
 #pragma unroll
-        for (int h = 0; h < SEG / 16; ++h) {
-          float v[16];
-          const uint32_t ta = taddr + P::acc_col(sg * SEG + h * 16);
-          if (P::LO_DELTA > 0) tmem_ld16_sum(ta, ta + P::LO_DELTA, v);
-          else tmem_ld16(ta, v);
-          float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int h = 0; h < SEG / 8; ++h) {
+          float v[8];
+          const int c = sg * SEG + h * 8;
+          const uint32_t ta = taddr + P::acc_col(c & ~15) + (c & 15);
+          if (P::LO_DELTA > 0) tmem_ld8_sum(ta, ta + P::LO_DELTA, v);
+          else tmem_ld8(ta, v);
+          float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 8);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
         __syncwarp();
         // (3) coalesced finish: LPR lanes cover one row's SEG floats, RPI rows per instruction
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const float4 val = *reinterpret_cast<const float4*>(stg + (i * RPI + rsub) * (SEG + 4) + c4 * 4);
-          if (dstp[i] != nullptr)
-            *reinterpret_cast<float4*>(dstp[i]) = P::finish(g, val, aux[i]);
+          float* base = rowp[i * RPI + rsub];
+          if (cok && base != nullptr)
+            *reinterpret_cast<float4*>(base + soff) = P::finish(g, val, aux[i]);
         }
         __syncwarp();
       }
@@ -392,8 +432,6 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -443,9 +481,13 @@ struct GemmArgs {
 template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI>
 struct GemmPolicy : PolicyBase {
   using Args = GemmArgs;
-  static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = 8, ACC_COLS = N_TILE_;
+  static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = EPI == EPI_MASK ? 4 : 8, ACC_COLS = N_TILE_;
   static constexpr int OUT_COLS = N_TILE_, LO_DELTA = 0, SEG = 32;
-  static constexpr int PROD_WARPS = 16;
+  static constexpr bool HAS_AUX = EPI != EPI_PLAIN, AUX_ROW_INVARIANT = EPI != EPI_MASK;
+  // the relu-mask epilogue waits on HBM: two epilogue sets, and 8 producer warps so that the 17
+  // warps get 96 registers per thread (8 float4 mask loads in flight per epilogue lane)
+  static constexpr int EPI_SETS = EPI == EPI_MASK ? 2 : 1;
+  static constexpr int PROD_WARPS = EPI == EPI_MASK ? 8 : 16;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   // K-major image: plane (8 k) = (ROWS + KPAD) rows of 16 B; MN-major image: plane (8 rows) =
   // (KB + 1) k of 16 B.  Pads make the producers' 8-byte stores bank-conflict-free.
@@ -482,7 +524,7 @@ struct GemmPolicy : PolicyBase {
                                                  int glane, int gsize) {
     constexpr int Q = TRANS ? ROWS / 4 : KB / 4;            // float4 per contiguous run
     constexpr int TOTAL = TRANS ? KB * Q : ROWS * Q;
-    constexpr int U = 8;
+    constexpr int U = PROD_WARPS == 16 ? 6 : 8;            // 80 vs 128 registers per thread
     for (int f0 = glane; f0 < TOTAL; f0 += U * gsize) {
       float4 x[U];
 #pragma unroll
