@@ -516,43 +516,46 @@ struct GemmPolicy : PolicyBase {
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
 
-  // one operand tile [ROWS x KB]; every lane moves float4s, a warp instruction reads 512
-  // contiguous bytes (TRANS) or (KB/4)-lane row segments (K-major); 4 loads in flight per lane
+  // one operand tile [ROWS x KB]; every lane moves float4s: a warp instruction reads 512
+  // contiguous bytes (TRANS) or (KB/4)-lane row segments (K-major).  A lane keeps its position b
+  // inside the contiguous run and walks the runs with a constant stride, so the loop body is
+  // load / split / two 8-byte stores plus three additions; U loads are in flight per lane.
+  static constexpr int GS = PROD_WARPS / STAGES * 32;       // lanes that fill one stage
   template <int ROWS, bool TRANS, int LBO>
   static __device__ __forceinline__ void load_op(uint8_t* hi, uint8_t* lo, const float* __restrict__ src,
                                                  int64_t ld, int r0, int rmax, int k0, int kmax,
-                                                 int glane, int gsize) {
+                                                 int glane) {
     constexpr int Q = TRANS ? ROWS / 4 : KB / 4;            // float4 per contiguous run
-    constexpr int TOTAL = TRANS ? KB * Q : ROWS * Q;
-    constexpr int U = PROD_WARPS == 16 ? 6 : 8;            // 80 vs 128 registers per thread
-    for (int f0 = glane; f0 < TOTAL; f0 += U * gsize) {
+    constexpr int NA = TRANS ? KB : ROWS;                   // number of runs
+    static_assert(GS % Q == 0 && NA % (GS / Q) == 0, "stage lanes must tile the operand");
+    constexpr int STEP = GS / Q, N = NA / STEP, U = N < 8 ? N : 8;
+    static_assert(N % U == 0, "load batches");
+    const int b = glane % Q, a0 = glane / Q;                // TRANS: (k, r4) = (a, b)  else (row, k4)
+    const bool bok = TRANS ? (r0 + b * 4 < rmax) : (k0 + b * 4 < kmax);
+    const int alim = (TRANS ? kmax - k0 : rmax - r0) - a0;  // run a0 + j*STEP exists iff j*STEP < alim
+    const float* p = src + (int64_t)((TRANS ? k0 : r0) + a0) * ld + (TRANS ? r0 : k0) + b * 4;
+    const int64_t pstep = (int64_t)STEP * ld;
+    int off = (b >> 1) * (TRANS ? PLANE_MN : LBO) + a0 * 16 + (b & 1) * 8;
+#pragma unroll 1
+    for (int j0 = 0; j0 < N; j0 += U) {
       float4 x[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int f = f0 + u * gsize;
-        const int a = f / Q, b = f % Q;                      // TRANS: (k, r4)   else: (row, k4)
-        const int r = r0 + (TRANS ? b * 4 : a), k = k0 + (TRANS ? a : b * 4);
         x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < TOTAL && r < rmax && k < kmax)
-          x[u] = ldg4(TRANS ? src + (int64_t)k * ld + r : src + (int64_t)r * ld + k);
+        if (bok && (j0 + u) * STEP < alim) x[u] = ldg4(p + (int64_t)u * pstep);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int f = f0 + u * gsize;
-        if (f >= TOTAL) break;
-        const int a = f / Q, b = f % Q;
-        const int off = TRANS ? (b >> 1) * PLANE_MN + a * 16 + (b & 1) * 8
-                              : (b >> 1) * LBO + a * 16 + (b & 1) * 8;
-        store_half_split(hi, lo, off, x[u]);
-      }
+      for (int u = 0; u < U; ++u) store_half_split(hi, lo, off + u * (STEP * 16), x[u]);
+      p += (int64_t)U * pstep;
+      off += U * STEP * 16;
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int gsize, Prod&) {
+                                                    uint8_t* st, int glane, int, Prod&) {
     const int k0 = t.k_begin + s * KB;
     uint8_t* a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = b_hi + B_BYTES;
-    load_op<kTileM, A_TRANS, LBO_A>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, glane, gsize);
-    load_op<N_TILE, B_TRANS, LBO_B>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, glane, gsize);
+    load_op<kTileM, A_TRANS, LBO_A>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, glane);
+    load_op<N_TILE, B_TRANS, LBO_B>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, glane);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s,
                                                uint32_t st, uint32_t, uint32_t d_tmem) {
