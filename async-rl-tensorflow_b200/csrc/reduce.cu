@@ -4,6 +4,7 @@
 
 namespace arl {
 
+// many elements, few partials (fc wgrad: 663 552 x 7): one thread per element
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, float* __restrict__ out,
                                        int num_partials, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,9 +21,40 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, float
   out[i] = (a0 + a1) + (a2 + a3);
 }
 
+// few elements, many partials (conv wgrads: 4096 / 8192 x 148; conv bias grads: 16 / 32 x 2368):
+// a block owns 32 elements; 32 slices of the partial index are summed in parallel (slice s takes
+// p = s, s+32, ...) and combined by a fixed-order tree, so the result does not depend on timing
+__global__ void __launch_bounds__(1024)
+reduce_partials_wide_kernel(const float* __restrict__ partials, float* __restrict__ out,
+                            int num_partials, int n) {
+  __shared__ float red[32][33];
+  const int e = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int p = s;
+    for (; p + 32 < num_partials; p += 64) {
+      a0 += partials[(size_t)p * n + i];
+      a1 += partials[(size_t)(p + 32) * n + i];
+    }
+    if (p < num_partials) a0 += partials[(size_t)p * n + i];
+  }
+  red[s][e] = a0 + a1;
+  __syncthreads();
+#pragma unroll
+  for (int h = 16; h > 0; h >>= 1) {
+    if (s < h) red[s][e] += red[s + h][e];
+    __syncthreads();
+  }
+  if (s == 0 && i < n) out[i] = red[0][e];
+}
+
 int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream) {
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, num_partials, n);
+  if (n >= 65536 || num_partials < 16)
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, num_partials, n);
+  else
+    reduce_partials_wide_kernel<<<(n + 31) / 32, 1024, 0, stream>>>(partials, out, num_partials, n);
   ARL_LAUNCH_CHECK("reduce_partials_kernel");
   return ARL_OK;
 }

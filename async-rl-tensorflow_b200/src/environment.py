@@ -211,9 +211,23 @@ class GymEnvironment(Environment):
     def act(self, action, is_training=True, fused=False):
         """environment.py:78-96, per env.  ``fused=True`` returns the raw frames instead of the
         84x84 screen so that History.add can run preprocess+push as one kernel."""
+        start_lives = self.lives.clone()
+        if self.action_repeat == 1:
+            # config.py:50 default: the loop body once, without the masks that only matter from
+            # the second repeat on (same arithmetic, 5 small launches instead of 14)
+            self._step(action)
+            cumulated, done = self.reward, self.terminal
+            if is_training:
+                lost = start_lives > self.lives                   # environment.py:86-88
+                cumulated = cumulated - lost.float()
+                done = done | lost
+            self.reward, self.terminal = cumulated, done
+            self.after_act(action)
+            if fused:
+                return self.frames, self.reward, self.terminal
+            return self.state
         cumulated = torch.zeros(self.num_envs, device=self.device)
         done = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        start_lives = self.lives.clone()
         for k in range(self.action_repeat):
             self._step(action)
             live = ~done
