@@ -87,13 +87,20 @@ struct __align__(16) K1Smem {
   uint64_t full[2], empty[2], out_full[2], out_empty[2];
 };
 
-__device__ __forceinline__ uint32_t luma8(uint32_t px /* R | G<<8 | B<<16 */, const uint32_t* fix) {
-  const uint32_t s = __dp4a(px, 0x00D2F04Eu, 0u) + (__dp4a(px, 0x00021B08u, 0u) << 8);
+// rare path (3384 of 2^24 triples: the exact value is an integer): is this one of the 774 where
+// the reference's float64 sum lands one ulp below?  Kept out of line so that the common path is
+// two dp4a, the division and one compare -- not a predicated copy of this lookup per pixel.
+__device__ __noinline__ uint32_t luma_fix_lookup(uint32_t rg /* G*256 + R */, const uint32_t* fix) {
+  return (fix[rg >> 5] >> (rg & 31)) & 1u;
+}
+// luma of the pixel whose R,G,B bytes sit at byte SHIFT.. of w (the other byte is ignored: its
+// dp4a coefficient is 0)
+template <int SHIFT>
+__device__ __forceinline__ uint32_t luma8(uint32_t w, const uint32_t* fix) {
+  constexpr uint32_t C0 = 0x00D2F04Eu << (8 * SHIFT), C1 = 0x00021B08u << (8 * SHIFT);
+  const uint32_t s = __dp4a(w, C0, 0u) + (__dp4a(w, C1, 0u) << 8);
   uint32_t q = __umulhi(s, 3518437209u) >> 13;               // s / 10000, exact for s <= 2 550 000
-  if (s == q * 10000u) {
-    const uint32_t idx = px & 0xFFFFu;                       // G*256 + R
-    q -= (fix[idx >> 5] >> (idx & 31)) & 1u;
-  }
+  if (__builtin_expect(s == q * 10000u, 0)) q -= luma_fix_lookup((w >> (8 * SHIFT)) & 0xFFFFu, fix);
   return q;
 }
 
@@ -170,14 +177,14 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
       const uint2 a = raw2[3 * u], b = raw2[3 * u + 1], c = raw2[3 * u + 2];
       const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y, w4 = c.x, w5 = c.y;
       uint32_t y0, y1;
-      y0 = luma8(w0 & 0x00FFFFFFu, sm.fix);
-      y0 |= luma8(__byte_perm(w0, w1, 0x4543), sm.fix) << 8;    // bytes 3,4,5
-      y0 |= luma8(__byte_perm(w1, w2, 0x4432), sm.fix) << 16;   // bytes 6,7,8
-      y0 |= luma8(w2 >> 8, sm.fix) << 24;                       // bytes 9,10,11
-      y1 = luma8(w3 & 0x00FFFFFFu, sm.fix);                     // bytes 12,13,14
-      y1 |= luma8(__byte_perm(w3, w4, 0x4543), sm.fix) << 8;    // bytes 15,16,17
-      y1 |= luma8(__byte_perm(w4, w5, 0x4432), sm.fix) << 16;   // bytes 18,19,20
-      y1 |= luma8(w5 >> 8, sm.fix) << 24;                       // bytes 21,22,23
+      y0 = luma8<0>(w0, sm.fix);                                   // bytes 0,1,2
+      y0 |= luma8<0>(__byte_perm(w0, w1, 0x4543), sm.fix) << 8;    // bytes 3,4,5
+      y0 |= luma8<0>(__byte_perm(w1, w2, 0x4432), sm.fix) << 16;   // bytes 6,7,8
+      y0 |= luma8<1>(w2, sm.fix) << 24;                            // bytes 9,10,11
+      y1 = luma8<0>(w3, sm.fix);                                   // bytes 12,13,14
+      y1 |= luma8<0>(__byte_perm(w3, w4, 0x4543), sm.fix) << 8;    // bytes 15,16,17
+      y1 |= luma8<0>(__byte_perm(w4, w5, 0x4432), sm.fix) << 16;   // bytes 18,19,20
+      y1 |= luma8<1>(w5, sm.fix) << 24;                            // bytes 21,22,23
       reinterpret_cast<uint2*>(Yw)[u] = make_uint2(y0, y1);
     }
     __syncwarp();

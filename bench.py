@@ -41,7 +41,7 @@ ENTRY_WORK = {
     "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * 7, 1024 + 56),
     "arl_heads_backward": ("heads_bwd_kernel", 4.0 * 256 * 7, 2048 + 28),
     "arl_fc_backward": ("tc_kernel<GemmPolicy fc dgrad> + <fc wgrad>", 4.0 * 663552,
-                        2 * 10368 + 1024 + 10368),
+                        2 * 10368 + 1024 + 10368 + 1024),
     "arl_conv2_backward": ("tc_kernel<Conv2Wgrad> + <Conv2Dgrad>", 4.0 * 663552,
                            2 * (25600 + 10368) + 25600),
     "arl_conv1_backward": ("tc_kernel<Conv1Wgrad>", 2.0 * 1638400, 28224 + 25600),
