@@ -41,6 +41,8 @@ int fc_gemm(int variant, const float* A, const float* B, float* D, const float* 
   const int items = g.m_tiles * g.n_tiles * g.k_splits;
   switch (variant) {
     case 0: return tc::launch<tc::GemmPolicy<256, 16, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
+    // few rows (one env step): narrow N tiles so every SM works; KB = 32 keeps the A rows 128-B
+    // segments (16 one-warp stages of KB = 16 measured 7 % slower: 64-B segments, same latency)
     case 1: return tc::launch<tc::GemmPolicy<64, 32, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
     case 2: return tc::launch<tc::GemmPolicy<256, 16, false, false, tc::EPI_MASK>>(g, items, st);
     case 3:   // (was: K-major images transposed in registers; now identical to 4)

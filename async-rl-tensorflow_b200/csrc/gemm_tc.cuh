@@ -267,7 +267,7 @@ struct PolicyBase {
 template <class P>
 struct Smem {
   static constexpr int BAR_OFF = P::STAGES * P::STAGE_BYTES + P::RES_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + 256;
+  static constexpr int EPI_OFF = BAR_OFF + 512;                 // up to 2*16 + 4 mbarriers + TMEM slot
   static constexpr int EPI_ROW = (P::SEG + 4) * 4;              // staged row, padded: conflict-free
   static constexpr int EPI_WARP = 32 * EPI_ROW + 32 * 8;        // staging + 32 row pointers
   static constexpr int TOTAL = EPI_OFF + epi_warps<P>() * EPI_WARP;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   constexpr int kEpiWarps = epi_warps<P>();
   constexpr int kMmaWarp = kEpiWarps + P::PROD_WARPS;
   static_assert(P::PROD_WARPS % STAGES == 0, "producer warps must divide evenly over the stages");
-  static_assert(STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
+  static_assert(STAGES == 16 || STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* res = smem + STAGES * P::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -478,10 +478,11 @@ struct GemmArgs {
 //   X_TRANS=false (element (r,k) at src[r*ld + k], k contiguous) -> K-major image
 //   X_TRANS=true  (element (r,k) at src[k*ld + r], r contiguous) -> MN-major image
 // (the instruction descriptor carries one major-ness bit per operand).
-template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI>
+template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI, int STAGES_ = 0>
 struct GemmPolicy : PolicyBase {
   using Args = GemmArgs;
-  static constexpr int N_TILE = N_TILE_, KB = KB_, STAGES = EPI == EPI_MASK ? 4 : 8, ACC_COLS = N_TILE_;
+  static constexpr int N_TILE = N_TILE_, KB = KB_, ACC_COLS = N_TILE_;
+  static constexpr int STAGES = STAGES_ > 0 ? STAGES_ : EPI == EPI_MASK ? 4 : 8;
   static constexpr int OUT_COLS = N_TILE_, LO_DELTA = 0, SEG = 32;
   static constexpr bool HAS_AUX = EPI != EPI_PLAIN, AUX_ROW_INVARIANT = EPI != EPI_MASK;
   // the relu-mask epilogue waits on HBM: two epilogue sets, and 8 producer warps so that the 17
