@@ -44,6 +44,7 @@ class AgentConfig(object):
     reduce_mean = True                   # sum over t, mean over envs (False: pure sum)
     clip_norm = 40.0                     # agent.py:319
     resize = 'cv2'                       # environment.py:5-12 executed branch
+    loss_mode = 'a3c'                    # 'a3c' (network.py heads/loss) | 'async_q' (agent.py as run)
 
 
 class EnvironmentConfig(object):

@@ -87,6 +87,20 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint3
   return c0;
 }
 
+// second output word of the same block (used by the epsilon-greedy draw)
+__device__ __forceinline__ void philox_two(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  x0 = c0; x1 = c1;
+}
+
 __global__ void sample_actions_kernel(const float* __restrict__ probs, int32_t* __restrict__ actions,
                                       int num_envs, int A, uint64_t env_id_base, uint64_t step,
                                       uint64_t seed) {
@@ -116,6 +130,66 @@ __global__ void greedy_actions_kernel(const float* __restrict__ scores, int32_t*
   for (int j = 1; j < A; ++j)
     if (p[j] > best) { best = p[j]; a = j; }        // ties -> lowest index (tf.argmax)
   actions[b] = a;
+}
+
+// agent.py:141-151: with probability ep a uniformly random action, else argmax_a Q (ties -> lowest
+// index).  The reference draws from Python's `random` (main.py:41); here the draw is the Philox
+// block (env, step_lo, step_hi, 1): word 0 -> u < ep, word 1 -> action = floor(x1 * A / 2^32).
+__global__ void egreedy_actions_kernel(const float* __restrict__ q, int32_t* __restrict__ actions,
+                                       int num_envs, int A, float ep, uint64_t env_id_base,
+                                       uint64_t step, uint64_t seed) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= num_envs) return;
+  uint32_t x0, x1;
+  philox_two((uint32_t)(env_id_base + (uint64_t)b), (uint32_t)step, (uint32_t)(step >> 32), 1u,
+             (uint32_t)seed, (uint32_t)(seed >> 32), x0, x1);
+  const float u = (float)(x0 >> 8) * 5.9604644775390625e-08f;      // 2^-24
+  int a;
+  if (u < ep) {
+    a = (int)(((uint64_t)x1 * (uint64_t)A) >> 32);
+  } else {
+    const float* p = q + (size_t)b * A;
+    a = 0;
+    float best = p[0];
+    for (int j = 1; j < A; ++j)
+      if (p[j] > best) { best = p[j]; a = j; }
+  }
+  actions[b] = a;
+}
+
+// ------------------------------- async-Q loss gradients -----------------------------------
+// agent.py:186-190, 310-314: target = clip(r) + (1 - terminal) * discount * max_a Q_target(s'),
+// delta = target - Q(s)[a], loss = mean(delta^2)  ->  dQ[a] = -2 * delta * grad_scale.
+__global__ void q_lossgrad_kernel(const float* __restrict__ rewards,
+                                  const uint8_t* __restrict__ terminals,
+                                  const int32_t* __restrict__ actions, const float* __restrict__ q,
+                                  const float* __restrict__ q_next, float* __restrict__ target,
+                                  float* __restrict__ dq, float* __restrict__ loss_sums,
+                                  int64_t num_samples, int A, float discount, float rmin, float rmax,
+                                  float grad_scale) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s_loss = 0.f, s_q = 0.f;
+  if (n < num_samples) {
+    const float* qn = q_next + n * A;
+    float mx = qn[0];
+    for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
+    const float r = fminf(fmaxf(rewards[n], rmin), rmax);                 // agent.py:154
+    const float tgt = fmaf((1.0f - (terminals[n] ? 1.0f : 0.0f)) * discount, mx, r);   // agent.py:190
+    const int a = actions[n];
+    const float delta = tgt - q[n * A + a];
+    target[n] = tgt;
+    for (int j = 0; j < A; ++j) dq[n * A + j] = j == a ? -2.0f * delta * grad_scale : 0.f;
+    s_loss = delta * delta;
+    s_q = q[n * A + a];
+  }
+  if (loss_sums) {
+    s_loss = warp_sum(s_loss);
+    s_q = warp_sum(s_q);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(loss_sums + 0, s_loss);
+      atomicAdd(loss_sums + 1, s_q);
+    }
+  }
 }
 
 // ------------------------------- returns + loss gradients ---------------------------------
@@ -294,6 +368,38 @@ extern "C" int arl_greedy_actions(const float* scores, int32_t* actions, int num
   greedy_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       scores, actions, num_envs, action_size);
   ARL_LAUNCH_CHECK("greedy_actions_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_egreedy_actions(const float* q, int32_t* actions, int num_envs, int action_size,
+                                   float ep, int64_t env_id_base, int64_t step, uint64_t seed,
+                                   void* stream) {
+  ARL_REQUIRE(q && actions, "arl_egreedy_actions: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_egreedy_actions: negative size");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_egreedy_actions: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(ep >= 0.f && ep <= 1.f, "arl_egreedy_actions: ep %f outside [0,1]", (double)ep);
+  if (num_envs == 0) return ARL_OK;
+  egreedy_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      q, actions, num_envs, action_size, ep, (uint64_t)env_id_base, (uint64_t)step, seed);
+  ARL_LAUNCH_CHECK("egreedy_actions_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_q_lossgrad(const float* rewards, const uint8_t* terminals, const int32_t* actions,
+                              const float* q, const float* q_next, float* target, float* dq,
+                              float* loss_sums, int64_t num_samples, int action_size, float discount,
+                              float reward_min, float reward_max, float grad_scale, void* stream) {
+  ARL_REQUIRE(rewards && terminals && actions && q && q_next && target && dq,
+              "arl_q_lossgrad: null pointer");
+  ARL_REQUIRE(num_samples >= 0, "arl_q_lossgrad: negative size");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_q_lossgrad: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  if (num_samples == 0) return ARL_OK;
+  q_lossgrad_kernel<<<(unsigned)((num_samples + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      rewards, terminals, actions, q, q_next, target, dq, loss_sums, num_samples, action_size,
+      discount, reward_min, reward_max, grad_scale);
+  ARL_LAUNCH_CHECK("q_lossgrad_kernel");
   return ARL_OK;
 }
 

@@ -54,6 +54,14 @@ class Agent(BaseModel):
         self.step = 0
         self.T = 0
         self.update_count = 0
+        # loss_mode 'async_q' = the learner the reference actually runs: Q head,
+        # epsilon-greedy, 1-step targets from a target network (agent.py:141-207, 298-314)
+        self.loss_mode = getattr(config, 'loss_mode', 'a3c')
+        if self.loss_mode not in ('a3c', 'async_q'):
+            raise ValueError("loss_mode must be 'a3c' or 'async_q', got %r" % (self.loss_mode,))
+        if self.loss_mode == 'async_q':
+            self.network.make_target()
+            self._last_target_sync = 0
 
     # -- agent.py:33-50 ---------------------------------------------------------------------
     def before_train(self, is_chief=True):
@@ -62,6 +70,7 @@ class Agent(BaseModel):
         # agent.py:37-38: the stack starts as 4 copies of the first screen (K1, replicate=4)
         self.history.add(self.env.frames, replicate=self.history_length)
         self.t = 0
+        self.update_target_q_network()                           # main.py:92
         return self.env.frames, 0, 0, self.env.terminal, range(self.step, self.max_step)
 
     # -- agent.py:52-67 ---------------------------------------------------------------------
@@ -85,6 +94,9 @@ class Agent(BaseModel):
         """Forward of the current stack (already in the ring; ``s_t`` is accepted for signature
         compatibility and ignored) and one sampled action per env."""
         self.network.forward(self.history, self.t)
+        if self.loss_mode == 'async_q':                          # agent.py:142-149
+            ep = self.ep if test_ep is None else test_ep
+            return self.network.egreedy(self.t, self.step, self.seed, ep, self.env_id_base)
         return self.network.sample(self.t, self.step, self.seed, self.env_id_base)
 
     # -- agent.py:153-167 -------------------------------------------------------------------
@@ -96,14 +108,23 @@ class Agent(BaseModel):
         if self.t == self.t_max:                                 # agent.py:162-163
             self.batch_update(is_chief)
         self.T += self.global_envs                               # agent.py:165 counts every worker
+        if self.loss_mode == 'async_q' and \
+                self.T - self._last_target_sync >= self.target_q_update_step:
+            self.update_target_q_network()                       # agent.py:166-167
+            self._last_target_sync = self.T
 
     # -- agent.py:169-207 -------------------------------------------------------------------
     def batch_update(self, is_chief=False):
         net = self.network
-        v_boot = net.bootstrap_value(self.history)               # R = V(s_T), masked if terminal
-        scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
-        net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
-                              grad_scale=scale)
+        if self.loss_mode == 'async_q':
+            # agent.py:312-314 mean over the worker's batch; mean over (global) envs as in a3c mode
+            scale = 1.0 / (self.t_max * self.global_envs) if self.reduce_mean else 1.0 / self.t_max
+            net.compute_q_gradients(self.history, self.batch_reward, self.batch_terminal, scale)
+        else:
+            v_boot = net.bootstrap_value(self.history)           # R = V(s_T), masked if terminal
+            scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
+            net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
+                                  grad_scale=scale)
         if self.world_size > 1:
             dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)     # the one exchange per cycle
         net.apply_gradients(self.lr)
@@ -111,7 +132,15 @@ class Agent(BaseModel):
         self.t = 0
 
     def update_target_q_network(self):
-        """agent.py:342-344: no target network in the A3C path."""
+        """agent.py:342-344 (async_q mode; the A3C path has no target network)."""
+        if self.loss_mode == 'async_q':
+            self.network.update_target()
+
+    @property
+    def ep(self):
+        """agent.py:142-144."""
+        return self.ep_end + max(0., (self.ep_start - self.ep_end) *
+                                 (self.ep_end_t - max(0., self.step - self.learn_start)) / self.ep_end_t)
 
     @property
     def lr(self):

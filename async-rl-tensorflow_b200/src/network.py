@@ -223,6 +223,54 @@ class Network(object):
                          P(self.workspace), B, history.ring_slots, history.first_slot(T), T, st)
         return self.grads
 
+    # -- async-Q mode (agent.py:169-207, 298-314): the Q head lives in the p_w/p_b slot ---------
+    def make_target(self):
+        """agent.py:257-296: a second parameter set, the target network."""
+        self.target_params = self.params.clone()
+        N, A = self.num_envs * self.t_max, self.action_size
+        f32 = dict(device=self.device, dtype=torch.float32)
+        self.target_q = torch.empty(N, A, **f32)              # agent.py:186 q_t_plus_1
+        self.target_q_t = torch.empty(N, **f32)               # agent.py:190
+        self._tq_scratch = (torch.empty(N, A, **f32), torch.empty(N, **f32))
+        return self.target_params
+
+    def update_target(self):
+        """agent.py:298-303, 342-344: target <- prediction network."""
+        self.target_params.copy_(self.params)
+
+    def egreedy(self, t, step, seed, ep, env_id_base=0):
+        """agent.py:141-151 on the Q values of rollout slot t."""
+        r = self._rows(t)
+        _cabi.call("arl_egreedy_actions", _cabi.ptr(self.policy_logits[r]),
+                   _cabi.ptr(self.sampled_action[r]), self.num_envs, self.action_size, float(ep),
+                   int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
+        return self.sampled_action[r]
+
+    def compute_q_gradients(self, history, rewards, terminals, grad_scale):
+        """agent.py:186-197: target-network forward over s_1..s_T, 1-step targets, MSE gradient,
+        backward.  The backward scratch buffers hold the target activations meanwhile."""
+        T, B, A = self.t_max, self.num_envs, self.action_size
+        P, st = _cabi.ptr, _cabi.stream_ptr()
+        probs, value = self._tq_scratch
+        _cabi.call("arl_forward", P(self.target_params), A, P(history.ring), B, history.ring_slots,
+                   history.first_slot(T - 1), T, P(self.d_l1), P(self.d_l2), P(self.d_l4),
+                   P(self.target_q), P(probs), P(value), st)
+        self.loss_sums.zero_()
+        _cabi.call("arl_q_lossgrad", P(rewards), P(terminals), P(self.sampled_action),
+                   P(self.policy_logits), P(self.target_q), P(self.target_q_t), P(self.d_logits),
+                   P(self.loss_sums), T * B, A, self.gamma, self.min_reward, self.max_reward,
+                   float(grad_scale), st)
+        self.d_value.zero_()                                   # the value head is unused
+        _cabi.call("arl_backward", P(self.params), A, P(history.ring), B, history.ring_slots,
+                   history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
+                   P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
+                   P(self.d_l1), P(self.grads), P(self.workspace), st)
+        return self.grads
+
+    @property
+    def q(self):                                               # agent.py:252
+        return self.policy_logits
+
     def apply_gradients(self, lr):
         """agent.py:316-321: per-tensor clip_by_norm(40) + shared RMSProp (K5)."""
         _cabi.call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),

@@ -122,6 +122,23 @@ ARL_API int arl_sample_actions(const float* probs, int32_t* actions, int num_env
 ARL_API int arl_greedy_actions(const float* scores, int32_t* actions, int num_envs, int action_size,
                        void* stream);
 
+/* agent.py:141-151 (the as-running async-Q learner): with probability ep a uniform random action,
+ * else argmax_a q (ties -> lowest index).  The reference draws from Python's `random`
+ * (main.py:41); here: Philox4x32-10 block (env_id_base + b, step, 1) keyed by seed, word 0 ->
+ * u < ep, word 1 -> floor(x * A / 2^32).  q f32 [num_envs, A]. */
+ARL_API int arl_egreedy_actions(const float* q, int32_t* actions, int num_envs, int action_size, float ep,
+                        int64_t env_id_base, int64_t step, uint64_t seed, void* stream);
+
+/* agent.py:186-190 + 310-314 (async 1-step Q learning with a target network):
+ *   target = clip(r) + (1-terminal) * discount * max_a q_next[n][a]
+ *   delta  = target - q[n][actions[n]];   dq[n][a] = -2 * delta * grad_scale  (0 elsewhere)
+ * i.e. the gradient of grad_scale * sum(delta^2)  (grad_scale = 1/N gives the reference's
+ * mean(delta^2)).  loss_sums (optional) f32 [2] += {sum delta^2, sum q[n][a]}. */
+ARL_API int arl_q_lossgrad(const float* rewards, const uint8_t* terminals, const int32_t* actions,
+                   const float* q, const float* q_next, float* target, float* dq, float* loss_sums,
+                   int64_t num_samples, int action_size, float discount, float reward_min,
+                   float reward_max, float grad_scale, void* stream);
+
 /* Algorithm 3 (assets/a3c.png) returns with the terminal mask of agent.py:188-190 and the
  * reward clip of agent.py:154, then d(total_loss)/d(logits,value) per network.py:81-94:
  *   R_t = clip(r_t) + gamma*(1-term_t)*R_{t+1},  R_T = v_boot

@@ -254,3 +254,45 @@ def a3c_cycle(params, rms, screens, actions, rewards, terminals, step, *,
     new_p, new_r = update(params, rms, grads, lr)
     aux.update(R=R, v_boot=v_boot.numpy(), grads=grads, lr=lr)
     return new_p, new_r, aux
+
+
+# ---- the reference's AS-RUNNING learner: asynchronous 1-step Q-learning ------------
+def epsilon(step, ep_start=1.0, ep_end=0.1, ep_end_t=4000000, learn_start=32):
+    """agent.py:142-144."""
+    return ep_end + max(0.0, (ep_start - ep_end) * (ep_end_t - max(0.0, step - learn_start)) / ep_end_t)
+
+
+def q_targets(q_next, rewards, terminals, discount=0.99):
+    """agent.py:186-190: target_q_t = (1 - terminal) * discount * max_a Q_target(s_{t+1}) + reward
+    (the reward is already clipped by observe, agent.py:154)."""
+    q_next = np.asarray(q_next, np.float64)
+    term = np.asarray(terminals).astype(np.float64)
+    return (1.0 - term) * discount * q_next.max(axis=1) + clip_rewards(rewards)
+
+
+def async_q_gradients(params_np, target_params_np, stacks_t, stacks_tp1, actions, rewards,
+                      terminals, discount=0.99, scale=None, dtype=torch.float64, masks=None):
+    """agent.py:169-207 + 306-317 with the Q head in the p_w/p_b slot (q = the policy-logit
+    head; the value head is unused and gets zero gradient):
+        q_t_plus_1 = target_q(s_{t+1})            agent.py:186   (no gradient)
+        target     = q_targets(...)               agent.py:188-190
+        q_acted    = sum(q * onehot(action))      agent.py:310-311
+        loss       = mean((target - q_acted)^2)   agent.py:312-314
+    ``scale`` replaces the 1/N of the mean (1/(T * global envs) under env-sharded sync DP)."""
+    p = to_torch(params_np, dtype, requires_grad=True)
+    with torch.no_grad():
+        q_next, _ = forward(to_torch(target_params_np, dtype), stacks_tp1)
+    tgt = torch.as_tensor(q_targets(q_next.numpy(), np.asarray(rewards).reshape(-1),
+                                    np.asarray(terminals).reshape(-1), discount), dtype=dtype)
+    q, _ = forward(p, stacks_t, masks=masks)
+    at = torch.as_tensor(np.asarray(actions).reshape(-1)).long()
+    q_acted = q.gather(1, at.reshape(-1, 1)).reshape(-1)
+    delta = tgt - q_acted
+    n = delta.shape[0]
+    loss = (delta ** 2).sum() * (1.0 / n if scale is None else scale)
+    loss.backward()
+    grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy().copy())
+                        for k, v in p.items())
+    aux = dict(q=q.detach().numpy(), q_next=q_next.numpy(), target=tgt.numpy(),
+               loss=float(loss.detach()), delta=delta.detach().numpy())
+    return grads, aux

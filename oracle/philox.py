@@ -71,3 +71,21 @@ def sample_actions(probs, env_ids, step, seed):
         act[hit] = j
         done |= hit
     return act
+
+
+def egreedy_actions(q, env_ids, step, seed, ep):
+    """agent.py:141-151 with the draw defined by DESIGN.md: Philox block
+    (env, step_lo, step_hi, 1): word 0 -> u < ep, word 1 -> floor(x1 * A / 2^32); else argmax
+    (ties -> lowest index, numpy argmax == tf.argmax)."""
+    q = np.asarray(q, np.float32)
+    B, A = q.shape
+    env_ids = np.asarray(env_ids, np.uint32)
+    z = np.zeros_like(env_ids)
+    x0, x1, _, _ = philox4x32_10(env_ids, z + np.uint32(step & 0xFFFFFFFF),
+                                 z + np.uint32((step >> 32) & 0xFFFFFFFF), z + np.uint32(1),
+                                 z + np.uint32(seed & 0xFFFFFFFF),
+                                 z + np.uint32((seed >> 32) & 0xFFFFFFFF))
+    u = (x0 >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    rand = ((x1.astype(np.uint64) * np.uint64(A)) >> np.uint64(32)).astype(np.int32)
+    greedy = q.argmax(axis=1).astype(np.int32)
+    return np.where(u < np.float32(ep), rand, greedy).astype(np.int32)

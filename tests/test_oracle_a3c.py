@@ -111,3 +111,40 @@ def test_cycle_shapes_and_terminal_mask():
     assert all(newp[k].shape == p[k].shape for k in p)
     st = a3c.stacks_from_screens(screens, T)
     assert st.shape == (T + 1, B, 84, 84, 4) and np.array_equal(st[1, :, :, :, 0], screens[1])
+
+
+def test_async_q_oracle_matches_closed_form():
+    """agent.py:186-190, 310-314: autograd of mean(delta^2) == the closed form the CUDA kernel
+    emits at the head (dq[a] = -2*delta/N), and the target uses the TARGET parameters."""
+    A, N = 5, 6
+    rng = np.random.default_rng(0)
+    params, tparams = a3c.init_params(A, 1), a3c.init_params(A, 2)
+    s_t = rng.integers(0, 256, (N, 84, 84, 4)).astype(np.uint8)
+    s_tp1 = rng.integers(0, 256, (N, 84, 84, 4)).astype(np.uint8)
+    acts = rng.integers(0, A, N)
+    rew = rng.choice([-2.0, 0.0, 1.0], N)
+    term = rng.random(N) < 0.5
+    grads, aux = a3c.async_q_gradients(params, tparams, s_t, s_tp1, acts, rew, term, 0.99)
+    with torch.no_grad():
+        qn, _ = a3c.forward(a3c.to_torch(tparams), s_tp1)
+    tgt = (1.0 - term) * 0.99 * qn.numpy().max(1) + np.clip(rew, -1, 1)
+    assert np.allclose(aux["target"], tgt, rtol=0, atol=1e-12)
+    # head gradient in closed form: d loss / d p_b = sum_n dq[n]
+    delta = tgt - aux["q"][np.arange(N), acts]
+    dq = np.zeros((N, A))
+    dq[np.arange(N), acts] = -2.0 * delta / N
+    assert np.allclose(grads["p_b"], dq.sum(0), rtol=1e-10, atol=1e-14)
+    assert np.abs(grads["q_w"]).max() == 0.0                       # value head unused
+    assert abs(a3c.epsilon(0) - 1.0) < 1e-12 and abs(a3c.epsilon(10 ** 9) - 0.1) < 1e-12
+
+
+def test_egreedy_oracle_properties():
+    from oracle import philox
+    q = np.random.default_rng(1).normal(0, 1, (4096, 6)).astype(np.float32)
+    ids = np.arange(4096)
+    assert np.array_equal(philox.egreedy_actions(q, ids, 5, 123, 0.0), q.argmax(1))
+    a = philox.egreedy_actions(q, ids, 5, 123, 1.0)
+    counts = np.bincount(a, minlength=6)
+    assert counts.min() > 4096 / 6 * 0.8 and counts.max() < 4096 / 6 * 1.2
+    frac = (philox.egreedy_actions(q, ids, 5, 123, 0.25) != q.argmax(1)).mean()
+    assert 0.15 < frac < 0.27                                      # 0.25 * 5/6 = 0.208
