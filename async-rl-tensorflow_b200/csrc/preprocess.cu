@@ -300,6 +300,20 @@ extern "C" int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num
   return ARL_OK;
 }
 
+extern "C" int arl_upload_frames(const uint8_t* host_frames, uint8_t* dev_frames, int num_envs,
+                                 void* stream) {
+  ARL_REQUIRE(host_frames && dev_frames, "arl_upload_frames: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_upload_frames: num_envs %d < 0", num_envs);
+  if (num_envs == 0) return ARL_OK;
+  // a frame = 42 groups of 5 rows (2400 B); K1 reads rows 0,1 and 3,4 of every group
+  const size_t pitch = 5 * kRowBytes, groups = (size_t)num_envs * (kH / 5);
+  ARL_CUDA(cudaMemcpy2DAsync(dev_frames, pitch, host_frames, pitch, 2 * kRowBytes, groups,
+                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  ARL_CUDA(cudaMemcpy2DAsync(dev_frames + 3 * kRowBytes, pitch, host_frames + 3 * kRowBytes, pitch,
+                             2 * kRowBytes, groups, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return ARL_OK;
+}
+
 extern "C" int arl_history_get(const uint8_t* ring, void* out, int out_is_u8, int num_envs,
                                int ring_slots, int first_slot, void* stream) {
   ARL_REQUIRE(ring && out, "arl_history_get: null pointer");

@@ -80,7 +80,7 @@ class SyntheticAtari(object):
             self._frames = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
             self._frames.copy_(frames)
             # double-buffered staging: the upload of step i+1 overlaps the compute of step i
-            self._stage = [torch.empty((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device)
+            self._stage = [torch.zeros((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device)
                            for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._ready = [None, None]
@@ -92,7 +92,7 @@ class SyntheticAtari(object):
         self._i = 0
         self.ale = _ALE(self)
         self.action_space = _ActionSpace(self, int(action_size))
-        self.h2d_bytes_per_step = B * FRAME_SHAPE[0] * FRAME_SHAPE[1] * FRAME_SHAPE[2] if host else 0
+        self.h2d_bytes_per_step = B * 168 * FRAME_SHAPE[1] * FRAME_SHAPE[2] if host else 0
 
     def _upload(self, i):
         """Queue the pinned-host -> device copy of step i's frames on the copy stream.  The copy
@@ -103,7 +103,9 @@ class SyntheticAtari(object):
             return
         self._copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
-            self._stage[k].copy_(self._frames[i % self.pool], non_blocking=True)
+            # only the 168 of 210 rows K1 reads cross PCIe (80 640 B per frame)
+            _cabi.call("arl_upload_frames", self._frames[i % self.pool].data_ptr(),
+                       _cabi.ptr(self._stage[k]), self.num_envs, self._copy_stream.cuda_stream)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         self._ready[k], self._staged_for[k] = ev, i

@@ -80,6 +80,13 @@ ARL_API int arl_param_layout(int action_size, int64_t* offsets);
 ARL_API int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num_envs, int ring_slots,
                         int slot, int replicate, void* stream);
 
+/* Host -> device upload of exactly the frame rows K1 reads (environment.py:53 -> cv2.resize
+ * 210x160 -> 84x84 never touches source rows == 2 mod 5): two strided async copies of
+ * num_envs*42 x 960 B each = 80 640 of the 100 800 B of a frame.  host_frames should be pinned;
+ * dev_frames keeps the full [num_envs,210,160,3] layout (the skipped rows are left as they are). */
+ARL_API int arl_upload_frames(const uint8_t* host_frames, uint8_t* dev_frames, int num_envs,
+                      void* stream);
+
 /* History.get()/copy() (src/history.py:20-27): materialise the NHWC stack
  * f32 [num_envs,84,84,4] (or u8 when out_is_u8) whose oldest plane is `first_slot`. */
 ARL_API int arl_history_get(const uint8_t* ring, void* out, int out_is_u8, int num_envs,

@@ -143,3 +143,25 @@ def test_full_size_properties_4096_envs(pkg, cuda):
     assert bool((out == first[perm]).all())
     assert np.array_equal(first.cpu().numpy(), P.screen(base.cpu().numpy()))
     assert int(ring[:, :8].max()) == 0
+
+
+def test_upload_frames_skips_only_unread_rows(pkg, cuda):
+    """arl_upload_frames moves rows != 2 (mod 5) from pinned host memory; K1 on the uploaded
+    buffer equals the oracle on the full host frames, and the skipped rows are left untouched."""
+    B = 37
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (B, 210, 160, 3), dtype=np.uint8)
+    host = torch.empty((B, 210, 160, 3), dtype=torch.uint8, pin_memory=True)
+    host.copy_(torch.as_tensor(frames))
+    dev = torch.full((B, 210, 160, 3), 9, dtype=torch.uint8, device=cuda)
+    pkg._cabi.call("arl_upload_frames", host.data_ptr(), pkg._cabi.ptr(dev), B,
+                   pkg._cabi.stream_ptr())
+    ring = torch.zeros(B, 4, 84, 84, dtype=torch.uint8, device=cuda)
+    pkg._cabi.call("arl_preprocess_push", pkg._cabi.ptr(dev), pkg._cabi.ptr(ring), B, 4, 2, 1,
+                   pkg._cabi.stream_ptr())
+    torch.cuda.synchronize()
+    got = dev.cpu().numpy()
+    keep = np.arange(210) % 5 != 2
+    assert np.array_equal(got[:, keep], frames[:, keep])
+    assert (got[:, ~keep] == 9).all()
+    assert np.array_equal(ring[:, 2].cpu().numpy(), P.screen(frames))
