@@ -334,3 +334,69 @@ def test_rmsprop_trajectory_100_updates_config2(pkg, cuda):
     assert max(worst["flat"], worst["param"], worst["bias"]) <= REL_TOL, worst
     # every tensor (biases included) at the end of the run
     assert max(v[0] for v in worst["per_tensor"].values()) <= REL_TOL, worst
+
+
+def test_full_size_properties_4096_envs_t5(pkg, cuda):
+    """BASELINE config 3 size (4096 envs, t_max 5, A=6), size-independent properties:
+    (1) forward of a random subset of the 20 480 samples equals the oracle,
+    (2) the gradient is additive over samples: full batch == first half + second half of the
+        envs (different tiling, split-K ranges and partial counts on the device),
+    (3) two runs are bit-identical (no float atomics on the gradient path)."""
+    A, B, T = 6, 4096, 5
+    params = make_params(A, seed=5, scale=2.0)
+    g = torch.Generator(device=cuda).manual_seed(3)
+
+    def run(envs, ring_full=None, lo=0):
+        cfg = pkg.config.get_config({"model": "m1", "num_envs": envs, "t_max": T})
+        net = net_for(pkg, A, envs, T, params)
+        hist = pkg.History(cfg, num_envs=envs, device=cuda)
+        if ring_full is None:
+            hist.ring.copy_(torch.randint(0, 256, tuple(hist.ring.shape), dtype=torch.uint8,
+                                          device=cuda, generator=g))
+        else:
+            hist.ring.copy_(ring_full[lo:lo + envs])
+        hist.head = T + 3                                         # slots 0..T+3 = f_-3 .. f_T
+        for t in range(T):
+            pkg._cabi.call("arl_forward", pkg._cabi.ptr(net.params), A, pkg._cabi.ptr(hist.ring),
+                           envs, hist.ring_slots, t, 1, *[pkg._cabi.ptr(x[t * envs:(t + 1) * envs])
+                                                          for x in (net.l1, net.l2, net.l4,
+                                                                    net.policy_logits, net.policy,
+                                                                    net.value)],
+                           pkg._cabi.stream_ptr())
+        return net, hist
+
+    net, hist = run(B)
+    rng = np.random.default_rng(0)
+    acts = torch.as_tensor(rng.integers(0, A, T * B).astype(np.int32), device=cuda)
+    rew = torch.as_tensor(rng.choice([-1.0, 0.0, 1.0], (T, B)).astype(np.float32), device=cuda)
+    term = torch.as_tensor((rng.random((T, B)) < 0.05).astype(np.uint8), device=cuda)
+    v_boot = torch.zeros(B, device=cuda)
+
+    def grads_of(net, hist, a, r, tm, vb):
+        net.compute_gradients(hist, r.contiguous(), tm.contiguous(), vb, actions=a.contiguous(),
+                              grad_scale=1.0 / B)
+        torch.cuda.synchronize()
+        return net.grads.clone()
+
+    g_full = grads_of(net, hist, acts, rew, term, v_boot)
+    g_again = grads_of(net, hist, acts, rew, term, v_boot)
+    assert bool((g_full == g_again).all())                        # (3)
+
+    # (1) forward of 48 random samples vs the oracle
+    ring = hist.ring.cpu().numpy()
+    pick = rng.choice(T * B, 48, replace=False)
+    stacks = np.stack([np.stack([ring[n % B, (n // B) + k] for k in range(4)], axis=-1) for n in pick])
+    logits, value = a3c.forward(a3c.to_torch(params), stacks)
+    assert rel_err(net.policy_logits[torch.as_tensor(pick, device=cuda)].cpu(), logits) <= REL_TOL
+    assert rel_err(net.value[torch.as_tensor(pick, device=cuda)].cpu(), value) <= REL_TOL
+
+    # (2) additivity over env halves
+    a2d, half = acts.view(T, B), B // 2
+    total = torch.zeros_like(g_full)
+    for lo in (0, half):
+        n2, h2 = run(half, hist.ring, lo)
+        total += grads_of(n2, h2, a2d[:, lo:lo + half].reshape(-1), rew[:, lo:lo + half],
+                          term[:, lo:lo + half], v_boot[lo:lo + half])
+    err = float((total - g_full).abs().max()) / float(g_full.abs().max())
+    print("additivity rel-err", err)
+    assert err <= 1e-5
