@@ -169,10 +169,11 @@ __device__ __forceinline__ void stream_x2(uint8_t* hi, uint8_t* lo, const float*
 }
 
 // ---- conv1 A operand: space-to-depth rows of the u8 ring ---------------------------------------
-// X row (n, y', x') -> 8 chunks; chunk kc = c*2 + h holds channels ch = (c*4+i)*4+j for
-// i in {2h, 2h+1}, j in 0..3 = frame rows 4y'+2h, 4y'+2h+1, columns 4x'..4x'+3 of plane c.
-// Work unit = (row, plane c): four 4-byte loads -> two 16-B chunks.  Lanes run along the rows of
-// one plane (consecutive x' = consecutive 4-byte words); U units (4U loads) are in flight per lane.
+// The ring stores every 84x84 plane in 4x4 blocks (K1 writes it that way): the 16 bytes at
+// plane + q*16 are block q = y'*21 + x' = frame rows 4y'..4y'+3, columns 4x'..4x'+3 = the 16
+// channels plane c contributes to X row (n, y', x') -> chunks kc = 2c (rows 0,1) and 2c+1 (rows
+// 2,3).  Work unit = (row, plane): ONE 16-byte load; lanes run along the rows of one plane, so a
+// warp instruction reads 512 contiguous bytes.  U units are in flight per lane.
 // SHIFTED: also store the copy shifted by one row into planes 8..15 (tap b = 1 of the wgrad).
 struct RingGeo {
   const uint8_t* ring;
@@ -181,11 +182,11 @@ struct RingGeo {
 template <int ROWS, int PL, int U, bool SHIFTED>
 __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr0, int num_samples,
                                           int glane, int gsize) {
-  constexpr int GW = 21, GROWS = 441, TOTAL = ROWS * 4;
+  constexpr int GROWS = 441, TOTAL = ROWS * 4;
   const int n0 = xr0 / GROWS, q0 = xr0 - n0 * GROWS;
   const int tt0 = n0 / g.num_envs, b0 = n0 - tt0 * g.num_envs;
   for (int u0 = glane; u0 < TOTAL; u0 += U * gsize) {
-    uint32_t w[U][4];
+    uint4 w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int un = u0 + u * gsize;
@@ -195,15 +196,12 @@ __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr
         q -= GROWS; ++n; ++b;
         if (b == g.num_envs) { b = 0; ++tt; }
       }
-      w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
+      w[u] = make_uint4(0u, 0u, 0u, 0u);
       if (un < TOTAL && n < num_samples) {
-        const int yp = q / GW, xp = q - yp * GW;
         int slot = g.first_slot + tt + c;
         slot -= slot >= g.ring_slots ? g.ring_slots : 0;
         slot -= slot >= g.ring_slots ? g.ring_slots : 0;
-        const uint8_t* src = g.ring + ((size_t)b * g.ring_slots + slot) * kPlane + (4 * yp) * ARL_SCREEN + 4 * xp;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[u][i] = __ldg(reinterpret_cast<const uint32_t*>(src + i * ARL_SCREEN));
+        w[u] = __ldg(reinterpret_cast<const uint4*>(g.ring + ((size_t)b * g.ring_slots + slot) * kPlane) + q);
       }
     }
 #pragma unroll
@@ -211,7 +209,7 @@ __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr
       const int un = u0 + u * gsize;
       if (un >= TOTAL) break;
       const int c = un / ROWS, r = un - c * ROWS;
-      const uint4 lo2 = tc::bytes8_to_bf16(w[u][0], w[u][1]), hi2 = tc::bytes8_to_bf16(w[u][2], w[u][3]);
+      const uint4 lo2 = tc::bytes8_to_bf16(w[u].x, w[u].y), hi2 = tc::bytes8_to_bf16(w[u].z, w[u].w);
       uint8_t* d = img + (2 * c) * PL + r * 16;
       *reinterpret_cast<uint4*>(d) = lo2;
       *reinterpret_cast<uint4*>(d + PL) = hi2;

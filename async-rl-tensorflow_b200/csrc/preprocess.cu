@@ -206,7 +206,10 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
           const uint8_t* r0 = row + sx;
           const int h0 = r0[0] * c0 + r0[1] * c1;
           const int h1 = r0[kW] * c0 + r0[kW + 1] * c1;
-          out[dy * kS + dx] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+          // ring planes are stored in 4x4 blocks (space-to-depth): byte (y,x) of the screen sits at
+          // ((y/4)*21 + x/4)*16 + (y%4)*4 + x%4, so conv1's 8x8-stride-4 windows are 16-B vectors
+          out[(warp * 21 + (dx >> 2)) * 16 + ry * 4 + (dx & 3)] =
+              (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
         }
       }
     }
@@ -225,7 +228,9 @@ __global__ void history_get_kernel(const uint8_t* __restrict__ ring, OutT* __res
        i += (int64_t)gridDim.x * blockDim.x) {
     const int env = (int)(i / kPlane);
     const int px = (int)(i - (int64_t)env * kPlane);
-    const uint8_t* base = ring + (size_t)env * ring_slots * kPlane + px;
+    const int y = px / kS, x = px - y * kS;                      // ring planes are 4x4-blocked
+    const uint8_t* base = ring + (size_t)env * ring_slots * kPlane +
+                          ((y >> 2) * 21 + (x >> 2)) * 16 + (y & 3) * 4 + (x & 3);
     OutT v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -14,7 +14,7 @@ import random
 import torch
 
 from .. import _cabi
-from .history import SCREEN, FRAME_SHAPE
+from .history import SCREEN, FRAME_SHAPE, from_blocked
 
 
 class _ALE(object):
@@ -187,7 +187,7 @@ class Environment(object):
         """environment.py:49-53 on the device (K1, bit-exact): u8 [B,84,84]."""
         _cabi.call("arl_preprocess_push", _cabi.ptr(self._screen), _cabi.ptr(self._scratch),
                    self.num_envs, 4, 0, 1, _cabi.stream_ptr())
-        return self._scratch[:, 0]
+        return from_blocked(self._scratch[:, 0]).contiguous()        # the ring layout is 4x4-blocked
 
     @property
     def action_size(self):

@@ -2,9 +2,14 @@
 on the device as a ring of u8 planes so the T+1 overlapping stacks of a rollout are windows
 into one buffer instead of T+1 float32 copies (reference agent.py:157 copies 113 KB/step).
 
-    ring u8 [num_envs, ring_slots, 84, 84];  ``head`` = slot of the newest frame.
+    ring u8 [num_envs, ring_slots, 7056];  ``head`` = slot of the newest frame.
     stack at offset t (t = 0 newest state) = slots head-3-t .. head-t, oldest first --
     the channel order of History.get() (history.py:20-24).
+
+Each 84x84 plane is stored in 4x4 blocks (space-to-depth): byte (y, x) sits at
+((y//4)*21 + x//4)*16 + (y%4)*4 + x%4.  An 8x8 stride-4 conv window is then four 16-byte
+vectors, which is how the conv1 kernels read it; ``get``/``copy``/``planes`` return the
+row-major layout of the reference.
 """
 import torch
 
@@ -12,6 +17,22 @@ from .. import _cabi
 
 SCREEN = 84
 FRAME_SHAPE = (210, 160, 3)
+
+
+def to_blocked(screens):
+    """[..., 84, 84] row-major -> the ring's 4x4-block order (same shape)."""
+    lead = screens.shape[:-2]
+    x = screens.reshape(lead + (21, 4, 21, 4))
+    n = len(lead)
+    return x.permute(*range(n), n, n + 2, n + 1, n + 3).reshape(lead + (SCREEN, SCREEN))
+
+
+def from_blocked(planes):
+    """Inverse of to_blocked."""
+    lead = planes.shape[:-2]
+    x = planes.reshape(lead + (21, 21, 4, 4))
+    n = len(lead)
+    return x.permute(*range(n), n, n + 2, n + 1, n + 3).reshape(lead + (SCREEN, SCREEN))
 
 
 class History(object):
@@ -48,7 +69,7 @@ class History(object):
                 _cabi.call(*args)
         elif tuple(screen.shape[1:]) == (SCREEN, SCREEN):
             for r in range(replicate):
-                self.ring[:, (new_head + r) % self.ring_slots].copy_(screen)
+                self.ring[:, (new_head + r) % self.ring_slots].copy_(to_blocked(screen))
         else:
             raise ValueError("expected [B,210,160,3] frames or [B,84,84] screens, got %s"
                              % (tuple(screen.shape),))
@@ -73,6 +94,12 @@ class History(object):
     def copy(self):
         """history.py:26-27."""
         return self.get().contiguous()
+
+    def planes(self, slot=None):
+        """Row-major u8 view-copy of the ring planes: [B, ring_slots, 84, 84], or [B, 84, 84] of
+        one slot (the ring itself is 4x4-blocked)."""
+        src = self.ring if slot is None else self.ring[:, slot]
+        return from_blocked(src).contiguous()
 
     # -- ring bookkeeping used by Network/Agent --------------------------------------------
     def first_slot(self, back=0):

@@ -16,7 +16,10 @@
  *   - samples are indexed n = t * num_envs + b  (t-major).  The frame ring is
  *     u8 [num_envs][ring_slots][84*84]; sample (t,b) reads the 4 planes
  *     ring[b][(first_slot + t + k) % ring_slots], k = 0 (oldest) .. 3 (newest),
- *     i.e. History.get() channel order (src/history.py:20-24).
+ *     i.e. History.get() channel order (src/history.py:20-24).  Inside a plane the
+ *     bytes are stored in 4x4 blocks (space-to-depth): screen byte (y,x) sits at
+ *     ((y/4)*21 + x/4)*16 + (y%4)*4 + x%4 -- arl_preprocess_push writes that order,
+ *     arl_conv1_* read it, arl_history_get returns the reference's row-major stack.
  *   - parameters / gradients / RMSProp slots are flat f32 buffers in the
  *     reference's own variable order and layouts (see arl_param_layout).
  */

@@ -71,7 +71,7 @@ def test_async_q_cycle_vs_oracle(pkg, cuda, A, B, T):
     agent.step = 100                                            # somewhere inside the anneal
     hist = agent.history
     first = hist.first_slot(0)
-    snap = hist.ring.cpu().numpy()
+    snap = hist.planes().cpu().numpy()
     screens = [snap[:, (first + k) % hist.ring_slots] for k in range(4)]
     rews, terms, eps = [], [], []
     for t in range(T):
@@ -85,7 +85,7 @@ def test_async_q_cycle_vs_oracle(pkg, cuda, A, B, T):
         agent.batch_reward[t].copy_(rew)
         agent.batch_terminal[t].copy_(term)
         rews.append(rew.cpu().numpy()); terms.append(term.cpu().numpy())
-        screens.append(hist.ring[:, hist.head].cpu().numpy())
+        screens.append(hist.planes(hist.head).cpu().numpy())
         agent.t += 1
         agent.step += 1
     assert abs(eps[0] - a3c.epsilon(100)) < 1e-12

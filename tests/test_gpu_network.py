@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import a3c, philox
-from util import REL_TOL, norm_err, rel_err
+from util import REL_TOL, norm_err, rel_err, unblock
 
 pytestmark = pytest.mark.gpu
 
@@ -38,6 +38,7 @@ def gpu_masks(net):
 
 def ring_stacks(ring_np, first_slot, steps):
     """oracle-side view of the ring: [steps*B, 84, 84, 4], t-major."""
+    ring_np = unblock(ring_np)
     B, R = ring_np.shape[:2]
     out = []
     for t in range(steps):
@@ -277,7 +278,7 @@ def _run_trajectory(pkg, cuda, A, B, T, updates, seed=123):
         ring = agent.history
         screens = []
         first = ring.first_slot(0)
-        snap = ring.ring.cpu().numpy()
+        snap = ring.planes().cpu().numpy()
         screens = [snap[:, (first + k) % ring.ring_slots] for k in range(4)]
         step0 = agent.step
         for t in range(T):
@@ -286,7 +287,7 @@ def _run_trajectory(pkg, cuda, A, B, T, updates, seed=123):
             agent.history.add(scr)
             agent.batch_reward[t].copy_(rew)
             agent.batch_terminal[t].copy_(term)
-            screens.append(agent.history.ring[:, agent.history.head].cpu().numpy())
+            screens.append(agent.history.planes(agent.history.head).cpu().numpy())
             agent.t += 1
             agent.step += 1
         agent.step -= 1                                          # lr uses the step of the last frame
@@ -383,7 +384,7 @@ def test_full_size_properties_4096_envs_t5(pkg, cuda):
     assert bool((g_full == g_again).all())                        # (3)
 
     # (1) forward of 48 random samples vs the oracle
-    ring = hist.ring.cpu().numpy()
+    ring = hist.planes().cpu().numpy()
     pick = rng.choice(T * B, 48, replace=False)
     stacks = np.stack([np.stack([ring[n % B, (n // B) + k] for k in range(4)], axis=-1) for n in pick])
     logits, value = a3c.forward(a3c.to_torch(params), stacks)

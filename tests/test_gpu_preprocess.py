@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import preprocess as P
-from util import golden_seq_frames
+from util import golden_seq_frames, unblock
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,7 @@ def push(pkg, frames_np, ring_slots=4, slot=0, replicate=1, ring=None):
     pkg._cabi.call("arl_preprocess_push", pkg._cabi.ptr(frames), pkg._cabi.ptr(ring), B,
                    ring.shape[1], slot, replicate, pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
-    return ring
+    return unblock(ring)                                         # row-major screens
 
 
 def test_golden_frames_bit_exact(pkg, cuda, golden):
@@ -138,7 +138,7 @@ def test_full_size_properties_4096_envs(pkg, cuda):
     pkg._cabi.call("arl_preprocess_push", pkg._cabi.ptr(frames), pkg._cabi.ptr(ring), B, 9, 8, 1,
                    pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
-    out = ring[:, 8]
+    out = unblock(ring[:, 8])
     first = torch.stack([out[(perm == k).nonzero()[0, 0]] for k in range(64)])
     assert bool((out == first[perm]).all())
     assert np.array_equal(first.cpu().numpy(), P.screen(base.cpu().numpy()))
@@ -164,4 +164,4 @@ def test_upload_frames_skips_only_unread_rows(pkg, cuda):
     keep = np.arange(210) % 5 != 2
     assert np.array_equal(got[:, keep], frames[:, keep])
     assert (got[:, ~keep] == 9).all()
-    assert np.array_equal(ring[:, 2].cpu().numpy(), P.screen(frames))
+    assert np.array_equal(unblock(ring[:, 2]).cpu().numpy(), P.screen(frames))

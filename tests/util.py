@@ -25,3 +25,24 @@ def golden_seq_frames(golden):
     """The 10 sequence frames of the fixture (rolls of frame random0, see oracle/make_golden.py)."""
     base = golden["frame_random0"]
     return [np.roll(base, tuple(int(v) for v in s), axis=(0, 1)) for s in golden["seq_shifts"]]
+
+
+def unblock(ring):
+    """Ring planes are stored in 4x4 blocks (space-to-depth, see src/history.py); returns the
+    row-major [..., 84, 84] screens.  numpy or torch."""
+    lead = tuple(ring.shape[:-2])
+    x = ring.reshape(lead + (21, 21, 4, 4))
+    n = len(lead)
+    order = tuple(range(n)) + (n, n + 2, n + 1, n + 3)
+    x = x.transpose(order) if isinstance(x, np.ndarray) else x.permute(*order)
+    return x.reshape(lead + (84, 84))
+
+
+def block(screens):
+    """Inverse of unblock."""
+    lead = tuple(screens.shape[:-2])
+    x = screens.reshape(lead + (21, 4, 21, 4))
+    n = len(lead)
+    order = tuple(range(n)) + (n, n + 2, n + 1, n + 3)
+    x = x.transpose(order) if isinstance(x, np.ndarray) else x.permute(*order)
+    return x.reshape(lead + (84, 84))
