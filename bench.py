@@ -211,6 +211,14 @@ def main():
 
     import torch
     import torch.distributed as dist
+    try:
+        # pin this rank to the CPUs next to its GPU BEFORE any pinned host buffer is allocated
+        # (first touch decides the NUMA node the end-to-end arm uploads from)
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
