@@ -199,10 +199,10 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
         try:
-            res = cpu_reference(cores, args.t_max, args.actions, 2, 1, 40)
+            res = cpu_reference(cores, args.t_max, args.actions, 2, 1, 250)   # ~10 s of CPU work
             cpu_base = {"value": res["frames_per_sec"], "unit": UNIT, "cores": cores,
                         "kind": "port",
-                        "sample": "%d workers x 2 timed steps x 40 cycles x t_max %d = %d frames "
+                        "sample": "%d workers x 2 timed steps x 250 cycles x t_max %d = %d frames "
                                   "(%.1f s)" % (cores, args.t_max, 2 * res["frames_per_step"],
                                                 sum(res["step_seconds"]))}
         except Exception as e:                                  # report, never fake
