@@ -229,47 +229,111 @@ struct Conv1FwdArgs {
   int64_t rows;          // 441 * num_samples (grid rows)
   int num_samples;
 };
+// The ring planes ARE the tensor-core operand: a plane is 441 blocks of 16 bytes, and 16 bytes
+// = 16 u8 K-values of one row is exactly the core-matrix row of the K-major no-swizzle layout for
+// 8-bit operands.  So the A image of a tile is 4 x (rows x 16 B) copied verbatim by
+// cp.async.bulk (no conversion, no LSU traffic), the MMA is kind::i8 (u8 x s8 -> s32, K = 32)
+// and the fp32 weights enter as three s8 limbs, w = s*(L0/64 + L1/2^13 + L2/2^20) (residual
+// < 5e-7 * max|w|), concatenated along N (N = 48: one MMA per K block instead of three).  The
+// integer accumulation is exact; the epilogue recombines the limb sums in fp32.
 struct Conv1Fwd : tc::PolicyBase {
   using Args = Conv1FwdArgs;
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
-  static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one k-chunk
-  static constexpr int PROD_WARPS = 16, STAGES = 8, STAGE_BYTES = 8 * PL;      // hi only
-  // resident W1 image: rows = [16 co hi | 16 co lo] (N = 32), 32 k-chunk planes
-  static constexpr int PLB = 33 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
-  static constexpr int ACC_COLS = 32, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
-  static constexpr bool HAS_AUX = true;
+  static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one 16-channel chunk
+  static constexpr int PROD_WARPS = 8, STAGES = 8, STAGE_BYTES = 4 * PL;       // u8: 4 planes
+  // resident W1 image (s8): rows = limb*16 + co (N = 48), 16 k-chunk planes (tap*4 + c); then
+  // the three limb scales
+  static constexpr int PLB = 49 * 16, B_IMG = 16 * PLB, SCALE_OFF = B_IMG, RES_BYTES = B_IMG + 16;
+  static constexpr int ACC_COLS = 64, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
+  static constexpr bool HAS_AUX = true, ACC_LIMBS3 = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
   static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
-    for (int ch = ptid; ch < 16 * 32; ch += nthr) {
-      const int co = ch & 15, kc = ch >> 4;                    // kc = tap*8 + c*2 + h
-      const int tap = kc >> 3, c = (kc >> 1) & 3, h = kc & 1, a = tap >> 1, b = tap & 1;
-      float x[8];
+    // (1) s = max |w1| over the tensor, by all producer threads (named barrier 1)
+    uint32_t* smax = reinterpret_cast<uint32_t*>(res + SCALE_OFF + 12);
+    if (ptid == 0) *smax = 0u;
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+    float m = 0.f;
+    for (int i = ptid; i < 4096; i += nthr) m = fmaxf(m, fabsf(g.params[i]));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = 2 * h + (e >> 2), j = e & 3;
-        x[e] = g.params[(((4 * a + i) * 8 + 4 * b + j) * 4 + c) * 16 + co];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((ptid & 31) == 0) atomicMax(smax, __float_as_uint(m));      // non-negative floats order as uints
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+    const float s = fmaxf(__uint_as_float(*smax), 1e-30f), inv = 1.0f / s;
+    if (ptid == 0) {
+      float* sc = reinterpret_cast<float*>(res + SCALE_OFF);
+      sc[0] = s * (1.0f / 64.0f); sc[1] = s * (1.0f / 8192.0f); sc[2] = s * (1.0f / 1048576.0f);
+    }
+    // (2) limbs: one thread per (k-chunk plane, co): 16 K-values = block bytes e = i*4 + j
+    for (int ch = ptid; ch < 16 * 16; ch += nthr) {
+      const int co = ch & 15, kc = ch >> 4, tap = kc >> 2, c = kc & 3, a = tap >> 1, b = tap & 1;
+      uint32_t l0[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0}, l2[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int i = e >> 2, j = e & 3;
+        const float v = g.params[(((4 * a + i) * 8 + 4 * b + j) * 4 + c) * 16 + co] * inv * 64.0f;
+        const float r0 = rintf(v), f1 = (v - r0) * 128.0f, r1 = rintf(f1), r2 = rintf((f1 - r1) * 128.0f);
+        l0[e >> 2] |= ((uint32_t)(int)r0 & 0xFFu) << (8 * (e & 3));
+        l1[e >> 2] |= ((uint32_t)(int)r1 & 0xFFu) << (8 * (e & 3));
+        l2[e >> 2] |= ((uint32_t)(int)r2 & 0xFFu) << (8 * (e & 3));
       }
-      tc::store_chunk_split(res, res + 16 * 16, kc * PLB + co * 16, x);
+      uint8_t* d = res + kc * PLB + co * 16;
+      *reinterpret_cast<uint4*>(d) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+      *reinterpret_cast<uint4*>(d + 16 * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+      *reinterpret_cast<uint4*>(d + 32 * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
     }
   }
+  // rows of the window that belong to no sample (only in the last tile) are zero-filled here
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
                                                     uint8_t* st, int glane, int gsize, Prod&) {
-    stream_x1<TROWS, PL, 10, false>(st, g.geo, t.mt * 128, g.num_samples, glane, gsize);
+    const int64_t valid = (int64_t)g.num_samples * GROWS - (int64_t)t.mt * 128;
+    if (valid >= TROWS) return;
+    for (int c = glane; c < TROWS * 4; c += gsize) {
+      const int r = c % TROWS, kc = c / TROWS;
+      if (r >= valid) *reinterpret_cast<uint4*>(st + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int, uint8_t* st,
+                                                    int glane, int, uint64_t* full) {
+    if (glane != 0) return false;
+    const int xr0 = t.mt * 128;
+    const int n0 = xr0 / GROWS, q0 = xr0 - n0 * GROWS;
+    // at most two samples intersect the window: rows [q0, 441) of n0, then rows [0, ..) of n0+1
+    int cnt[2] = {min(GROWS - q0, TROWS), 0};
+    cnt[1] = TROWS - cnt[0];
+    if (n0 >= g.num_samples) cnt[0] = 0;
+    if (n0 + 1 >= g.num_samples) cnt[1] = 0;
+    mbar_expect_tx(full, (uint32_t)(cnt[0] + cnt[1]) * 16u * 4u);
+    int roff = 0;
+#pragma unroll
+    for (int sgm = 0; sgm < 2; ++sgm) {
+      if (cnt[sgm] > 0) {
+        const int n = n0 + sgm, tt = n / g.geo.num_envs, b = n - tt * g.geo.num_envs;
+        const int qa = sgm == 0 ? q0 : 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int slot = (g.geo.first_slot + tt + c) % g.geo.ring_slots;
+          const uint8_t* src = g.geo.ring + ((size_t)b * g.geo.ring_slots + slot) * kPlane + qa * 16;
+          bulk_g2s(st + c * PL + roff * 16, src, (uint32_t)cnt[sgm] * 16u, full);
+        }
+      }
+      roff += sgm == 0 ? min(GROWS - q0, TROWS) : 0;
+    }
+    return true;
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(32);                 // x . [w_hi | w_lo]
+    constexpr uint32_t idesc = tc::make_idesc_i8(48);              // x(u8) . [L0 | L1 | L2](s8)
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
       const uint32_t a0 = st + ((tap >> 1) * GW + (tap & 1)) * 16;
 #pragma unroll
-      for (int k16 = 0; k16 < 4; ++k16) {
-        const uint64_t da = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
-        const uint32_t b0 = res + (tap * 8 + 2 * k16) * PLB;
-        tc::umma_f16(d, da, tc::make_sdesc(b0, PLB), idesc, (tap | k16) != 0 ? 1u : 0u);
+      for (int k32 = 0; k32 < 2; ++k32) {
+        const uint64_t da = tc::make_sdesc(a0 + 2 * k32 * PL, PL);
+        const uint64_t db = tc::make_sdesc(res + (tap * 4 + 2 * k32) * PLB, PLB);
+        tc::umma_i8(d, da, db, idesc, (tap | k32) != 0 ? 1u : 0u);
       }
     }
   }

@@ -70,6 +70,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (s32) (+)= A[smem desc] (u8) . B[smem desc] (s8), K = 32
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
@@ -102,6 +112,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// three s32 limb accumulators (int8 path), 8 columns each: v = a0*s0 + a1*s1 + a2*s2
+__device__ __forceinline__ void tmem_ld8_limbs3(uint32_t t0, uint32_t t1, uint32_t t2, float s0,
+                                                float s1, float s2, float (&v)[8]) {
+  uint32_t a[8], b[8], c[8];
+#define ARL_LD8(dst, addr)                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"          \
+               : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), \
+                 "=r"(dst[6]), "=r"(dst[7])                                                      \
+               : "r"(addr)                                                                       \
+               : "memory")
+  ARL_LD8(a, t0);
+  ARL_LD8(b, t1);
+  ARL_LD8(c, t2);
+#undef ARL_LD8
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    v[i] = fmaf((float)(int)a[i], s0, fmaf((float)(int)b[i], s1, (float)(int)c[i] * s2));
 }
 // hi-part + lo-part accumulators, 8 columns: two loads in flight, one wait
 __device__ __forceinline__ void tmem_ld8_sum(uint32_t taddr_a, uint32_t taddr_b, float (&v)[8]) {
@@ -148,6 +177,10 @@ __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr_a, uint32_t taddr_b
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+// instruction descriptor: u8 x s8 -> s32 (kind::i8), M=128, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 // shared-memory matrix descriptor, SWIZZLE_NONE.  The operand images in this file place the 16-B
 // vector of (index r of the 16-B-strided axis, chunk c of the other axis) at c*PLANE + r*16.
@@ -216,6 +249,14 @@ struct TileCoord {
 // column sums of the operand a producer streams through its registers anyway = a bias gradient).
 struct PolicyBase {
   static constexpr int EPI_SETS = 1;
+  static constexpr bool ACC_LIMBS3 = false;    // accumulators are 3 s32 limb sets (int8 path)
+  static constexpr int SCALE_OFF = 0;          // byte offset of the 3 limb scales in resident smem
+  // Operand data that needs no conversion is moved by cp.async.bulk: the hook runs after
+  // load_stage; the lane that issues copies does mbarrier.arrive.expect_tx on `full` itself and
+  // returns true (the framework then skips that lane's plain arrive).
+  template <class Args>
+  static __device__ __forceinline__ bool bulk_stage(const Args&, const TileCoord&, int, uint8_t*, int,
+                                                    int, uint64_t*) { return false; }
   static constexpr bool HAS_AUX = false;       // finish() needs an operand from HBM (bias, relu mask)
   static constexpr bool AUX_ROW_INVARIANT = true;   // ... that depends on the column only (bias)
   struct Prod {};
@@ -332,7 +373,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
         mbar_wait(&empty[pg], ((i / STAGES) & 1) ^ 1);
         P::load_stage(g, tc, s, st, glane, 32 * WPS, ps);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(&full[pg]);
+        if (!P::bulk_stage(g, tc, s, st, glane, 32 * WPS, &full[pg])) mbar_arrive(&full[pg]);
       }
       P::prod_end(g, tc, ps, pw, lane);
     }
@@ -409,7 +450,10 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           float v[8];
           const int c = sg * SEG + h * 8;
           const uint32_t ta = taddr + P::acc_col(c & ~15) + (c & 15);
-          if (P::LO_DELTA > 0) tmem_ld8_sum(ta, ta + P::LO_DELTA, v);
+          if (P::ACC_LIMBS3) {
+            const float* sc = reinterpret_cast<const float*>(res + P::SCALE_OFF);
+            tmem_ld8_limbs3(ta, ta + P::LO_DELTA, ta + 2 * P::LO_DELTA, sc[0], sc[1], sc[2], v);
+          } else if (P::LO_DELTA > 0) tmem_ld8_sum(ta, ta + P::LO_DELTA, v);
           else tmem_ld8(ta, v);
           float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 8);
           d[0] = make_float4(v[0], v[1], v[2], v[3]);
