@@ -240,7 +240,9 @@ struct Conv1Fwd : tc::PolicyBase {
   using Args = Conv1FwdArgs;
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one 16-channel chunk
-  static constexpr int PROD_WARPS = 8, STAGES = 8, STAGE_BYTES = 4 * PL;       // u8: 4 planes
+  // two epilogue sets: with bulk-copied operands and 8 short MMAs per tile the accumulator
+  // read-out is the longest stage of the pipeline
+  static constexpr int EPI_SETS = 2, PROD_WARPS = 8, STAGES = 8, STAGE_BYTES = 4 * PL;   // u8: 4 planes
   // resident W1 image (s8): rows = limb*16 + co (N = 48), 16 k-chunk planes (tap*4 + c); then
   // the three limb scales
   static constexpr int PLB = 49 * 16, B_IMG = 16 * PLB, SCALE_OFF = B_IMG, RES_BYTES = B_IMG + 16;
@@ -338,9 +340,8 @@ struct Conv1Fwd : tc::PolicyBase {
     }
   }
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
-    const int64_t xr = (int64_t)t.mt * 128 + row;
-    const int n = (int)(xr / GROWS);
-    const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
+    const int xr = t.mt * 128 + row, n = xr / GROWS;
+    const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
     if (n >= g.num_samples || yp >= 20 || xp >= 20) return nullptr;
     return g.a1 + ((int64_t)n * 400 + yp * 20 + xp) * 16;
   }
@@ -407,9 +408,8 @@ struct Conv2Fwd : tc::PolicyBase {
     }
   }
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
-    const int64_t xr = (int64_t)t.mt * 128 + row;
-    const int n = (int)(xr / GROWS);
-    const int q = (int)(xr - (int64_t)n * GROWS), yp = q / GW, xp = q - yp * GW;
+    const int xr = t.mt * 128 + row, n = xr / GROWS;
+    const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
     if (n >= g.num_samples || yp >= 9 || xp >= 9) return nullptr;
     return g.a2 + ((int64_t)n * 81 + yp * 9 + xp) * 32;
   }
@@ -485,9 +485,8 @@ struct Conv2Dgrad : tc::PolicyBase {
   // row (yy, xx) on the 11-wide grid -> the 2x2 block of dy1 pixels (2yy+dy, 2xx+dx); segment dy =
   // parity classes (dy,0),(dy,1) = two adjacent pixels = 32 contiguous floats
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
-    const int64_t pr = (int64_t)t.mt * 128 + row;
-    const int n = (int)(pr / GROWS);
-    const int q = (int)(pr - (int64_t)n * GROWS), yy = q / GW, xx = q - yy * GW;
+    const int pr = t.mt * 128 + row, n = pr / GROWS;
+    const int q = pr - n * GROWS, yy = q / GW, xx = q - yy * GW;
     if (n >= g.num_samples || yy >= 10 || xx >= 10) return nullptr;
     return g.dy1 + (int64_t)n * ARL_A1_ELEMS + ((2 * yy) * 20 + 2 * xx) * 16;
   }
@@ -694,7 +693,7 @@ extern "C" int arl_conv1_forward(const float* params, const uint8_t* ring, float
               "arl_conv1_forward: pointers must be 16-byte aligned");
   const int64_t N = (int64_t)num_envs * steps;
   if (N == 0) return ARL_OK;
-  ARL_REQUIRE(N * 441 / 128 < (1LL << 31) - 2, "arl_conv1_forward: too many samples");
+  ARL_REQUIRE(N * 441 < (1LL << 31) - 256, "arl_conv1_forward: too many samples");
   Conv1FwdArgs g{params, {ring, num_envs, ring_slots, first_slot}, a1, N * 441, (int)N};
   return tc::launch<Conv1Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
