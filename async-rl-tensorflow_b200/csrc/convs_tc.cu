@@ -241,7 +241,7 @@ struct Conv1Fwd : tc::PolicyBase {
   static constexpr int GW = 21, GROWS = 441, TROWS = 150;
   static constexpr int PL = (TROWS + 1) * 16;                 // 2416: plane of one 16-channel chunk
   // two epilogue sets: with bulk-copied operands and 8 short MMAs per tile the accumulator
-  // read-out is the longest stage of the pipeline
+  // read-out is the longest stage of the pipeline (four sets measured: no further gain)
   static constexpr int EPI_SETS = 2, PROD_WARPS = 8, STAGES = 8, STAGE_BYTES = 4 * PL;   // u8: 4 planes
   // resident W1 image (s8): rows = limb*16 + co (N = 48), 16 k-chunk planes (tap*4 + c); then
   // the three limb scales

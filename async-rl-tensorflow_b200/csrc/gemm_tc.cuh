@@ -326,21 +326,24 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   uint8_t* res = smem + STAGES * P::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;      // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // accumulator stages: one per epilogue set (at least two)
+  constexpr int NUM_ACC = P::EPI_SETS > 2 ? P::EPI_SETS : 2;
+  uint64_t* tfull = empty + STAGES;      // [NUM_ACC]
+  uint64_t* tempty = tfull + NUM_ACC;    // [NUM_ACC]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty + NUM_ACC);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t kTmemCols = 2 * P::ACC_COLS <= 32 ? 32 : 2 * P::ACC_COLS <= 64 ? 64
-                               : 2 * P::ACC_COLS <= 128 ? 128 : 2 * P::ACC_COLS <= 256 ? 256 : 512;
-  static_assert(2 * P::ACC_COLS <= 512 && P::ACC_COLS % 16 == 0, "TMEM budget");
+  constexpr uint32_t kTmemCols = NUM_ACC * P::ACC_COLS <= 32 ? 32 : NUM_ACC * P::ACC_COLS <= 64 ? 64
+                               : NUM_ACC * P::ACC_COLS <= 128 ? 128 : NUM_ACC * P::ACC_COLS <= 256 ? 256 : 512;
+  static_assert(NUM_ACC * P::ACC_COLS <= 512 && P::ACC_COLS % 16 == 0, "TMEM budget");
+  static_assert(P::EPI_SETS == 1 || P::EPI_SETS == 2 || P::EPI_SETS == 4, "EPI_SETS");
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 32 * WPS);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
     }
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
         const TileCoord tc = P::coord(g, item);
         const int ns = P::num_stages(g, tc);
-        const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
+        const uint32_t acc = k % NUM_ACC, acc_phase = (k / NUM_ACC) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * P::ACC_COLS;
@@ -410,8 +413,8 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     const int c4 = lane % LPR, rsub = lane / LPR, quad = warp & 3, set = warp >> 2;
     int k = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
-      if (P::EPI_SETS == 2 && (k & 1) != set) continue;
-      const uint32_t acc = k & 1, acc_phase = (k >> 1) & 1;
+      if (P::EPI_SETS > 1 && (k % P::EPI_SETS) != set) continue;
+      const uint32_t acc = k % NUM_ACC, acc_phase = (k / NUM_ACC) & 1;
       const TileCoord tc = P::coord(g, item);
       __syncwarp();
       rowp[lane] = P::row_ptr(g, tc, quad * 32 + lane);
