@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       P::prod_begin(ps);
       for (int s = 0; s < ns; ++s, ++i) {
         if (i % STAGES != pg) continue;
-        mbar_wait(&empty[pg], ((i / STAGES) & 1) ^ 1);
+        mbar_wait_sleep(&empty[pg], ((i / STAGES) & 1) ^ 1);
         P::load_stage(g, tc, s, st, glane, 32 * WPS, ps);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
         if (!P::bulk_stage(g, tc, s, st, glane, 32 * WPS, &full[pg])) mbar_arrive(&full[pg]);
@@ -389,12 +389,12 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
         const TileCoord tc = P::coord(g, item);
         const int ns = P::num_stages(g, tc);
         const uint32_t acc = k % NUM_ACC, acc_phase = (k / NUM_ACC) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait_sleep(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * P::ACC_COLS;
         for (int s = 0; s < ns; ++s, ++i) {
           const int stage = i % STAGES;
-          mbar_wait(&full[stage], (i / STAGES) & 1);
+          mbar_wait_sleep(&full[stage], (i / STAGES) & 1);
           tc_fence_after();
           P::issue(g, tc, s, smem_u32(smem + stage * P::STAGE_BYTES), res_addr, d_tmem);
           umma_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           for (int i = 0; i < NI; ++i) aux[i] = a;
         }
         if (!waited) {
-          mbar_wait(&tfull[acc], acc_phase);
+          mbar_wait_sleep(&tfull[acc], acc_phase);
           tc_fence_after();
           waited = true;
         }
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
         __syncwarp();
       }
       if (!waited) {
-        mbar_wait(&tfull[acc], acc_phase);
+        mbar_wait_sleep(&tfull[acc], acc_phase);
         tc_fence_after();
       }
       tc_fence_before();
