@@ -105,6 +105,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         : "memory");
   } while (ok == 0);
 }
+// the many warps that wait for long (producers for a free stage, epilogue warps for an
+// accumulator) back off between polls: every poll is a shared-memory wavefront
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(NS);
+}
 // 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       P::prod_begin(ps);
       for (int s = 0; s < ns; ++s, ++i) {
         if (i % STAGES != pg) continue;
-        mbar_wait_sleep(&empty[pg], ((i / STAGES) & 1) ^ 1);
+        mbar_wait_backoff<128>(&empty[pg], ((i / STAGES) & 1) ^ 1);
         P::load_stage(g, tc, s, st, glane, 32 * WPS, ps);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
         if (!P::bulk_stage(g, tc, s, st, glane, 32 * WPS, &full[pg])) mbar_arrive(&full[pg]);
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           for (int i = 0; i < NI; ++i) aux[i] = a;
         }
         if (!waited) {
-          mbar_wait_sleep(&tfull[acc], acc_phase);
+          mbar_wait_backoff<64>(&tfull[acc], acc_phase);
           tc_fence_after();
           waited = true;
         }
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
         __syncwarp();
       }
       if (!waited) {
-        mbar_wait_sleep(&tfull[acc], acc_phase);
+        mbar_wait_backoff<64>(&tfull[acc], acc_phase);
         tc_fence_after();
       }
       tc_fence_before();
