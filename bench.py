@@ -35,7 +35,7 @@ UNIT = "frames/s"
 ENTRY_WORK = {
     # entry: (kernels behind it, flop per sample (one exact pass), algorithmic HBM bytes per sample)
     "arl_preprocess_push": ("preprocess_kernel", 0.0, 80640 + 7056),
-    "arl_conv1_forward": ("tc_kernel<Conv1Fwd>", 2.0 * 1638400, 28224 + 25600),
+    "arl_conv1_forward": ("tc_kernel<Conv1Fwd> (kind::i8, bulk-copied ring)", 2.0 * 1638400, 28224 + 25600),
     "arl_conv2_forward": ("tc_kernel<Conv2Fwd>", 2.0 * 663552, 25600 + 10368),
     "arl_fc_forward": ("tc_kernel<GemmPolicy fc fwd>", 2.0 * 663552, 10368 + 1024),
     "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * 7, 1024 + 56),

@@ -12,9 +12,9 @@ ENTRY_OF = [
     ("preprocess_kernel", "arl_preprocess_push"),
     ("Conv1Fwd", "arl_conv1_forward"),
     ("Conv2Fwd", "arl_conv2_forward"),
-    ("GemmPolicy<64, 32, 0, 1, 1>", "arl_fc_forward"),
-    ("GemmPolicy<256, 16, 0, 0, 2>", "arl_fc_backward"),
-    ("GemmPolicy<256, 16, 1, 1, 0>", "arl_fc_backward"),
+    ("GemmPolicy<64, 32, 0, 1, 1", "arl_fc_forward"),
+    ("GemmPolicy<256, 16, 0, 0, 2", "arl_fc_backward"),
+    ("GemmPolicy<256, 16, 1, 1, 0", "arl_fc_backward"),
     ("Conv2Wgrad", "arl_conv2_backward"),
     ("Conv2Dgrad", "arl_conv2_backward"),
     ("Conv1Wgrad", "arl_conv1_backward"),
