@@ -123,51 +123,6 @@ using GridDy1 = PixelGrid<21, 441, 20, 20, 0, 4>;     // dy1 [N,400,16] on the c
 using GridDy2 = PixelGrid<10, 100, 9, 9, 0, 8>;       // dy2 [N,81,32] on the conv2 X2 grid
 using GridZ   = PixelGrid<11, 121, 9, 9, 1, 8>;       // dy2 zero-padded by one (transposed conv)
 
-// ---- conv2 A operand: space-to-depth rows of a1 ------------------------------------------------
-// X2 row (n, yp, xp) = a1[n][2yp..2yp+1][2xp..2xp+1][16] -> 8 chunks kc = (i*2+j)*2 + chalf.  The
-// 10 X2 rows of one (n, yp) are the 2560 contiguous bytes a1[n][2yp..2yp+1][:][:], and consecutive
-// (n, yp) follow each other, so a window of X2 rows is one contiguous float4 range of a1.
-// SHIFTED: also store the copy shifted by one row into planes 8..15 (tap b = 1 of the wgrad).
-template <int ROWS, int PL, int U, bool SHIFTED>
-__device__ __forceinline__ void stream_x2(uint8_t* hi, uint8_t* lo, const float* __restrict__ a1,
-                                          int xr0, int num_samples, int glane, int gsize) {
-  const int Y0 = xr0 / 10;
-  const int nY = (xr0 + ROWS - 1) / 10 - Y0 + 1;
-  const int Yrem = num_samples * 10 - Y0;                    // (n, yp) pairs that exist from Y0 on
-  const float4* s4 = reinterpret_cast<const float4*>(a1) + (int64_t)Y0 * 160;
-  const int total = nY * 160;
-  const int rbase = Y0 * 10 - xr0;                           // row of (Y0, xp = 0) in the window
-  for (int f0 = glane; f0 < total; f0 += U * gsize) {
-    float4 x[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int f = f0 + u * gsize;
-      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f < total && f / 160 < Yrem) x[u] = __ldg(s4 + f);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int f = f0 + u * gsize;
-      if (f >= total) break;
-      const int Yl = f / 160, w = f - Yl * 160, i = w >= 80 ? 1 : 0, wp = w - 80 * i;
-      const int pix = wp >> 2, q4 = wp & 3, xp = pix >> 1, j = pix & 1;
-      const int r = rbase + Yl * 10 + xp;
-      if (r < 0 || r >= ROWS) continue;
-      const int kc = (i * 2 + j) * 2 + (q4 >> 1);
-      const int off = kc * PL + r * 16 + (q4 & 1) * 8;
-      uint2 h, l;
-      tc::split2(x[u].x, x[u].y, h.x, l.x);
-      tc::split2(x[u].z, x[u].w, h.y, l.y);
-      *reinterpret_cast<uint2*>(hi + off) = h;
-      *reinterpret_cast<uint2*>(lo + off) = l;
-      if (SHIFTED && r > 0) {
-        *reinterpret_cast<uint2*>(hi + off + 8 * PL - 16) = h;
-        *reinterpret_cast<uint2*>(lo + off + 8 * PL - 16) = l;
-      }
-    }
-  }
-}
-
 // ---- conv1 A operand: space-to-depth rows of the u8 ring ---------------------------------------
 // The ring stores every 84x84 plane in 4x4 blocks (K1 writes it that way): the 16 bytes at
 // plane + q*16 are block q = y'*21 + x' = frame rows 4y'..4y'+3, columns 4x'..4x'+3 = the 16
@@ -221,11 +176,64 @@ __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr
   }
 }
 
+// ---- a1 in HBM: split bf16, blocked ("a1s") ----------------------------------------------------
+// conv1's output is only ever consumed as a tensor-core operand (conv2 forward / conv2 wgrad)
+// and as a relu mask (conv2 dgrad), so it is stored the way those kernels want it -- same 25 600
+// bytes per sample as fp32 [20,20,16], but as bf16 hi and lo planes in space-to-depth order:
+//   a1s[n][part (hi,lo)][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 channels]     (16-B vectors)
+// with pixel (y,x) = (2yp+i, 2xp+j) and channels chalf*8 .. chalf*8+7.  A run of X2 rows of one
+// (part, kc) is then contiguous: the conv2 kernels fetch their A images with cp.async.bulk and
+// convert nothing.  hi + lo reproduces the fp32 value to ~2^-17 relative.
+constexpr int kA1sSample = 25600, kA1sPart = 12800, kA1sPlane = 1600;    // bytes
+__device__ __forceinline__ int a1s_offset(int y, int x, int chalf) {       // bytes inside a part
+  return (((y & 1) * 2 + (x & 1)) * 2 + chalf) * kA1sPlane + ((y >> 1) * 10 + (x >> 1)) * 16;
+}
+
+// Bulk copies of X2 grid rows [xr0, xr0 + ROWS) of planes (part, kc) into an image whose vector
+// (row r, kc) sits at part*IMG + kc*PL + r*16; SHIFT additionally fills planes 8..15 with the
+// image shifted by one row (tap b = 1 of the wgrad).  Called by the lanes that own one (part, kc)
+// each; returns the bytes this lane has put in flight (it must expect_tx them BEFORE calling).
+template <int ROWS, int PL, int IMG, bool SHIFT>
+__device__ __forceinline__ uint32_t a1s_bulk_bytes(int xr0, int num_samples) {
+  // bytes one (part, kc) owner moves: every existing row once (+ once more, minus the first, if SHIFT)
+  const int rows_left = num_samples * 100 - xr0;
+  const int n = rows_left < ROWS ? (rows_left > 0 ? rows_left : 0) : ROWS;
+  return (uint32_t)(SHIFT ? (n > 0 ? 2 * n - 1 : 0) : n) * 16u;
+}
+template <int ROWS, int PL, int IMG, bool SHIFT>
+__device__ __forceinline__ void a1s_bulk_issue(uint8_t* st, const uint8_t* a1s, int xr0, int num_samples,
+                                               int part, int kc, uint64_t* full) {
+  int r = 0, n = xr0 / 100, q = xr0 - n * 100;
+  while (r < ROWS && n < num_samples) {
+    const int cnt = min(100 - q, ROWS - r);
+    const uint8_t* src = a1s + (size_t)n * kA1sSample + part * kA1sPart + kc * kA1sPlane + q * 16;
+    uint8_t* dst = st + part * IMG + kc * PL + r * 16;
+    bulk_g2s(dst, src, (uint32_t)cnt * 16u, full);
+    if (SHIFT) {
+      if (r > 0) bulk_g2s(dst + 8 * PL - 16, src, (uint32_t)cnt * 16u, full);
+      else if (cnt > 1) bulk_g2s(dst + 8 * PL, src + 16, (uint32_t)(cnt - 1) * 16u, full);
+    }
+    r += cnt; q = 0; ++n;
+  }
+}
+// rows of the window beyond the last sample (last tile only): zero, by all lanes of the group
+template <int ROWS, int PL, int IMG, int PLANES>
+__device__ __forceinline__ void a1s_zero_tail(uint8_t* st, int xr0, int num_samples, int glane, int gsize) {
+  const int valid = num_samples * 100 - xr0;
+  if (valid >= ROWS) return;
+  for (int c = glane; c < ROWS * PLANES * 2; c += gsize) {
+    const int r = c % ROWS, pk = c / ROWS, part = pk / PLANES, kc = pk - part * PLANES;
+    // planes 8.. (if any) hold the image shifted by one row: their row r is source row r+1
+    if (r >= valid - (kc >= 8 ? 1 : 0))
+      *reinterpret_cast<uint4*>(st + part * IMG + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // =================================== conv1 forward ============================================
 struct Conv1FwdArgs {
   const float* params;
   RingGeo geo;
-  float* a1;
+  uint8_t* a1s;          // split-bf16 blocked output (see a1s above), 25 600 B per sample
   int64_t rows;          // 441 * num_samples (grid rows)
   int num_samples;
 };
@@ -247,7 +255,7 @@ struct Conv1Fwd : tc::PolicyBase {
   // the three limb scales
   static constexpr int PLB = 49 * 16, B_IMG = 16 * PLB, SCALE_OFF = B_IMG, RES_BYTES = B_IMG + 16;
   static constexpr int ACC_COLS = 64, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
-  static constexpr bool HAS_AUX = true, ACC_LIMBS3 = true;
+  static constexpr bool CUSTOM_EPI = true, ACC_LIMBS3 = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -339,25 +347,43 @@ struct Conv1Fwd : tc::PolicyBase {
       }
     }
   }
-  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
+  // epilogue: lane = output pixel; limbs -> fp32 -> /255 + bias, relu -> bf16 hi/lo -> four 16-B
+  // vectors straight into the a1s planes (no staging: 16 consecutive lanes write 256 contiguous B)
+  static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t,
+                                                         const uint8_t* res, uint32_t taddr, int row) {
+    const float* sc = reinterpret_cast<const float*>(res + SCALE_OFF);
+    float v[16];
+    {
+      float a[8], b[8];
+      tc::tmem_ld8_limbs3(taddr, taddr + 16, taddr + 32, sc[0], sc[1], sc[2], a);
+      tc::tmem_ld8_limbs3(taddr + 8, taddr + 24, taddr + 40, sc[0], sc[1], sc[2], b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[e] = a[e]; v[8 + e] = b[e]; }
+    }
     const int xr = t.mt * 128 + row, n = xr / GROWS;
-    const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
-    if (n >= g.num_samples || yp >= 20 || xp >= 20) return nullptr;
-    return g.a1 + ((int64_t)n * 400 + yp * 20 + xp) * 16;
-  }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col) {
-    return tc::ldg4(g.params + 4096 + col);
-  }
-  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 bb) {
-    return make_float4(fmaxf(fmaf(v.x, 1.0f / 255.0f, bb.x), 0.f), fmaxf(fmaf(v.y, 1.0f / 255.0f, bb.y), 0.f),
-                       fmaxf(fmaf(v.z, 1.0f / 255.0f, bb.z), 0.f), fmaxf(fmaf(v.w, 1.0f / 255.0f, bb.w), 0.f));
+    const int q = xr - n * GROWS, y = q / GW, x = q - y * GW;
+    if (n >= g.num_samples || y >= 20 || x >= 20) return;
+    const float* bias = g.params + 4096;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(bias) + e);
+      const float o0 = fmaxf(fmaf(v[2 * e], 1.0f / 255.0f, bb.x), 0.f);
+      const float o1 = fmaxf(fmaf(v[2 * e + 1], 1.0f / 255.0f, bb.y), 0.f);
+      tc::split2(o0, o1, hi[e], lo[e]);
+    }
+    uint8_t* d = g.a1s + (size_t)n * kA1sSample + a1s_offset(y, x, 0);
+    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(d + kA1sPlane) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(d + kA1sPart) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(d + kA1sPart + kA1sPlane) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
   }
 };
 
 // =================================== conv2 forward ============================================
 struct Conv2FwdArgs {
   const float* params;
-  const float* a1;
+  const uint8_t* a1s;    // split-bf16 blocked conv1 output
   float* a2;
   int64_t rows;          // 100 * num_samples
   int num_samples;
@@ -365,8 +391,10 @@ struct Conv2FwdArgs {
 struct Conv2Fwd : tc::PolicyBase {
   using Args = Conv2FwdArgs;
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PL = 146 * 16, IMG = 8 * PL;           // plane rows = 2 (mod 8): 8-B stores conflict-free
-  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
+  static constexpr int PL = (TROWS + 1) * 16, IMG = 8 * PL;
+  // operands arrive by cp.async.bulk straight from the a1s planes: one producer warp per stage,
+  // lanes 0..15 own one (part, kc) plane each; two epilogue sets
+  static constexpr int EPI_SETS = 2, PROD_WARPS = 4, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
   // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
   static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
@@ -389,7 +417,14 @@ struct Conv2Fwd : tc::PolicyBase {
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
                                                     uint8_t* st, int glane, int gsize, Prod&) {
-    stream_x2<TROWS, PL, 8, false>(st, st + IMG, g.a1, t.mt * 128, g.num_samples, glane, gsize);
+    a1s_zero_tail<TROWS, PL, IMG, 8>(st, t.mt * 128, g.num_samples, glane, gsize);
+  }
+  static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int, uint8_t* st,
+                                                    int glane, int, uint64_t* full) {
+    if (glane >= 16) return false;
+    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PL, IMG, false>(t.mt * 128, g.num_samples));
+    a1s_bulk_issue<TROWS, PL, IMG, false>(st, g.a1s, t.mt * 128, g.num_samples, glane >> 3, glane & 7, full);
+    return true;
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
@@ -413,7 +448,8 @@ struct Conv2Fwd : tc::PolicyBase {
     if (n >= g.num_samples || yp >= 9 || xp >= 9) return nullptr;
     return g.a2 + ((int64_t)n * 81 + yp * 9 + xp) * 32;
   }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col) {
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col,
+                                                    int64_t) {
     return tc::ldg4(g.params + 4112 + 8192 + col);
   }
   static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 bb) {
@@ -425,7 +461,7 @@ struct Conv2Fwd : tc::PolicyBase {
 // =================================== conv2 input gradient =====================================
 struct Conv2DgradArgs {
   const float* params;
-  const float* a1;       // relu mask of conv1
+  const uint8_t* a1s;    // relu mask of conv1: sign of the hi plane of the split-bf16 output
   const float* dy2;      // [N, 81, 32]
   float* dy1;            // [N, 400, 16]
   int64_t rows;          // 121 * num_samples
@@ -493,8 +529,21 @@ struct Conv2Dgrad : tc::PolicyBase {
   static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int dy) {
     return dy * 20 * 16;
   }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float* dst, int) {
-    return tc::ldg4(g.a1 + (dst - g.dy1));
+  // relu mask = sign of a1's hi plane.  Row (yy,xx) covers pixels (2yy+dy, 2xx+dx): all four share
+  // q = yy*10 + xx, so one byte offset per row serves its loads; lane (dy, col) adds its plane:
+  // kc = (dy*2 + dx)*2 + chalf, and 8 bytes = 4 channels inside the 16-B vector.
+  static __device__ __forceinline__ int64_t row_aux(const Args& g, const TileCoord& t, int row) {
+    const int pr = t.mt * 128 + row, n = pr / GROWS;
+    const int q = pr - n * GROWS, yy = q / GW, xx = q - yy * GW;
+    return (int64_t)n * kA1sSample + (yy * 10 + xx) * 16;
+  }
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col,
+                                                    int64_t row_off) {
+    // col = dy*32 + dx*16 + channel (a multiple of 4)
+    const int kc = (col >> 4) * 2 + ((col >> 3) & 1);
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(g.a1s + row_off + kc * kA1sPlane + (col & 7) * 2));
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+                       __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
   }
   static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 m) {
     return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f,
@@ -524,7 +573,7 @@ __device__ __forceinline__ void bias_partial_store(float* dst_row, float (&acc)[
 }
 
 struct Conv2WgradArgs {
-  const float* a1;
+  const uint8_t* a1s;    // split-bf16 blocked conv1 output
   const float* dy2;
   float* partials;       // [items][8192]
   float* bias_partials;  // [items * PROD_WARPS][32]  column sums of dy2 (= db2), per producer warp
@@ -535,7 +584,7 @@ struct Conv2Wgrad : tc::PolicyBase {
   using Args = Conv2WgradArgs;
   struct Prod { float acc[4]; };    // running column sums of dy2 (bias gradient)
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PLA = 146 * 16, A_IMG = 16 * PLA;           // 2 shifted copies x 8 ch groups
+  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // 2 shifted copies x 8 ch groups
   static constexpr int PLB = 130 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
   static constexpr int PROD_WARPS = 16, STAGES = 2, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
   // accumulator columns: a*64 + part*32 + co (the lo image of dy2 follows its hi image, so one
@@ -557,12 +606,23 @@ struct Conv2Wgrad : tc::PolicyBase {
                                                     uint8_t* st, int glane, int gsize, Prod& ps) {
     const int p0 = t.k_begin + s * 128;
     uint8_t* a_hi = st, *a_lo = st + A_IMG, *b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
-    // A: X2 rows p0 .. p0+139; planes 0..7 hold row r at r*16, planes 8..15 the same image shifted
-    // by one row (tap b = 1)
-    stream_x2<TROWS, PLA, 5, true>(a_hi, a_lo, g.a1, p0, g.num_samples, glane, gsize);
+    // A: X2 rows p0 .. p0+139 arrive by cp.async.bulk (bulk_stage); only the rows beyond the last
+    // sample need zeros here
+    a1s_zero_tail<TROWS, PLA, A_IMG, 16>(a_hi, p0, g.num_samples, glane, gsize);
+    (void)a_lo;
     // B: dy2 on the 10-wide grid, zero at y'=9 / x'=9 and outside [k_begin, k_end)
     stream_pixels<GridDy2, 8, 128, PLB, 5, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
                                                  gsize, ps.acc);
+  }
+  // planes 0..7 hold row r at r*16, planes 8..15 the same image shifted by one row (tap b = 1);
+  // lanes 0, 16, 32, ... of the stage's 256 own one (part, kc) plane pair each
+  static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
+                                                    int glane, int, uint64_t* full) {
+    if ((glane & 15) != 0) return false;
+    const int p0 = t.k_begin + s * 128, owner = glane >> 4;          // 0..15
+    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PLA, A_IMG, true>(p0, g.num_samples));
+    a1s_bulk_issue<TROWS, PLA, A_IMG, true>(st, g.a1s, p0, g.num_samples, owner >> 3, owner & 7, full);
+    return true;
   }
   static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
                                                   int lane) {
@@ -694,7 +754,7 @@ extern "C" int arl_conv1_forward(const float* params, const uint8_t* ring, float
   const int64_t N = (int64_t)num_envs * steps;
   if (N == 0) return ARL_OK;
   ARL_REQUIRE(N * 441 < (1LL << 31) - 256, "arl_conv1_forward: too many samples");
-  Conv1FwdArgs g{params, {ring, num_envs, ring_slots, first_slot}, a1, N * 441, (int)N};
+  Conv1FwdArgs g{params, {ring, num_envs, ring_slots, first_slot}, reinterpret_cast<uint8_t*>(a1), N * 441, (int)N};
   return tc::launch<Conv1Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 
@@ -705,7 +765,7 @@ extern "C" int arl_conv2_forward(const float* params, const float* a1, float* a2
   ARL_REQUIRE(aligned16(params) && aligned16(a1) && aligned16(a2),
               "arl_conv2_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
-  Conv2FwdArgs g{params, a1, a2, num_samples * 100, (int)num_samples};
+  Conv2FwdArgs g{params, reinterpret_cast<const uint8_t*>(a1), a2, num_samples * 100, (int)num_samples};
   return tc::launch<Conv2Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 
@@ -758,7 +818,7 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
     return ARL_OK;
   }
   Conv2WgradArgs w;
-  w.a1 = a1;
+  w.a1s = reinterpret_cast<const uint8_t*>(a1);
   w.dy2 = d_a2;
   w.partials = (float*)workspace;
   w.rows = num_samples * 100;
@@ -772,6 +832,6 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
   // l2_b = column sums of d_a2, accumulated by the wgrad producers while they stream d_a2
   rc = reduce_partials(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, st);
   if (rc) return rc;
-  Conv2DgradArgs d{params, a1, d_a2, d_a1, num_samples * 121, (int)num_samples};
+  Conv2DgradArgs d{params, reinterpret_cast<const uint8_t*>(a1), d_a2, d_a1, num_samples * 121, (int)num_samples};
   return tc::launch<Conv2Dgrad>(d, (int)((d.rows + 127) / 128), st);
 }

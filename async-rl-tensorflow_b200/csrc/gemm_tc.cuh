@@ -249,6 +249,12 @@ struct TileCoord {
 // column sums of the operand a producer streams through its registers anyway = a bias gradient).
 struct PolicyBase {
   static constexpr int EPI_SETS = 1;
+  static constexpr bool CUSTOM_EPI = false;    // policy provides custom_epilogue(g, tc, res, taddr, row)
+  template <class Args>
+  static __device__ __forceinline__ void custom_epilogue(const Args&, const TileCoord&, const uint8_t*,
+                                                         uint32_t, int) {}
+  template <class Args>
+  static __device__ __forceinline__ float* row_ptr(const Args&, const TileCoord&, int) { return nullptr; }
   static constexpr bool ACC_LIMBS3 = false;    // accumulators are 3 s32 limb sets (int8 path)
   static constexpr int SCALE_OFF = 0;          // byte offset of the 3 limb scales in resident smem
   // Operand data that needs no conversion is moved by cp.async.bulk: the hook runs after
@@ -270,9 +276,12 @@ struct PolicyBase {
   template <class Args>
   static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int) { return 0; }
   template <class Args>
-  static __device__ __forceinline__ float4 aux_load(const Args&, const TileCoord&, const float*, int) {
+  static __device__ __forceinline__ float4 aux_load(const Args&, const TileCoord&, const float*, int, int64_t) {
     return make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  // per-row quantity the aux loads of a row share (computed once per row, kept in smem)
+  template <class Args>
+  static __device__ __forceinline__ int64_t row_aux(const Args&, const TileCoord&, int) { return 0; }
   template <class Args>
   static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4) { return v; }
 };
@@ -310,7 +319,7 @@ struct Smem {
   static constexpr int BAR_OFF = P::STAGES * P::STAGE_BYTES + P::RES_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 512;                 // up to 2*16 + 4 mbarriers + TMEM slot
   static constexpr int EPI_ROW = (P::SEG + 4) * 4;              // staged row, padded: conflict-free
-  static constexpr int EPI_WARP = 32 * EPI_ROW + 32 * 8;        // staging + 32 row pointers
+  static constexpr int EPI_WARP = 32 * EPI_ROW + 32 * 8 + 32 * 8;   // staging + 32 row pointers + 32 row aux offsets
   static constexpr int TOTAL = EPI_OFF + epi_warps<P>() * EPI_WARP;
 };
 
@@ -409,6 +418,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     uint8_t* ep = smem + S::EPI_OFF + warp * S::EPI_WARP;
     float* stg = reinterpret_cast<float*>(ep);
     float** rowp = reinterpret_cast<float**>(ep + 32 * S::EPI_ROW);
+    int64_t* rowa = reinterpret_cast<int64_t*>(ep + 32 * S::EPI_ROW + 32 * 8);
     constexpr int NI = 32 / RPI;
     const int c4 = lane % LPR, rsub = lane / LPR, quad = warp & 3, set = warp >> 2;
     int k = 0;
@@ -416,8 +426,19 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       if (P::EPI_SETS > 1 && (k % P::EPI_SETS) != set) continue;
       const uint32_t acc = k % NUM_ACC, acc_phase = (k / NUM_ACC) & 1;
       const TileCoord tc = P::coord(g, item);
+      if constexpr (P::CUSTOM_EPI) {
+        // the policy reads its accumulator row (lane = row) and writes its output itself
+        mbar_wait_backoff<64>(&tfull[acc], acc_phase);
+        tc_fence_after();
+        P::custom_epilogue(g, tc, res, tmem_base + ((uint32_t)(quad * 32) << 16) + acc * P::ACC_COLS,
+                           quad * 32 + lane);
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        continue;
+      }
       __syncwarp();
       rowp[lane] = P::row_ptr(g, tc, quad * 32 + lane);
+      if (P::HAS_AUX && !P::AUX_ROW_INVARIANT) rowa[lane] = P::row_aux(g, tc, quad * 32 + lane);
       __syncwarp();
       bool waited = false;
 #pragma unroll 1
@@ -434,10 +455,10 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           const float* base = rowp[i * RPI + rsub];
           aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (P::HAS_AUX && !P::AUX_ROW_INVARIANT && cok && base != nullptr)
-            aux[i] = P::aux_load(g, tc, base + soff, sg * SEG + c4 * 4);
+            aux[i] = P::aux_load(g, tc, base + soff, sg * SEG + c4 * 4, rowa[i * RPI + rsub]);
         }
         if (P::HAS_AUX && P::AUX_ROW_INVARIANT && cok) {         // e.g. a bias: one load serves all rows
-          const float4 a = P::aux_load(g, tc, nullptr, sg * SEG + c4 * 4);
+          const float4 a = P::aux_load(g, tc, nullptr, sg * SEG + c4 * 4, 0);
 #pragma unroll
           for (int i = 0; i < NI; ++i) aux[i] = a;
         }
@@ -638,7 +659,7 @@ struct GemmPolicy : PolicyBase {
     return t.nt * N_TILE + col < g.N;
   }
   static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord& t, const float* dst,
-                                                    int col) {
+                                                    int col, int64_t) {
     if (EPI == EPI_BIAS_RELU) return ldg4(g.extra + t.nt * N_TILE + col);
     if (EPI == EPI_MASK) return ldg4(g.extra + (dst - g.D));
     return make_float4(0.f, 0.f, 0.f, 0.f);

@@ -20,6 +20,18 @@ PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l4_w", "l4_b", "p_w", "p_b", "q_
 A1_ELEMS, A2_ELEMS, FC = 6400, 2592, 256
 
 
+def decode_a1(raw):
+    """conv1's output lives in HBM as split bf16 in space-to-depth blocks (csrc/convs_tc.cu "a1s":
+    [n][hi|lo][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 ch], pixel (y,x) = (2yp+i, 2xp+j)) -- the
+    layout the conv2 tensor-core kernels consume without conversion.  ``raw`` is the float32
+    [N,20,20,16]-shaped storage the C-ABI fills; returns the float32 [N,20,20,16] activations
+    (network.py:47-48 l1)."""
+    n = raw.shape[0]
+    b = raw.reshape(n, 6400).view(torch.bfloat16).reshape(n, 2, 2, 2, 2, 10, 10, 8)
+    v = b[:, 0].float() + b[:, 1].float()                     # [n, i, j, chalf, yp, xp, 8]
+    return v.permute(0, 4, 1, 5, 2, 3, 6).reshape(n, 20, 20, 16)
+
+
 def param_shapes(action_size):
     return OrderedDict([
         ("l1_w", (8, 8, 4, 16)), ("l1_b", (16,)), ("l2_w", (4, 4, 16, 32)), ("l2_b", (32,)),
@@ -84,7 +96,7 @@ class Network(object):
         N = B * T
         f32 = dict(device=dev, dtype=torch.float32)
         # rollout activations, t-major: sample n = t*B + b
-        self.l1 = torch.empty(N, 20, 20, 16, **f32)           # network.py:47-48
+        self.l1 = torch.empty(N, 20, 20, 16, **f32)           # network.py:47-48, stored split-bf16 blocked: see a1()
         self.l2 = torch.empty(N, A2_ELEMS, **f32)             # network.py:49-50 (flattened NHWC)
         self.l4 = torch.empty(N, FC, **f32)                   # network.py:51-52
         self.policy_logits = torch.empty(N, A, **f32)         # network.py:62
@@ -162,6 +174,10 @@ class Network(object):
         self._forward_into(history, self.l1[r], self.l2[r], self.l4[r], self.policy_logits[r],
                            self.policy[r], self.value[r])
         return self.policy_logits[r], self.policy[r], self.value[r]
+
+    def a1(self):
+        """conv1 activations of the rollout as float32 [N,20,20,16] (decoded from the device layout)."""
+        return decode_a1(self.l1)
 
     def sample(self, t, step, seed, env_id_base=0):
         """network.py:72-73 sampled_action for rollout slot t."""

@@ -32,7 +32,7 @@ def net_for(pkg, A, B, T, params):
 
 def gpu_masks(net):
     """relu activation pattern of the device forward (see oracle.a3c._relu)."""
-    return dict(a1=(net.l1 > 0).cpu().numpy(), a2=(net.l2 > 0).cpu().numpy(),
+    return dict(a1=(net.a1() > 0).cpu().numpy(), a2=(net.l2 > 0).cpu().numpy(),
                 h=(net.l4 > 0).cpu().numpy())
 
 
@@ -62,6 +62,7 @@ def test_forward_layers_vs_oracle(pkg, cuda, A, B, T, R, first):
                    a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
                    v.data_ptr(), pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
+    a1 = pkg.network.decode_a1(a1)                                # device layout: split bf16, blocked
     logits, value, keep = a3c.forward(a3c.to_torch(params), ring_stacks(ring_np, first, T), keep=True)
     pi, _, _ = a3c.policy_terms(logits)
     errs = dict(a1=rel_err(a1.cpu(), keep["a1"]), a2=rel_err(a2.cpu(), keep["a2"]),
@@ -90,7 +91,7 @@ def test_ops_wrappers_layer_by_layer(pkg, cuda):
     torch.cuda.synchronize()
     stacks = hist.get().cpu().numpy()
     logits, value, keep = a3c.forward(a3c.to_torch(params), stacks, keep=True)
-    assert rel_err(l1.cpu(), keep["a1"]) <= REL_TOL and rel_err(l4.cpu(), keep["h"]) <= REL_TOL
+    assert rel_err(pkg.network.decode_a1(l1).cpu(), keep["a1"]) <= REL_TOL and rel_err(l4.cpu(), keep["h"]) <= REL_TOL
     assert rel_err(lg.cpu(), logits) <= REL_TOL and rel_err(v.cpu(), value) <= REL_TOL
     ref_act = philox.sample_actions(pr.cpu().numpy(), np.arange(10, 10 + B), 5, 123)
     assert np.array_equal(act.cpu().numpy(), ref_act)
