@@ -87,21 +87,47 @@ struct __align__(16) K1Smem {
   uint64_t full[2], empty[2], out_full[2], out_empty[2];
 };
 
-// rare path (3384 of 2^24 triples: the exact value is an integer): is this one of the 774 where
-// the reference's float64 sum lands one ulp below?  Kept out of line so that the common path is
-// two dp4a, the division and one compare -- not a predicated copy of this lookup per pixel.
+// luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path: per
+// pixel two dp4a (coefficients held in registers), the exact division by 10000 and one compare;
+// the "exact multiple of 10000" flags of the 8 pixels are OR-ed and tested ONCE.  Only then
+// (3384 of 2^24 triples; 774 of them need the -1) the correction bitmap is consulted.
+struct LumaCoef { uint32_t c0, c1, c0s, c1s; };
+__device__ __forceinline__ LumaCoef luma_coef() {
+  LumaCoef k;      // opaque to constant propagation: stays in registers instead of a UMOV per use
+  asm volatile("mov.u32 %0, 0x00D2F04E;" : "=r"(k.c0));
+  asm volatile("mov.u32 %0, 0x00021B08;" : "=r"(k.c1));
+  asm volatile("mov.u32 %0, 0xD2F04E00;" : "=r"(k.c0s));
+  asm volatile("mov.u32 %0, 0x021B0800;" : "=r"(k.c1s));
+  return k;
+}
 __device__ __noinline__ uint32_t luma_fix_lookup(uint32_t rg /* G*256 + R */, const uint32_t* fix) {
   return (fix[rg >> 5] >> (rg & 31)) & 1u;
 }
-// luma of the pixel whose R,G,B bytes sit at byte SHIFT.. of w (the other byte is ignored: its
-// dp4a coefficient is 0)
-template <int SHIFT>
-__device__ __forceinline__ uint32_t luma8(uint32_t w, const uint32_t* fix) {
-  constexpr uint32_t C0 = 0x00D2F04Eu << (8 * SHIFT), C1 = 0x00021B08u << (8 * SHIFT);
-  const uint32_t s = __dp4a(w, C0, 0u) + (__dp4a(w, C1, 0u) << 8);
-  uint32_t q = __umulhi(s, 3518437209u) >> 13;               // s / 10000, exact for s <= 2 550 000
-  if (__builtin_expect(s == q * 10000u, 0)) q -= luma_fix_lookup((w >> (8 * SHIFT)) & 0xFFFFu, fix);
-  return q;
+__device__ __forceinline__ void luma_px(uint32_t w, uint32_t c0, uint32_t c1, uint32_t& q, uint32_t& rem0) {
+  const uint32_t s = __dp4a(w, c0, 0u) + (__dp4a(w, c1, 0u) << 8);
+  q = __umulhi(s, 3518437209u) >> 13;                         // s / 10000, exact for s <= 2 550 000
+  rem0 = s - q * 10000u;                                      // 0 <=> exact multiple
+}
+__device__ __forceinline__ uint2 luma_8px(const uint32_t (&w)[6], const LumaCoef& k, const uint32_t* fix) {
+  uint32_t px[8], q[8], r[8];
+  px[0] = w[0];                            px[1] = __byte_perm(w[0], w[1], 0x4543);   // bytes 3,4,5
+  px[2] = __byte_perm(w[1], w[2], 0x4432); px[3] = w[2];                              // 6,7,8 | 9,10,11 (<<8)
+  px[4] = w[3];                            px[5] = __byte_perm(w[3], w[4], 0x4543);
+  px[6] = __byte_perm(w[4], w[5], 0x4432); px[7] = w[5];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = (i & 3) == 3;                             // pixel sits in bytes 1..3 of its word
+    luma_px(px[i], hi ? k.c0s : k.c0, hi ? k.c1s : k.c1, q[i], r[i]);
+  }
+  const uint32_t any0 = (r[0] == 0) | (r[1] == 0) | (r[2] == 0) | (r[3] == 0) | (r[4] == 0) |
+                        (r[5] == 0) | (r[6] == 0) | (r[7] == 0);
+  if (__builtin_expect(any0 != 0, 0)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r[i] == 0) q[i] -= luma_fix_lookup(((i & 3) == 3 ? px[i] >> 8 : px[i]) & 0xFFFFu, fix);
+  }
+  return make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24),
+                    q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
 }
 
 __global__ void __launch_bounds__(kK1Threads, 1)
@@ -166,6 +192,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
 #pragma unroll
   for (int p = 0; p < 3; ++p) xt[p] = c_taps.x[min(p * 32 + lane, kS - 1)];
   uint8_t* Yw = sm.Y + warp * (8 * kW);
+  const LumaCoef coef = luma_coef();
   for (int f = 0; f < frames_here; ++f) {
     const int stage = f & 1, ob = f & 1;
     mbar_wait(&sm.full[stage], (f >> 1) & 1);
@@ -175,17 +202,8 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     for (int it = 0; it < 5; ++it) {
       const int u = it * 32 + lane;
       const uint2 a = raw2[3 * u], b = raw2[3 * u + 1], c = raw2[3 * u + 2];
-      const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y, w4 = c.x, w5 = c.y;
-      uint32_t y0, y1;
-      y0 = luma8<0>(w0, sm.fix);                                   // bytes 0,1,2
-      y0 |= luma8<0>(__byte_perm(w0, w1, 0x4543), sm.fix) << 8;    // bytes 3,4,5
-      y0 |= luma8<0>(__byte_perm(w1, w2, 0x4432), sm.fix) << 16;   // bytes 6,7,8
-      y0 |= luma8<1>(w2, sm.fix) << 24;                            // bytes 9,10,11
-      y1 = luma8<0>(w3, sm.fix);                                   // bytes 12,13,14
-      y1 |= luma8<0>(__byte_perm(w3, w4, 0x4543), sm.fix) << 8;    // bytes 15,16,17
-      y1 |= luma8<0>(__byte_perm(w4, w5, 0x4432), sm.fix) << 16;   // bytes 18,19,20
-      y1 |= luma8<1>(w5, sm.fix) << 24;                            // bytes 21,22,23
-      reinterpret_cast<uint2*>(Yw)[u] = make_uint2(y0, y1);
+      const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+      reinterpret_cast<uint2*>(Yw)[u] = luma_8px(w, coef, sm.fix);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[stage]);               // raw[stage] may be refilled
