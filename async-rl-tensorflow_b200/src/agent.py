@@ -14,6 +14,9 @@ Asynchronous hogwild updates through a parameter server (main.py:60-62, agent.py
 synchronous data parallelism: every rank holds a replica, gradients are summed with one NCCL
 all-reduce per t_max cycle, every rank applies the identical update.
 """
+import json
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -88,6 +91,105 @@ class Agent(BaseModel):
             # reference, the History is NOT reset on terminal.
         self.step_op = self.step + 1
         return self.step_op
+
+    # -- agent.py:69-139 --------------------------------------------------------------------
+    def train_with_summary(self, sv=None, is_chief=True, num_steps=None, log_path=None):
+        """The chief's loop (agent.py:69-139): same steps as ``train`` plus the statistics the
+        reference injects every ``test_step`` steps, with the reference's tag names, as JSON lines
+        (``log_path``) instead of TF summaries.  The running sums live on the device; one small
+        device->host read per ``test_step`` window."""
+        screen, reward, action, terminal, iterator = self.before_train(is_chief)
+        end = self.max_step if num_steps is None else min(self.max_step, self.step + num_steps)
+        dev, B = self.device, self.num_envs
+        zeros = lambda *shape: torch.zeros(*shape, device=dev)
+        ep_reward = zeros(B)                                     # agent.py:72 per env
+        # [sum reward, #games, sum/max/min episode reward, sum loss, sum q]
+        acc = dict(reward=zeros(()), games=zeros(()), ep_sum=zeros(()),
+                   ep_max=torch.full((), -float('inf'), device=dev),
+                   ep_min=torch.full((), float('inf'), device=dev), loss=zeros(()), q=zeros(()))
+        action_hist = torch.zeros(self.env.action_size, device=dev)
+        updates = 0
+        test_step = max(1, int(self.test_step))
+        records = []
+        out = open(log_path, 'a') if (log_path and is_chief) else None
+        for self.step in range(self.step, end):
+            action = self.predict()
+            screen, reward, terminal = self.env.act(action, is_training=True, fused=True)
+            before = self.update_count
+            self.observe(screen, reward, action, terminal, is_chief=True)
+            if self.update_count != before:                      # agent.py:199-201
+                sums = self.network.loss_sums
+                if self.loss_mode == 'async_q':
+                    n = float(self.t_max * B)
+                    acc['loss'] += sums[0] / n
+                    acc['q'] += sums[1] / n
+                else:
+                    acc['loss'] += (sums[0] + sums[1]) / float(B)
+                    acc['q'] += self.network.value.mean()
+                updates += 1
+            term = terminal.bool()
+            r = torch.clamp(reward, self.min_reward, self.max_reward)   # observe clips (agent.py:154)
+            finished = torch.where(term, ep_reward, torch.zeros_like(ep_reward))
+            acc['games'] += term.sum()
+            acc['ep_sum'] += finished.sum()
+            acc['ep_max'] = torch.maximum(acc['ep_max'], torch.where(
+                term, ep_reward, torch.full_like(ep_reward, -float('inf'))).max())
+            acc['ep_min'] = torch.minimum(acc['ep_min'], torch.where(
+                term, ep_reward, torch.full_like(ep_reward, float('inf'))).min())
+            ep_reward = torch.where(term, torch.zeros_like(ep_reward), ep_reward + r)   # agent.py:97-102
+            acc['reward'] += r.sum()
+            action_hist += torch.bincount(action.long(), minlength=self.env.action_size).float()
+            if self.step % test_step == test_step - 1:           # agent.py:104
+                vals = {k: float(v) for k, v in acc.items()}
+                games = int(vals['games'])
+                rec = {
+                    'step': self.step, 'T': self.T,
+                    'average.reward': vals['reward'] / (test_step * B),
+                    'average.loss': vals['loss'] / max(updates, 1),
+                    'average.q': vals['q'] / max(updates, 1),
+                    'episode.max reward': vals['ep_max'] if games else 0.0,
+                    'episode.min reward': vals['ep_min'] if games else 0.0,
+                    'episode.avg reward': vals['ep_sum'] / games if games else 0.0,
+                    'episode.num of game': games,
+                    'episode.actions': [int(c) for c in action_hist.tolist()],
+                    'training.learning_rate': self.lr,
+                }
+                records.append(rec)
+                if out is not None:
+                    out.write(json.dumps(rec) + "\n")
+                    out.flush()
+                for k, v in acc.items():                          # agent.py:133-139
+                    v.fill_(-float('inf') if k == 'ep_max' else float('inf') if k == 'ep_min' else 0.0)
+                action_hist.zero_()
+                updates = 0
+        if out is not None:
+            out.close()
+        self.step_op = self.step + 1
+        return records
+
+    # -- checkpoints: agent.py:29 Saver(w + step_op), main.py:74-80 Supervisor autosave ------
+    def save_checkpoint(self, checkpoint_dir=None):
+        """Weights under the reference's variable names + the RMSProp slot (which the reference
+        forgets to save) + the step counter (agent.py:25, 34)."""
+        d = checkpoint_dir or self.checkpoint_dir
+        path = self.network.save_model(checkpoint_dir=d, step=self.step_op)
+        if self.loss_mode == 'async_q':
+            torch.save(self.network.target_params.cpu(), os.path.join(d, "target-%d.pt" % self.step_op))
+        return path
+
+    def load_checkpoint(self, checkpoint_dir=None):
+        """Resume (agent.py:34 ``self.step = self.step_op.eval()``).  Returns True if restored."""
+        d = checkpoint_dir or self.checkpoint_dir
+        if not self.network.load_model(checkpoint_dir=d):
+            return False
+        self.step_op = self.network.loaded_step
+        if self.loss_mode == 'async_q':
+            p = os.path.join(d, "target-%d.pt" % self.step_op)
+            if os.path.exists(p):
+                self.network.target_params.copy_(torch.load(p).to(self.device))
+            else:
+                self.network.update_target()
+        return True
 
     # -- agent.py:141-151 -------------------------------------------------------------------
     def predict(self, s_t=None, test_ep=None):

@@ -402,3 +402,43 @@ def test_full_size_properties_4096_envs_t5(pkg, cuda):
     err = float((total - g_full).abs().max()) / float(g_full.abs().max())
     print("additivity rel-err", err)
     assert err <= 1e-5
+
+
+def test_train_with_summary_and_checkpoint_resume(pkg, cuda, tmp_path):
+    """agent.py:69-139 statistics (reference tag names, JSON lines) and agent.py:29/34 +
+    main.py:74-80 checkpoint/resume: a restored agent continues bit-identically."""
+    import json
+    A, B, T = 6, 12, 5
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T, "_test_step": 10})
+
+    def make():
+        import random
+        random.seed(123)
+        env = pkg.GymEnvironment(cfg, env=pkg.SyntheticAtari(B, A, seed=9, pool=64, device=cuda,
+                                                             p_terminal=0.1), device=cuda)
+        return pkg.Agent(cfg, env, device=cuda), env
+
+    agent, env = make()
+    log = tmp_path / "stats.jsonl"
+    recs = agent.train_with_summary(num_steps=20, log_path=str(log))
+    assert len(recs) == 2 and agent.step_op == 20 and agent.update_count == 4
+    lines = [json.loads(l) for l in open(log)]
+    assert lines == recs
+    for key in ("average.reward", "average.loss", "average.q", "episode.max reward",
+                "episode.min reward", "episode.avg reward", "episode.num of game",
+                "training.learning_rate"):
+        assert key in recs[0]
+    # the reward statistic equals a host recomputation from the synthetic env's reward table
+    r = env.env._rewards.clamp(-1, 1)
+    first = env.env._i - 20                                        # pool index of the first timed step
+    ref = float(sum(r[(first + i) % env.env.pool].sum() for i in range(10))) / (10 * B)
+    assert abs(recs[0]["average.reward"] - ref) < 1e-6
+    assert sum(recs[0]["episode.actions"]) == 10 * B and recs[0]["episode.num of game"] >= 0
+
+    # checkpoint -> a fresh agent -> identical continuation
+    ck = tmp_path / "ck"
+    agent.save_checkpoint(str(ck))
+    agent2, env2 = make()
+    assert agent2.load_checkpoint(str(ck)) and agent2.step_op == 20
+    assert bool((agent2.network.params == agent.network.params).all())
+    assert bool((agent2.network.rms == agent.network.rms).all())
