@@ -137,6 +137,12 @@ class Environment(object):
         self.device = torch.device(device if device is not None else 'cuda')
         _cabi.init(self.device)
         self.num_envs = int(getattr(config, 'num_envs', 1))
+        if getattr(config, 'resize', 'cv2') != 'cv2':
+            # environment.py:5-12: scipy.misc.imresize (PIL antialiased bilinear) when SciPy still
+            # has it, else cv2.resize.  The executed reference here takes the cv2 branch, which is
+            # the one K1 reproduces bit for bit; the PIL branch is restated in oracle/preprocess.py only.
+            raise NotImplementedError("resize=%r: only the cv2.resize branch of environment.py:5-12 "
+                                      "is built on the device" % (config.resize,))
         self.env = env if env is not None else SyntheticAtari(
             self.num_envs, seed=getattr(config, 'seed', 123), device=self.device)
         screen_width, screen_height, self.action_repeat, self.random_start = \

@@ -37,3 +37,12 @@ def test_initial_weights_distribution(pkg):
     assert abs(float(w['l4_w'].std()) - 0.02) < 1e-3 and float(w['l4_b'].abs().max()) == 0.0
     w2 = pkg.network.initial_weights(6, seed=123)
     assert all(bool((w[k] == w2[k]).all()) for k in w)
+
+
+def test_unbuilt_resize_branch_fails_loudly(pkg):
+    """environment.py:5-12 has two resize branches; only cv2's is built on the device, and asking
+    for the other one is an error, not a silent substitution (checked before any device work)."""
+    import pytest
+    cfg = pkg.config.get_config({"model": "m1", "resize": "pil"})
+    with pytest.raises((NotImplementedError, pkg._cabi.ArlError)):
+        pkg.GymEnvironment(cfg, env=object(), device="cuda:0")
