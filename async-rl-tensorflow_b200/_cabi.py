@@ -20,6 +20,7 @@ SIGNATURES = {
     "arl_init": [c_int],
     "arl_param_layout": [c_int, ctypes.POINTER(c_i64)],
     "arl_preprocess_push": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_preprocess_push_pil": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_upload_frames": [c_vp, c_vp, c_int, c_vp],
     "arl_history_get": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_history_reset": [c_vp, c_int, c_int, c_vp],

@@ -237,6 +237,126 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   }
 }
 
+// ---- the other branch of environment.py:5-12: scipy.misc.imresize = PIL BILINEAR ------------
+// Pillow's 8-bit resize (ImagingResample): antialiased triangle filter with support = scale,
+// coefficients int(0.5 + w * 2^22) of the double weights normalised to sum 1, accumulator seeded
+// with 2^21, >> 22, clip; horizontal pass to u8 [210][84] first, then the vertical pass.
+// This branch reads every source row.  One CTA per frame, phases separated by __syncthreads: it is
+// the optional mode (resize='pil'); the executed reference takes the cv2 branch above.
+constexpr int kPilMaxTaps = 8;
+struct PilTaps {
+  int xmin[kS], xn[kS], xk[kS][kPilMaxTaps];     // horizontal: 160 -> 84
+  int ymin[kS], yn[kS], yk[kS][kPilMaxTaps];     // vertical:   210 -> 84
+};
+__device__ PilTaps g_pil;
+
+static bool pil_coeffs(int src, int dst, int* mn, int* cnt, int (*k)[kPilMaxTaps]) {
+  const double scale = (double)src / (double)dst;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  for (int i = 0; i < dst; ++i) {
+    const double center = (i + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > src) xmax = src;
+    const int n = xmax - xmin;
+    if (n > kPilMaxTaps) return false;
+    double w[kPilMaxTaps], tot = 0.0;
+    for (int j = 0; j < n; ++j) {
+      double x = (j + xmin - center + 0.5) / filterscale;
+      if (x < 0) x = -x;
+      w[j] = x < 1.0 ? 1.0 - x : 0.0;
+      tot += w[j];
+    }
+    for (int j = 0; j < kPilMaxTaps; ++j) k[i][j] = 0;
+    for (int j = 0; j < n; ++j) {
+      const double v = tot != 0.0 ? w[j] / tot : w[j];
+      k[i][j] = v >= 0 ? (int)(0.5 + v * 4194304.0) : (int)(-0.5 + v * 4194304.0);
+    }
+    mn[i] = xmin;
+    cnt[i] = n;
+  }
+  return true;
+}
+
+struct __align__(16) PilSmem {
+  uint8_t raw[kFrameBytes];          // 100 800
+  uint8_t Y[kH * kW];                // 33 600
+  uint8_t tmp[kH * kS];              // 17 640 (+8 pad below keeps out 16-B aligned)
+  uint8_t pad[8];
+  uint8_t out[kPlane];
+  uint32_t fix[kBitmapWords];
+  uint64_t full;
+};
+
+__global__ void __launch_bounds__(512, 1)
+preprocess_pil_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring, int num_envs,
+                      int ring_slots, int slot, int replicate) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  PilSmem& sm = *reinterpret_cast<PilSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kBitmapWords; i += 512) sm.fix[i] = g_luma_fix[i];
+  if (tid == 0) {
+    mbar_init(&sm.full, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const LumaCoef coef = luma_coef();
+  int it = 0;
+  for (int env = blockIdx.x; env < num_envs; env += gridDim.x, ++it) {
+    if (tid == 0) {
+      bulk_wait_read<0>();                                    // previous plane store has read sm.out
+      mbar_expect_tx(&sm.full, kFrameBytes);
+      const uint8_t* src = frames + (size_t)env * kFrameBytes;
+      for (int c = 0; c < 4; ++c)                             // 4 x 25 200 B
+        bulk_g2s(sm.raw + c * (kFrameBytes / 4), src + c * (kFrameBytes / 4), kFrameBytes / 4, &sm.full);
+    }
+    mbar_wait(&sm.full, it & 1);
+    // luma of all 210 x 160 pixels, 8 per thread-iteration
+    const uint2* raw2 = reinterpret_cast<const uint2*>(sm.raw);
+    for (int u = tid; u < kH * kW / 8; u += 512) {
+      const uint2 a = raw2[3 * u], b = raw2[3 * u + 1], c = raw2[3 * u + 2];
+      const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+      reinterpret_cast<uint2*>(sm.Y)[u] = luma_8px(w, coef, sm.fix);
+    }
+    __syncthreads();
+    // horizontal pass -> u8 [210][84]
+    for (int o = tid; o < kH * kS; o += 512) {
+      const int row = o / kS, dx = o - row * kS;
+      const uint8_t* p = sm.Y + row * kW + g_pil.xmin[dx];
+      int acc = 1 << 21;
+      const int n = g_pil.xn[dx];
+      for (int j = 0; j < n; ++j) acc += (int)p[j] * g_pil.xk[dx][j];
+      acc >>= 22;
+      sm.tmp[o] = (uint8_t)min(max(acc, 0), 255);
+    }
+    __syncthreads();
+    // vertical pass -> the ring's 4x4-blocked plane
+    for (int o = tid; o < kPlane; o += 512) {
+      const int dy = o / kS, dx = o - dy * kS;
+      const uint8_t* p = sm.tmp + g_pil.ymin[dy] * kS + dx;
+      int acc = 1 << 21;
+      const int n = g_pil.yn[dy];
+      for (int j = 0; j < n; ++j) acc += (int)p[j * kS] * g_pil.yk[dy][j];
+      acc >>= 22;
+      sm.out[((dy >> 2) * 21 + (dx >> 2)) * 16 + (dy & 3) * 4 + (dx & 3)] = (uint8_t)min(max(acc, 0), 255);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      uint8_t* dst = ring + ((size_t)env * ring_slots) * kPlane;
+      for (int r = 0; r < replicate; ++r) {
+        int sl = slot + r;
+        if (sl >= ring_slots) sl -= ring_slots;
+        bulk_s2g(dst + (size_t)sl * kPlane, sm.out, kPlane);
+      }
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
 // ---- History.get / reset -----------------------------------------------------------------
 template <typename OutT>
 __global__ void history_get_kernel(const uint8_t* __restrict__ ring, OutT* __restrict__ out,
@@ -293,6 +413,16 @@ int preprocess_init(int device) {
   ARL_LAUNCH_CHECK("luma_fix_init_kernel");
   ARL_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(K1Smem)));
+  {
+    static PilTaps pt;
+    if (!pil_coeffs(kW, kS, pt.xmin, pt.xn, pt.xk) || !pil_coeffs(kH, kS, pt.ymin, pt.yn, pt.yk)) {
+      set_error("arl_init: PIL resize needs more than %d taps", kPilMaxTaps);
+      return ARL_ERR_UNSUPPORTED;
+    }
+    ARL_CUDA(cudaMemcpyToSymbol(g_pil, &pt, sizeof(pt)));
+    ARL_CUDA(cudaFuncSetAttribute(preprocess_pil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(PilSmem)));
+  }
   ARL_CUDA(cudaDeviceSynchronize());
   g_ready[device] = true;
   return ARL_OK;
@@ -320,6 +450,25 @@ extern "C" int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num
   preprocess_kernel<<<grid, kK1Threads, sizeof(K1Smem), (cudaStream_t)stream>>>(
       frames, ring, num_envs, ring_slots, slot, replicate);
   ARL_LAUNCH_CHECK("preprocess_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_preprocess_push_pil(const uint8_t* frames, uint8_t* ring, int num_envs,
+                                       int ring_slots, int slot, int replicate, void* stream) {
+  ARL_REQUIRE(frames && ring, "arl_preprocess_push_pil: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_preprocess_push_pil: num_envs %d < 0", num_envs);
+  ARL_REQUIRE(ring_slots >= ARL_HISTORY && slot >= 0 && slot < ring_slots && replicate >= 1 &&
+                  replicate <= ring_slots,
+              "arl_preprocess_push_pil: bad ring geometry (slots %d, slot %d, replicate %d)",
+              ring_slots, slot, replicate);
+  ARL_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ring) & 15) == 0,
+              "arl_preprocess_push_pil: frames and ring must be 16-byte aligned");
+  if (num_envs == 0) return ARL_OK;
+  const int grid = num_envs < num_sms() ? num_envs : num_sms();
+  preprocess_pil_kernel<<<grid, 512, sizeof(PilSmem), (cudaStream_t)stream>>>(
+      frames, ring, num_envs, ring_slots, slot, replicate);
+  ARL_LAUNCH_CHECK("preprocess_pil_kernel");
   return ARL_OK;
 }
 

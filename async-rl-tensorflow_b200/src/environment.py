@@ -137,12 +137,13 @@ class Environment(object):
         self.device = torch.device(device if device is not None else 'cuda')
         _cabi.init(self.device)
         self.num_envs = int(getattr(config, 'num_envs', 1))
-        if getattr(config, 'resize', 'cv2') != 'cv2':
-            # environment.py:5-12: scipy.misc.imresize (PIL antialiased bilinear) when SciPy still
-            # has it, else cv2.resize.  The executed reference here takes the cv2 branch, which is
-            # the one K1 reproduces bit for bit; the PIL branch is restated in oracle/preprocess.py only.
-            raise NotImplementedError("resize=%r: only the cv2.resize branch of environment.py:5-12 "
-                                      "is built on the device" % (config.resize,))
+        # environment.py:5-12: scipy.misc.imresize (PIL antialiased bilinear) when SciPy still has
+        # it, else cv2.resize (the branch the reference takes with any current SciPy: the default)
+        self.resize = getattr(config, 'resize', 'cv2')
+        if self.resize not in ('cv2', 'pil'):
+            raise NotImplementedError("resize=%r: environment.py:5-12 has two branches, 'cv2' "
+                                      "(cv2.resize) and 'pil' (scipy.misc.imresize)" % (self.resize,))
+        self._push = "arl_preprocess_push" if self.resize == 'cv2' else "arl_preprocess_push_pil"
         self.env = env if env is not None else SyntheticAtari(
             self.num_envs, seed=getattr(config, 'seed', 123), device=self.device)
         screen_width, screen_height, self.action_repeat, self.random_start = \
@@ -191,7 +192,7 @@ class Environment(object):
     @property
     def screen(self):
         """environment.py:49-53 on the device (K1, bit-exact): u8 [B,84,84]."""
-        _cabi.call("arl_preprocess_push", _cabi.ptr(self._screen), _cabi.ptr(self._scratch),
+        _cabi.call(self._push, _cabi.ptr(self._screen), _cabi.ptr(self._scratch),
                    self.num_envs, 4, 0, 1, _cabi.stream_ptr())
         return from_blocked(self._scratch[:, 0]).contiguous()        # the ring layout is 4x4-blocked
 

@@ -52,6 +52,10 @@ class History(object):
                                 dtype=torch.uint8, device=self.device)   # history.py:10-11
         self.head = self.ring_slots - 1
         self.timer = None
+        resize = getattr(config, 'resize', 'cv2')                # environment.py:5-12 branch
+        if resize not in ('cv2', 'pil'):
+            raise NotImplementedError("resize=%r" % (resize,))
+        self._push = "arl_preprocess_push" if resize == 'cv2' else "arl_preprocess_push_pil"
 
     # -- reference API ------------------------------------------------------------------
     def add(self, screen, replicate=1):
@@ -61,7 +65,7 @@ class History(object):
         if tuple(screen.shape[1:]) == FRAME_SHAPE:
             if screen.dtype != torch.uint8:
                 raise TypeError("frames must be uint8")
-            args = ("arl_preprocess_push", _cabi.ptr(screen), _cabi.ptr(self.ring),
+            args = (self._push, _cabi.ptr(screen), _cabi.ptr(self.ring),
                     self.num_envs, self.ring_slots, new_head, int(replicate), _cabi.stream_ptr())
             if self.timer is not None:
                 self.timer(*args)                    # bench.py: event pair around K1

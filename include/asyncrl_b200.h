@@ -88,6 +88,13 @@ ARL_API int arl_param_layout(int action_size, int64_t* offsets);
 ARL_API int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num_envs, int ring_slots,
                         int slot, int replicate, void* stream);
 
+/* The other resize branch of environment.py:5-12: scipy.misc.imresize(y, (84,84)) = PIL
+ * Image.resize(BILINEAR) on the truncated luma (antialiased triangle filter, 22-bit fixed point,
+ * horizontal pass to u8 then vertical).  Same arguments and ring layout as arl_preprocess_push;
+ * bit-exact against Pillow.  Reads every source row. */
+ARL_API int arl_preprocess_push_pil(const uint8_t* frames, uint8_t* ring, int num_envs, int ring_slots,
+                            int slot, int replicate, void* stream);
+
 /* Host -> device upload of exactly the frame rows K1 reads (environment.py:53 -> cv2.resize
  * 210x160 -> 84x84 never touches source rows == 2 mod 5): two strided async copies of
  * num_envs*42 x 960 B each = 80 640 of the 100 800 B of a frame.  host_frames should be pinned;

@@ -165,3 +165,42 @@ def test_upload_frames_skips_only_unread_rows(pkg, cuda):
     assert np.array_equal(got[:, keep], frames[:, keep])
     assert (got[:, ~keep] == 9).all()
     assert np.array_equal(unblock(ring[:, 2]).cpu().numpy(), P.screen(frames))
+
+
+def test_pil_branch_bit_exact(pkg, cuda):
+    """environment.py:5-7: the scipy.misc.imresize branch = PIL BILINEAR.  arl_preprocess_push_pil
+    against the oracle restatement and, when Pillow is importable, against Pillow itself."""
+    rng = np.random.default_rng(21)
+    frames = rng.integers(0, 256, (9, 210, 160, 3), dtype=np.uint8)
+    frames[0] = 255; frames[1] = 0
+    frames[2, :, ::2] = 0; frames[2, :, 1::2] = 255                 # vertical stripes: worst case for the filter
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    frames[3] = pal[rng.integers(0, 16, (21, 16))].repeat(10, 0).repeat(10, 1)
+    dev_frames = torch.as_tensor(frames, device=cuda)
+    ring = torch.full((9, 5, 84, 84), 7, dtype=torch.uint8, device=cuda)
+    pkg._cabi.call("arl_preprocess_push_pil", pkg._cabi.ptr(dev_frames), pkg._cabi.ptr(ring), 9, 5, 4, 2,
+                   pkg._cabi.stream_ptr())                           # slots 4 and 0 (wrap)
+    torch.cuda.synchronize()
+    got = unblock(ring).cpu().numpy()
+    ref = P.screen(frames, resize="pil")
+    assert np.array_equal(got[:, 4], ref) and np.array_equal(got[:, 0], ref)
+    assert (got[:, 1:4] == 7).all()
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    y = P.luma_truncate(frames)
+    for i in range(len(frames)):
+        pil = np.asarray(Image.fromarray(y[i]).resize((84, 84), Image.BILINEAR))
+        assert np.array_equal(got[i, 4], pil), i
+
+
+def test_history_uses_the_configured_resize_branch(pkg, cuda):
+    rng = np.random.default_rng(4)
+    frames = rng.integers(0, 256, (5, 210, 160, 3), dtype=np.uint8)
+    for mode in ("cv2", "pil"):
+        cfg = pkg.config.get_config({"model": "m1", "num_envs": 5, "resize": mode})
+        hist = pkg.History(cfg, num_envs=5, device=cuda)
+        hist.add(torch.as_tensor(frames, device=cuda))
+        torch.cuda.synchronize()
+        assert np.array_equal(hist.planes(hist.head).cpu().numpy(), P.screen(frames, resize=mode))

@@ -40,9 +40,9 @@ def test_initial_weights_distribution(pkg):
 
 
 def test_unbuilt_resize_branch_fails_loudly(pkg):
-    """environment.py:5-12 has two resize branches; only cv2's is built on the device, and asking
-    for the other one is an error, not a silent substitution (checked before any device work)."""
+    """environment.py:5-12 has two resize branches ('cv2', 'pil'); anything else is an error, not a
+    silent substitution."""
     import pytest
-    cfg = pkg.config.get_config({"model": "m1", "resize": "pil"})
+    cfg = pkg.config.get_config({"model": "m1", "resize": "lanczos"})
     with pytest.raises((NotImplementedError, pkg._cabi.ArlError)):
         pkg.GymEnvironment(cfg, env=object(), device="cuda:0")
