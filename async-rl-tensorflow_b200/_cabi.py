@@ -26,10 +26,11 @@ SIGNATURES = {
     "arl_history_reset": [c_vp, c_int, c_int, c_vp],
     "arl_conv1_forward": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_conv2_forward": [c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_fc_forward": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_fc_prepare": [c_vp, c_vp, c_vp],
+    "arl_fc_forward": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_heads_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_forward": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
-                    c_vp, c_vp],
+    "arl_forward": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                    c_vp, c_vp, c_vp, c_vp],
     "arl_debug_gemm": [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_sample_actions": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_u64, c_vp],
     "arl_greedy_actions": [c_vp, c_vp, c_int, c_int, c_vp],
@@ -39,11 +40,11 @@ SIGNATURES = {
     "arl_returns_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,
                              c_int, c_int, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp],
     "arl_heads_backward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_fc_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_fc_backward": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_conv2_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
-    "arl_backward": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
-                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "arl_backward": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "arl_clip_rmsprop": [c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
 }
 OTHER = {

@@ -384,7 +384,7 @@ struct Conv1Fwd : tc::PolicyBase {
 struct Conv2FwdArgs {
   const float* params;
   const uint8_t* a1s;    // split-bf16 blocked conv1 output
-  float* a2;
+  uint8_t* a2s;          // split-bf16 chunked output, one block of num_samples rows (gemm_tc.cuh SplitMat)
   int64_t rows;          // 100 * num_samples
   int num_samples;
 };
@@ -398,7 +398,7 @@ struct Conv2Fwd : tc::PolicyBase {
   // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
   static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
-  static constexpr bool HAS_AUX = true;
+  static constexpr bool CUSTOM_EPI = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -442,19 +442,31 @@ struct Conv2Fwd : tc::PolicyBase {
       }
     }
   }
-  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
+  // epilogue: lane = output pixel (n, yp, xp); its 32 channels = features (yp*9+xp)*32 .. +31 of the
+  // NHWC flatten (agent.py:231-232) = chunks (yp*9+xp)*4 .. +3 of the split-bf16 a2 block
+  // [part][324 chunks][num_samples][8] that the fc256 kernels consume with cp.async.bulk
+  static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t, const uint8_t*,
+                                                         uint32_t taddr, int row) {
     const int xr = t.mt * 128 + row, n = xr / GROWS;
     const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
-    if (n >= g.num_samples || yp >= 9 || xp >= 9) return nullptr;
-    return g.a2 + ((int64_t)n * 81 + yp * 9 + xp) * 32;
-  }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col,
-                                                    int64_t) {
-    return tc::ldg4(g.params + 4112 + 8192 + col);
-  }
-  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 bb) {
-    return make_float4(fmaxf(v.x + bb.x, 0.f), fmaxf(v.y + bb.y, 0.f), fmaxf(v.z + bb.z, 0.f),
-                       fmaxf(v.w + bb.w, 0.f));
+    const bool ok = n < g.num_samples && yp < 9 && xp < 9;
+    const float* bias = g.params + 4112 + 8192;
+    const int64_t plane = (int64_t)g.num_samples * 16, part = 324 * plane;
+    uint8_t* d = g.a2s + (int64_t)((yp * 9 + xp) * 4) * plane + (int64_t)n * 16;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float v[8];
+      tc::tmem_ld8_sum(taddr + c8 * 8, taddr + 32 + c8 * 8, v);          // x_hi.w_hi + x_lo.w_hi, x_hi.w_lo
+      if (!ok) continue;
+      const float4 b0 = tc::ldg4(bias + c8 * 8), b1 = tc::ldg4(bias + c8 * 8 + 4);
+      uint4 h, l;
+      tc::split2(fmaxf(v[0] + b0.x, 0.f), fmaxf(v[1] + b0.y, 0.f), h.x, l.x);
+      tc::split2(fmaxf(v[2] + b0.z, 0.f), fmaxf(v[3] + b0.w, 0.f), h.y, l.y);
+      tc::split2(fmaxf(v[4] + b1.x, 0.f), fmaxf(v[5] + b1.y, 0.f), h.z, l.z);
+      tc::split2(fmaxf(v[6] + b1.z, 0.f), fmaxf(v[7] + b1.w, 0.f), h.w, l.w);
+      *reinterpret_cast<uint4*>(d + c8 * plane) = h;
+      *reinterpret_cast<uint4*>(d + part + c8 * plane) = l;
+    }
   }
 };
 
@@ -765,7 +777,8 @@ extern "C" int arl_conv2_forward(const float* params, const float* a1, float* a2
   ARL_REQUIRE(aligned16(params) && aligned16(a1) && aligned16(a2),
               "arl_conv2_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
-  Conv2FwdArgs g{params, reinterpret_cast<const uint8_t*>(a1), a2, num_samples * 100, (int)num_samples};
+  Conv2FwdArgs g{params, reinterpret_cast<const uint8_t*>(a1), reinterpret_cast<uint8_t*>(a2),
+                 num_samples * 100, (int)num_samples};
   return tc::launch<Conv2Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 

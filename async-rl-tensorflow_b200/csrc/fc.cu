@@ -1,9 +1,13 @@
 // K3: the fc256 layer (agent.py:251, ops.py:32-46) forward and backward on the tcgen05 tensor
-// cores (gemm_tc.cuh: TMEM accumulators, bf16x3 split of the fp32 operands, fp32 accumulate).
-//   forward : h    = relu(a2 [N,2592] . W [2592,256] + b)        A = a2 (K-major), B = W (k-rows)
-//   dgrad   : d_a2 = (d_h [N,256] . W^T) * (a2 > 0)              A = d_h, B = W rows (K-major)
-//   wgrad   : dW   = a2^T [2592,N] . d_h [N,256]                 both operands sample-major;
-//             split-K over samples, partials summed in a fixed order (deterministic)
+// cores (gemm_tc.cuh: TMEM accumulators, bf16x3 split of the fp32 values, fp32 accumulate).
+// Every operand is kept in HBM as split bf16 in 16-byte chunk vectors (gemm_tc.cuh "SplitMat"):
+// a2 by conv2 forward, d_h by heads backward, l4_w by arl_fc_prepare -- the kernels here move
+// them with cp.async.bulk only.
+//   forward : h    = relu(a2 [N,2592] . W [2592,256] + b)     A = a2s (K-major), B = Ws (MN-major)
+//   dgrad   : d_a2 = (d_h [N,256] . W^T) * (a2 > 0)           A = dhs (K-major), B = Ws (K-major),
+//                                                             mask = sign of a2s' hi part
+//   wgrad   : dW   = a2^T [2592,N] . d_h [N,256]              A = a2s, B = dhs (both MN-major: k =
+//             sample); split-K over samples, partials summed in a fixed order (deterministic)
 //   bgrad   : db   = column sums of d_h
 #include "gemm_tc.cuh"
 
@@ -12,49 +16,88 @@ namespace arl {
 int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream);
 
-// partial column sums of X [rows, 256]: block b sums rows b, b+grid, ... -> partials[b][256]
-__global__ void colsum256_kernel(const float* __restrict__ X, float* __restrict__ partials,
-                                 int64_t rows) {
-  const int col = threadIdx.x;
-  float s0 = 0.f, s1 = 0.f;
-  int64_t r = blockIdx.x;
-  for (; r + gridDim.x < rows; r += 2 * (int64_t)gridDim.x) {
-    s0 += X[r * 256 + col];
-    s1 += X[(r + gridDim.x) * 256 + col];
-  }
-  if (r < rows) s0 += X[r * 256 + col];
-  partials[(size_t)blockIdx.x * 256 + col] = s0 + s1;
+// X fp32 [rows][8*chunks] (row stride ld) -> one split block [part][chunk][row][8 bf16].
+// Thread = (row, chunk): reads 32 contiguous bytes, writes one hi and one lo vector.
+__global__ void split_rows_kernel(const float* __restrict__ X, int64_t ld, int rows, int chunks,
+                                  uint8_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * chunks) return;
+  const int row = (int)(idx / chunks), c = (int)(idx - (int64_t)row * chunks);
+  const float4 x0 = tc::ldg4(X + (int64_t)row * ld + c * 8), x1 = tc::ldg4(X + (int64_t)row * ld + c * 8 + 4);
+  uint4 h, l;
+  tc::split2(x0.x, x0.y, h.x, l.x);
+  tc::split2(x0.z, x0.w, h.y, l.y);
+  tc::split2(x1.x, x1.y, h.z, l.z);
+  tc::split2(x1.z, x1.w, h.w, l.w);
+  uint8_t* d = out + ((int64_t)c * rows + row) * 16;
+  *reinterpret_cast<uint4*>(d) = h;
+  *reinterpret_cast<uint4*>(d + (int64_t)chunks * rows * 16) = l;
+}
+int split_rows(const float* X, int64_t ld, int rows, int chunks, void* out, cudaStream_t st) {
+  const int64_t n = (int64_t)rows * chunks;
+  if (n == 0) return ARL_OK;
+  split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, ld, rows, chunks, (uint8_t*)out);
+  ARL_LAUNCH_CHECK("split_rows_kernel");
+  return ARL_OK;
 }
 
-// KB per variant: 8 stages must fit in 227 KB (N tile 256 -> KB 16, N tile 64 -> KB 32)
-int fc_gemm(int variant, const float* A, const float* B, float* D, const float* extra, int M, int N,
-            int K, int64_t lda, int64_t ldb, int64_t ldd, int k_splits, cudaStream_t st) {
-  tc::GemmArgs g;
-  g.A = A; g.B = B; g.D = D; g.extra = extra;
-  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldd = ldd;
-  const int n_tile = variant == 1 ? 64 : 256, kb = variant == 1 ? 32 : 16;
+// partial column sums of a split matrix [rows][256] (one block): CTA b sums its row range, warp w
+// the chunks 4w..4w+3, lanes stride over the rows (512 contiguous bytes per load) -> partials[b][256]
+__global__ void __launch_bounds__(256)
+colsum_split256_kernel(const uint8_t* __restrict__ xs, float* __restrict__ partials, int rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int beg = per * blockIdx.x, end = min(rows, beg + per);
+  const int64_t part = (int64_t)32 * rows * 16;
+  for (int c = warp * 4; c < warp * 4 + 4; ++c) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint8_t* p = xs + (int64_t)c * rows * 16;
+    for (int r = beg + lane; r < end; r += 32) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)r * 16));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + part + (int64_t)r * 16));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+      float* d = partials + (size_t)blockIdx.x * 256 + c * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = acc[i];
+    }
+  }
+}
+
+// forward: narrow N tiles (4 per row tile) so that one env step of 4096 samples fills 128 SMs
+using FcFwd = tc::BulkGemm<64, 32, false, true, tc::EPI_BIAS_RELU, 8>;
+using FcDgrad = tc::BulkGemm<128, 32, false, false, tc::EPI_MASK, 4>;
+using FcWgrad = tc::BulkGemm<128, 64, true, true, tc::EPI_PLAIN, 3>;
+
+template <class P>
+int run_gemm(tc::BulkGemmArgs& g, int k_splits, cudaStream_t st) {
   if (k_splits < 1) k_splits = 1;
-  g.k_chunk = ((K + k_splits - 1) / k_splits + kb - 1) / kb * kb;
-  g.k_splits = (K + g.k_chunk - 1) / g.k_chunk;
-  g.m_tiles = (M + tc::kTileM - 1) / tc::kTileM;
-  g.n_tiles = (N + n_tile - 1) / n_tile;
-  const int items = g.m_tiles * g.n_tiles * g.k_splits;
-  switch (variant) {
-    case 0: return tc::launch<tc::GemmPolicy<256, 16, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
-    // few rows (one env step): narrow N tiles so every SM works; KB = 32 keeps the A rows 128-B
-    // segments (16 one-warp stages of KB = 16 measured 7 % slower: 64-B segments, same latency)
-    case 1: return tc::launch<tc::GemmPolicy<64, 32, false, true, tc::EPI_BIAS_RELU>>(g, items, st);
-    case 2: return tc::launch<tc::GemmPolicy<256, 16, false, false, tc::EPI_MASK>>(g, items, st);
-    case 3:   // (was: K-major images transposed in registers; now identical to 4)
-    case 4: return tc::launch<tc::GemmPolicy<256, 16, true, true, tc::EPI_PLAIN>>(g, items, st);
-    default: set_error("fc_gemm: unknown variant %d", variant); return ARL_ERR_INVALID;
-  }
+  g.k_chunk = ((g.K + k_splits - 1) / k_splits + P::KB - 1) / P::KB * P::KB;
+  g.k_splits = (g.K + g.k_chunk - 1) / g.k_chunk;
+  g.m_tiles = (g.M + tc::kTileM - 1) / tc::kTileM;
+  g.n_tiles = (g.N + P::N_TILE - 1) / P::N_TILE;
+  return tc::launch<P>(g, g.m_tiles * g.n_tiles * g.k_splits, st);
 }
 
-// number of split-K slices fc_gemm(variant 3) produces for K samples and a request of `want`
+// number of split-K slices the wgrad produces for K samples and a request of `want`
 int fc_wgrad_splits(int K, int want) {
-  const int k_chunk = ((K + want - 1) / want + 15) / 16 * 16;
+  const int kb = FcWgrad::KB;
+  const int k_chunk = ((K + want - 1) / want + kb - 1) / kb * kb;
   return (K + k_chunk - 1) / k_chunk;
+}
+
+static tc::SplitMat mat(const void* base, int rows, int block_rows, int chunks) {
+  tc::SplitMat m;
+  m.base = (const uint8_t*)base; m.rows = rows; m.block_rows = block_rows; m.chunks = chunks;
+  return m;
 }
 
 }  // namespace arl
@@ -63,44 +106,79 @@ using namespace arl;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// Test hook: the four production instantiations of the tcgen05 GEMM on arbitrary shapes.
-// variant 0/1: D = relu(A[M,K] . B[K,N] + extra[N])      (N_TILE 256 / 64; B stored [K][N])
-// variant 2  : D = (A[M,K] . B[N,K]^T) masked by extra[M,N] > 0
-// variant 3  : D[z] = A[K,M]^T . B[K,N] over split-K slice z (k_splits slices, M*N floats each)
+// Test hook: the three production instantiations of the tcgen05 GEMM on arbitrary shapes.  The
+// fp32 operands are split into scratch buffers first (cudaMalloc + synchronise: test use only).
+// variant 0/1: D = relu(A[M,K] . B[K,N] + extra[N])                      (forward instantiation)
+// variant 2  : D = (A[M,K] . B[N,K]^T) masked by extra[M,N] > 0          (dgrad)
+// variant 3/4: D[z] = A[K,M]^T . B[K,N] over split-K slice z (k_splits slices, M*N floats each)
 extern "C" int arl_debug_gemm(int variant, const float* A, const float* B, float* D,
                               const float* extra, int M, int N, int K, int k_splits, void* stream) {
   ARL_REQUIRE(A && B && D, "arl_debug_gemm: null pointer");
+  ARL_REQUIRE(variant >= 0 && variant <= 4, "arl_debug_gemm: unknown variant %d", variant);
   ARL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 16 == 0 && (variant >= 3 || K % 8 == 0),
               "arl_debug_gemm: need M,N,K > 0, N %% 16 == 0, K %% 8 == 0");
   ARL_REQUIRE(variant < 3 || M % 8 == 0, "arl_debug_gemm: variants 3/4 need M %% 8 == 0");
-  const int64_t lda = variant >= 3 ? M : K;
-  const int64_t ldb = variant == 2 ? K : N;
-  return fc_gemm(variant, A, B, D, extra, M, N, K, lda, ldb, N, variant >= 3 ? k_splits : 1,
-                 (cudaStream_t)stream);
+  ARL_REQUIRE(variant == 2 || variant >= 3 || extra, "arl_debug_gemm: variants 0/1 need a bias");
+  ARL_REQUIRE(variant != 2 || extra, "arl_debug_gemm: variant 2 needs a mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  // stored shapes [rows][cols] of A, B (and the mask)
+  const int ar = variant >= 3 ? K : M, ac = variant >= 3 ? M : K;
+  const int br = variant == 2 ? N : K, bc = variant == 2 ? K : N;
+  uint8_t *as = nullptr, *bs = nullptr, *ms = nullptr;
+  ARL_CUDA(cudaMalloc(&as, (size_t)ar * ac * 4));
+  ARL_CUDA(cudaMalloc(&bs, (size_t)br * bc * 4));
+  if (variant == 2) ARL_CUDA(cudaMalloc(&ms, (size_t)M * N * 4));
+  int rc = split_rows(A, ac, ar, ac / 8, as, st);
+  if (!rc) rc = split_rows(B, bc, br, bc / 8, bs, st);
+  if (!rc && variant == 2) rc = split_rows(extra, N, M, N / 8, ms, st);
+  tc::BulkGemmArgs g;
+  g.A = mat(as, ar, ar, ac / 8);
+  g.B = mat(bs, br, br, bc / 8);
+  g.mask = mat(ms, M, M, N / 8);
+  g.D = D; g.bias = extra; g.M = M; g.N = N; g.K = K; g.ldd = N;
+  if (!rc) {
+    if (variant <= 1) rc = run_gemm<FcFwd>(g, 1, st);
+    else if (variant == 2) rc = run_gemm<FcDgrad>(g, 1, st);
+    else rc = run_gemm<FcWgrad>(g, k_splits, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(as); cudaFree(bs); cudaFree(ms);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "arl_debug_gemm");
+  return ARL_OK;
 }
 
-extern "C" int arl_fc_forward(const float* params, const float* a2, float* h, int64_t num_samples,
-                              void* stream) {
-  ARL_REQUIRE(params && a2 && h, "arl_fc_forward: null pointer");
+extern "C" int arl_fc_prepare(const float* params, float* w_split, void* stream) {
+  ARL_REQUIRE(params && w_split, "arl_fc_prepare: null pointer");
+  ARL_REQUIRE(aligned16(params) && aligned16(w_split), "arl_fc_prepare: pointers must be 16-byte aligned");
+  const ParamLayout L = param_layout(1);
+  return split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8, w_split, (cudaStream_t)stream);
+}
+
+extern "C" int arl_fc_forward(const float* params, const float* w_split, const float* a2, float* h,
+                              int64_t num_samples, void* stream) {
+  ARL_REQUIRE(params && w_split && a2 && h, "arl_fc_forward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_forward: bad num_samples");
-  ARL_REQUIRE(aligned16(params) && aligned16(a2) && aligned16(h),
+  ARL_REQUIRE(aligned16(params) && aligned16(w_split) && aligned16(a2) && aligned16(h),
               "arl_fc_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
   const ParamLayout L = param_layout(1);
-  const float* W = params + L.off[T_L4W];
-  const float* b = params + L.off[T_L4B];
   const int M = (int)num_samples;
-  // few samples (one env step): narrow N tiles so that every SM gets work
-  const int variant = ((M + 127) / 128 >= num_sms()) ? 0 : 1;
-  return fc_gemm(variant, a2, W, h, b, M, ARL_FC, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC, ARL_FC, 1,
-                 (cudaStream_t)stream);
+  tc::BulkGemmArgs g;
+  g.A = mat(a2, M, M, ARL_A2_ELEMS / 8);
+  g.B = mat(w_split, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
+  g.mask = mat(nullptr, 0, 1, 0);
+  g.D = h; g.bias = params + L.off[T_L4B];
+  g.M = M; g.N = ARL_FC; g.K = ARL_A2_ELEMS; g.ldd = ARL_FC;
+  return run_gemm<FcFwd>(g, 1, (cudaStream_t)stream);
 }
 
-extern "C" int arl_fc_backward(const float* params, const float* a2, const float* d_h, float* d_a2,
-                               float* grads, void* workspace, int64_t num_samples, void* stream) {
-  ARL_REQUIRE(params && a2 && d_h && d_a2 && grads && workspace, "arl_fc_backward: null pointer");
+extern "C" int arl_fc_backward(const float* w_split, const float* a2, int64_t a2_block_rows,
+                               const float* d_h, float* d_a2, float* grads, void* workspace,
+                               int64_t num_samples, void* stream) {
+  ARL_REQUIRE(w_split && a2 && d_h && d_a2 && grads && workspace, "arl_fc_backward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_backward: bad num_samples");
-  ARL_REQUIRE(aligned16(params) && aligned16(a2) && aligned16(d_h) && aligned16(d_a2) &&
+  ARL_REQUIRE(aligned16(w_split) && aligned16(a2) && aligned16(d_h) && aligned16(d_a2) &&
                   aligned16(grads) && aligned16(workspace),
               "arl_fc_backward: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -111,21 +189,32 @@ extern "C" int arl_fc_backward(const float* params, const float* a2, const float
     ARL_CUDA(cudaMemsetAsync(gW, 0, (size_t)(ARL_A2_ELEMS + 1) * ARL_FC * sizeof(float), st));
     return ARL_OK;
   }
-  const float* W = params + L.off[T_L4W];
+  ARL_REQUIRE(a2_block_rows > 0 && num_samples % a2_block_rows == 0,
+              "arl_fc_backward: num_samples %lld is not a whole number of a2 blocks of %lld rows",
+              (long long)num_samples, (long long)a2_block_rows);
   const int M = (int)num_samples;
-  // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0.  B rows = W rows (K-major).
-  int rc = fc_gemm(2, d_h, W, d_a2, a2, M, ARL_A2_ELEMS, ARL_FC, ARL_FC, ARL_FC, ARL_A2_ELEMS, 1, st);
+  const tc::SplitMat a2s = mat(a2, M, (int)a2_block_rows, ARL_A2_ELEMS / 8);
+  const tc::SplitMat dhs = mat(d_h, M, M, ARL_FC / 8);
+  const tc::SplitMat ws = mat(w_split, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
+  // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
+  tc::BulkGemmArgs g;
+  g.A = dhs; g.B = ws; g.mask = a2s;
+  g.D = d_a2; g.bias = nullptr;
+  g.M = M; g.N = ARL_A2_ELEMS; g.K = ARL_FC; g.ldd = ARL_A2_ELEMS;
+  int rc = run_gemm<FcDgrad>(g, 1, st);
   if (rc) return rc;
-  // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles = 147 work items
+  // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles x 2 column tiles = 294 items
   float* part = (float*)workspace;
-  rc = fc_gemm(4, a2, d_h, part, nullptr, ARL_A2_ELEMS, ARL_FC, M, ARL_A2_ELEMS, ARL_FC, ARL_FC, 7, st);
+  g.A = a2s; g.B = dhs; g.mask = mat(nullptr, 0, 1, 0);
+  g.D = part;
+  g.M = ARL_A2_ELEMS; g.N = ARL_FC; g.K = M; g.ldd = ARL_FC;
+  rc = run_gemm<FcWgrad>(g, 7, st);
   if (rc) return rc;
-  const int splits = fc_wgrad_splits(M, 7);
-  rc = reduce_partials(part, gW, splits, ARL_A2_ELEMS * ARL_FC, st);
+  rc = reduce_partials(part, gW, g.k_splits, ARL_A2_ELEMS * ARL_FC, st);
   if (rc) return rc;
   // bias grad
-  const int grid = (int)(num_samples < num_sms() ? num_samples : num_sms());
-  colsum256_kernel<<<grid, 256, 0, st>>>(d_h, part, num_samples);
-  ARL_LAUNCH_CHECK("colsum256_kernel");
+  const int grid = (int)((num_samples + 63) / 64 < num_sms() ? (num_samples + 63) / 64 : num_sms());
+  colsum_split256_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_h, part, M);
+  ARL_LAUNCH_CHECK("colsum_split256_kernel");
   return reduce_partials(part, gb, grid, ARL_FC, st);
 }

@@ -263,6 +263,16 @@ struct PolicyBase {
   template <class Args>
   static __device__ __forceinline__ bool bulk_stage(const Args&, const TileCoord&, int, uint8_t*, int,
                                                     int, uint64_t*) { return false; }
+  // A finishing operand that is laid out like the accumulator read-out (lane = row, 8 consecutive
+  // columns = one 16-byte vector): loaded ahead of the accumulator wait, applied in registers
+  static constexpr bool HAS_PRE = false;
+  template <class Args>
+  static __device__ __forceinline__ int64_t pre_row(const Args&, const TileCoord&, int) { return 0; }
+  template <class Args>
+  static __device__ __forceinline__ uint4 pre_load(const Args&, const TileCoord&, int64_t, int) {
+    return make_uint4(0u, 0u, 0u, 0u);
+  }
+  static __device__ __forceinline__ void pre_apply(float (&)[8], const uint4&) {}
   static constexpr bool HAS_AUX = false;       // finish() needs an operand from HBM (bias, relu mask)
   static constexpr bool AUX_ROW_INVARIANT = true;   // ... that depends on the column only (bias)
   struct Prod {};
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   constexpr int kEpiWarps = epi_warps<P>();
   constexpr int kMmaWarp = kEpiWarps + P::PROD_WARPS;
   static_assert(P::PROD_WARPS % STAGES == 0, "producer warps must divide evenly over the stages");
-  static_assert(STAGES == 16 || STAGES == 8 || STAGES == 4 || STAGES == 2, "STAGES");
+  static_assert(STAGES >= 2 && STAGES <= 16, "STAGES");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* res = smem + STAGES * P::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -439,6 +449,8 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       __syncwarp();
       rowp[lane] = P::row_ptr(g, tc, quad * 32 + lane);
       if (P::HAS_AUX && !P::AUX_ROW_INVARIANT) rowa[lane] = P::row_aux(g, tc, quad * 32 + lane);
+      int64_t prow = 0;
+      if constexpr (P::HAS_PRE) prow = P::pre_row(g, tc, quad * 32 + lane);
       __syncwarp();
       bool waited = false;
 #pragma unroll 1
@@ -462,6 +474,11 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
 #pragma unroll
           for (int i = 0; i < NI; ++i) aux[i] = a;
         }
+        uint4 pm[SEG / 8];
+        if constexpr (P::HAS_PRE) {
+#pragma unroll
+          for (int h = 0; h < SEG / 8; ++h) pm[h] = P::pre_load(g, tc, prow, sg * SEG + h * 8);
+        }
         if (!waited) {
           mbar_wait_backoff<64>(&tfull[acc], acc_phase);
           tc_fence_after();
@@ -479,6 +496,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
             tmem_ld8_limbs3(ta, ta + P::LO_DELTA, ta + 2 * P::LO_DELTA, sc[0], sc[1], sc[2], v);
           } else if (P::LO_DELTA > 0) tmem_ld8_sum(ta, ta + P::LO_DELTA, v);
           else tmem_ld8(ta, v);
+          if constexpr (P::HAS_PRE) P::pre_apply(v, pm[h]);
           float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 8);
           d[0] = make_float4(v[0], v[1], v[2], v[3]);
           d[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -528,49 +546,77 @@ int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   return ARL_OK;
 }
 
-// =============================== plain GEMM policy (fc256) ===================================
+// ====================== GEMM on split-bf16 operands kept in HBM (fc256) ========================
+// Every operand of the fc256 contractions lives in HBM already split into bf16 hi and lo parts, in
+// 16-byte vectors of 8 consecutive columns ("chunks") with the ROWS contiguous:
+//     xs[block][part (hi, lo)][chunk][row in block][8 bf16]          (same bytes as fp32 [rows][8*chunks])
+// written that way by the kernel that produces the tensor (conv2 forward: a2, heads backward:
+// d_h, arl_fc_prepare: l4_w).  A run of consecutive rows of one (part, chunk) is then one
+// contiguous byte range AND one contiguous range of the UMMA no-swizzle operand image:
+//   rows = the operand's M/N index, chunks over k  -> K-major image  (vector (r, kc) at kc*PLANE + r*16)
+//   rows = k, chunks over the M/N index            -> MN-major image (vector (k, c)  at c*PLANE  + k*16)
+// so the producers are cp.async.bulk copies (one elected lane per run, mbarrier complete_tx) and no
+// operand byte crosses the LSU: the L1 data pipe carries only the tensor-core operand reads.
+// Blocks: a tensor written by several launches (a2: one launch per env step) is a sequence of
+// blocks of block_rows rows, each a complete [part][chunk][row] array.
 enum { EPI_PLAIN = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2 };
 
-struct GemmArgs {
-  const float* A;      // element (m,k): A_TRANS ? A[k*lda + m] : A[m*lda + k]
-  const float* B;      // element (n,k): B_TRANS ? B[k*ldb + n] : B[n*ldb + k]
+struct SplitMat {
+  const uint8_t* base;
+  int rows;          // total rows (all blocks)
+  int block_rows;    // rows per block
+  int chunks;        // 8-column chunks per row
+};
+__host__ __device__ __forceinline__ int64_t split_part_bytes(const SplitMat& m) {
+  return (int64_t)m.chunks * m.block_rows * 16;
+}
+// rows [row0, row0 + cnt) of (part, chunk) -> cnt*16 contiguous bytes at dst
+__device__ __forceinline__ void split_bulk_rows(uint8_t* dst, const SplitMat& m, int part, int chunk,
+                                                int row0, int cnt, uint64_t* full) {
+  const int64_t pb = split_part_bytes(m);
+  int blk = row0 / m.block_rows, off = row0 - blk * m.block_rows;
+  while (cnt > 0) {
+    const int c = min(cnt, m.block_rows - off);
+    const uint8_t* src = m.base + (int64_t)blk * 2 * pb + part * pb + ((int64_t)chunk * m.block_rows + off) * 16;
+    bulk_g2s(dst, src, (uint32_t)c * 16u, full);
+    dst += c * 16; cnt -= c; off = 0; ++blk;
+  }
+}
+
+struct BulkGemmArgs {
+  SplitMat A, B;       // K-major operand: rows = M (N) index; MN-major operand: rows = k
+  SplitMat mask;       // EPI_MASK: split matrix [M rows][N columns]; output kept where its hi part > 0
   float* D;            // D[m*ldd + n]; split-K slice z writes D + z*M*ldd
-  const float* extra;  // EPI_BIAS_RELU: bias[n];  EPI_MASK: mask[m*ldd + n] (> 0 keeps)
+  const float* bias;   // EPI_BIAS_RELU: bias[n]
   int M, N, K;
-  int64_t lda, ldb, ldd;
+  int64_t ldd;
   int k_chunk, k_splits;   // K range per split-K slice (multiple of KB); ceil(K / k_chunk)
   int m_tiles, n_tiles;
 };
 
-// Operand images follow the SOURCE layout, so no transposition ever happens in registers:
-//   X_TRANS=false (element (r,k) at src[r*ld + k], k contiguous) -> K-major image
-//   X_TRANS=true  (element (r,k) at src[k*ld + r], r contiguous) -> MN-major image
-// (the instruction descriptor carries one major-ness bit per operand).
-template <int N_TILE_, int KB_, bool A_TRANS, bool B_TRANS, int EPI, int STAGES_ = 0>
-struct GemmPolicy : PolicyBase {
-  using Args = GemmArgs;
-  static constexpr int N_TILE = N_TILE_, KB = KB_, ACC_COLS = N_TILE_;
-  static constexpr int STAGES = STAGES_ > 0 ? STAGES_ : EPI == EPI_MASK ? 4 : 8;
-  static constexpr int OUT_COLS = N_TILE_, LO_DELTA = 0, SEG = 32;
-  static constexpr bool HAS_AUX = EPI != EPI_PLAIN, AUX_ROW_INVARIANT = EPI != EPI_MASK;
-  // the relu-mask epilogue waits on HBM: two epilogue sets, and 8 producer warps so that the 17
-  // warps get 96 registers per thread (8 float4 mask loads in flight per epilogue lane)
+// D[128 x NT] += A . B^T with the three bf16 products of the split:  A_hi.[B_hi | B_lo] as ONE MMA
+// of width 2*NT (the lo image of B sits right behind its hi image along N) and A_lo.B_hi of
+// width NT; output column c = acc[c] + acc[c + NT].
+template <int NT, int KB_, bool A_MN, bool B_MN, int EPI, int STAGES_>
+struct BulkGemm : PolicyBase {
+  using Args = BulkGemmArgs;
+  static constexpr int N_TILE = NT, KB = KB_, STAGES = STAGES_, PROD_WARPS = STAGES_;   // one warp per stage
+  static constexpr int ACC_COLS = 2 * NT, OUT_COLS = NT, LO_DELTA = NT, SEG = 32;
+  static constexpr bool HAS_AUX = EPI == EPI_BIAS_RELU, AUX_ROW_INVARIANT = true;
+  static constexpr bool HAS_PRE = EPI == EPI_MASK;
   static constexpr int EPI_SETS = EPI == EPI_MASK ? 2 : 1;
-  static constexpr int PROD_WARPS = EPI == EPI_MASK ? 8 : 16;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
-  // K-major image: plane (8 k) = (ROWS + KPAD) rows of 16 B; MN-major image: plane (8 rows) =
-  // (KB + 1) k of 16 B.  Pads make the producers' 8-byte stores bank-conflict-free.
-  static constexpr int KPAD = KB == 16 ? 4 : 2;
-  static constexpr int LBO_A = (kTileM + KPAD) * 16, LBO_B = (N_TILE + KPAD) * 16;
-  static constexpr int PLANE_MN = (KB + 1) * 16;
-  static constexpr int A_BYTES = A_TRANS ? (kTileM / 8) * PLANE_MN : (KB / 8) * LBO_A;   // one image
-  static constexpr int B_BYTES = B_TRANS ? (N_TILE / 8) * PLANE_MN : (KB / 8) * LBO_B;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  // stage = [A hi | A lo | B hi,lo]
+  static constexpr int A_PLANE = A_MN ? KB * 16 : kTileM * 16;       // K-major: 128 rows; MN-major: KB k
+  static constexpr int A_PART = kTileM * KB * 2;
+  static constexpr int B_PLANE = B_MN ? KB * 16 : 2 * NT * 16;       // K-major: rows [hi NT | lo NT]
+  static constexpr int B_OFF = 2 * A_PART;
+  static constexpr int STAGE_BYTES = 2 * A_PART + 4 * NT * KB;
   static constexpr int RES_BYTES = 0;
+  static constexpr int RA = A_MN ? kTileM / 8 : KB / 8, RB = B_MN ? NT / 8 : KB / 8;   // runs per part
+  static constexpr int NRUN = 2 * (RA + RB);
 
-  static __device__ __forceinline__ int num_items(const Args& g) {
-    return g.m_tiles * g.n_tiles * g.k_splits;
-  }
+  static __device__ __forceinline__ int num_items(const Args& g) { return g.m_tiles * g.n_tiles * g.k_splits; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
     TileCoord t;
     t.ks = item % g.k_splits;
@@ -585,94 +631,133 @@ struct GemmPolicy : PolicyBase {
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
 
-  // one operand tile [ROWS x KB]; every lane moves float4s: a warp instruction reads 512
-  // contiguous bytes (TRANS) or (KB/4)-lane row segments (K-major).  A lane keeps its position b
-  // inside the contiguous run and walks the runs with a constant stride, so the loop body is
-  // load / split / two 8-byte stores plus three additions; U loads are in flight per lane.
-  static constexpr int GS = PROD_WARPS / STAGES * 32;       // lanes that fill one stage
-  template <int ROWS, bool TRANS, int LBO>
-  static __device__ __forceinline__ void load_op(uint8_t* hi, uint8_t* lo, const float* __restrict__ src,
-                                                 int64_t ld, int r0, int rmax, int k0, int kmax,
-                                                 int glane) {
-    constexpr int Q = TRANS ? ROWS / 4 : KB / 4;            // float4 per contiguous run
-    constexpr int NA = TRANS ? KB : ROWS;                   // number of runs
-    static_assert(GS % Q == 0 && NA % (GS / Q) == 0, "stage lanes must tile the operand");
-    constexpr int STEP = GS / Q, N = NA / STEP, U = N < 8 ? N : 8;
-    static_assert(N % U == 0, "load batches");
-    const int b = glane % Q, a0 = glane / Q;                // TRANS: (k, r4) = (a, b)  else (row, k4)
-    const bool bok = TRANS ? (r0 + b * 4 < rmax) : (k0 + b * 4 < kmax);
-    const int alim = (TRANS ? kmax - k0 : rmax - r0) - a0;  // run a0 + j*STEP exists iff j*STEP < alim
-    const float* p = src + (int64_t)((TRANS ? k0 : r0) + a0) * ld + (TRANS ? r0 : k0) + b * 4;
-    const int64_t pstep = (int64_t)STEP * ld;
-    int off = (b >> 1) * (TRANS ? PLANE_MN : LBO) + a0 * 16 + (b & 1) * 8;
-#pragma unroll 1
-    for (int j0 = 0; j0 < N; j0 += U) {
-      float4 x[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bok && (j0 + u) * STEP < alim) x[u] = ldg4(p + (int64_t)u * pstep);
+  // the part of the stage no copy will fill and the MMA reduces over: k >= the end of the K range
+  static __device__ __forceinline__ void load_stage(const Args&, const TileCoord& t, int s, uint8_t* st,
+                                                    int glane, int gsize, Prod&) {
+    const int kvalid = t.k_end - (t.k_begin + s * KB);
+    if (kvalid >= KB) return;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    if (A_MN) {
+      const int nk = KB - kvalid;
+      for (int i = glane; i < 2 * RA * nk; i += gsize)
+        *reinterpret_cast<uint4*>(st + (i / nk) * A_PLANE + (kvalid + i % nk) * 16) = z;
+    } else {
+      const int c0 = kvalid / 8, nc = KB / 8 - c0;
+      for (int i = glane; i < 2 * nc * kTileM; i += gsize) {
+        const int part = i / (nc * kTileM), r = i % (nc * kTileM);
+        *reinterpret_cast<uint4*>(st + part * A_PART + c0 * A_PLANE + r * 16) = z;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) store_half_split(hi, lo, off + u * (STEP * 16), x[u]);
-      p += (int64_t)U * pstep;
-      off += U * STEP * 16;
+    }
+    if (B_MN) {
+      const int nk = KB - kvalid;
+      for (int i = glane; i < 2 * RB * nk; i += gsize)
+        *reinterpret_cast<uint4*>(st + B_OFF + (i / nk) * B_PLANE + (kvalid + i % nk) * 16) = z;
+    } else {
+      const int c0 = kvalid / 8, nc = KB / 8 - c0;
+      for (int i = glane; i < nc * 2 * NT; i += gsize)
+        *reinterpret_cast<uint4*>(st + B_OFF + c0 * B_PLANE + i * 16) = z;
     }
   }
-  static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int, Prod&) {
-    const int k0 = t.k_begin + s * KB;
-    uint8_t* a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = b_hi + B_BYTES;
-    load_op<kTileM, A_TRANS, LBO_A>(a_hi, a_lo, g.A, g.lda, t.mt * kTileM, g.M, k0, t.k_end, glane);
-    load_op<N_TILE, B_TRANS, LBO_B>(b_hi, b_lo, g.B, g.ldb, t.nt * N_TILE, g.N, k0, t.k_end, glane);
+  // run -> (matrix, part, chunk, first row, rows, byte offset in the stage); rows <= 0: nothing to copy
+  struct Run { const SplitMat* m; int part, chunk, row0, cnt, dst; };
+  static __device__ __forceinline__ Run run_of(const Args& g, const TileCoord& t, int k0, int kvalid, int run) {
+    Run r;
+    if (run < 2 * RA) {
+      const int c = run % RA;
+      r.m = &g.A; r.part = run / RA;
+      if (A_MN) {
+        r.chunk = t.mt * (kTileM / 8) + c; r.row0 = k0; r.cnt = r.chunk * 8 < g.M ? kvalid : 0;
+      } else {
+        r.chunk = k0 / 8 + c; r.row0 = t.mt * kTileM; r.cnt = c * 8 < kvalid ? min(kTileM, g.M - r.row0) : 0;
+      }
+      r.dst = r.part * A_PART + c * A_PLANE;
+    } else {
+      const int q = run - 2 * RA, c = q % RB;
+      r.m = &g.B; r.part = q / RB;
+      if (B_MN) {
+        r.chunk = t.nt * (NT / 8) + c; r.row0 = k0; r.cnt = r.chunk * 8 < g.N ? kvalid : 0;
+        r.dst = B_OFF + (r.part * (NT / 8) + c) * B_PLANE;
+      } else {
+        r.chunk = k0 / 8 + c; r.row0 = t.nt * NT; r.cnt = c * 8 < kvalid ? min(NT, g.N - r.row0) : 0;
+        r.dst = B_OFF + c * B_PLANE + r.part * NT * 16;
+      }
+    }
+    return r;
   }
-  static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s,
-                                               uint32_t st, uint32_t, uint32_t d_tmem) {
-    constexpr uint32_t idesc = make_idesc(N_TILE, A_TRANS, B_TRANS);
-    const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+  static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
+                                                    int glane, int gsize, uint64_t* full) {
+    if (glane >= NRUN) return false;
+    const int k0 = t.k_begin + s * KB, kvalid = min(KB, t.k_end - k0);
+    uint32_t bytes = 0;
+    for (int run = glane; run < NRUN; run += gsize) {
+      const Run r = run_of(g, t, k0, kvalid, run);
+      bytes += r.cnt > 0 ? (uint32_t)r.cnt * 16u : 0u;
+    }
+    mbar_expect_tx(full, bytes);
+    for (int run = glane; run < NRUN; run += gsize) {
+      const Run r = run_of(g, t, k0, kvalid, run);
+      if (r.cnt > 0) split_bulk_rows(st + r.dst, *r.m, r.part, r.chunk, r.row0, r.cnt, full);
+    }
+    return true;
+  }
+  static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st, uint32_t,
+                                               uint32_t d_tmem) {
+    constexpr uint32_t idesc2 = make_idesc(2 * NT, A_MN, B_MN), idesc1 = make_idesc(NT, A_MN, B_MN);
 #pragma unroll
     for (int k16 = 0; k16 < KB / 16; ++k16) {
-      const uint32_t ao = A_TRANS ? k16 * 256 : k16 * 2 * LBO_A;
-      const uint32_t bo = B_TRANS ? k16 * 256 : k16 * 2 * LBO_B;
-      const uint64_t da_hi = A_TRANS ? make_sdesc(a_hi + ao, 128, PLANE_MN) : make_sdesc(a_hi + ao, LBO_A);
-      const uint64_t da_lo = A_TRANS ? make_sdesc(a_lo + ao, 128, PLANE_MN) : make_sdesc(a_lo + ao, LBO_A);
-      const uint64_t db_hi = B_TRANS ? make_sdesc(b_hi + bo, 128, PLANE_MN) : make_sdesc(b_hi + bo, LBO_B);
-      const uint64_t db_lo = B_TRANS ? make_sdesc(b_lo + bo, 128, PLANE_MN) : make_sdesc(b_lo + bo, LBO_B);
-      umma_f16(d_tmem, da_hi, db_hi, idesc, (s | k16) != 0 ? 1u : 0u);
-      umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-      umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+      const uint32_t a = st + (A_MN ? k16 * 256 : k16 * 2 * A_PLANE);
+      const uint32_t b = st + B_OFF + (B_MN ? k16 * 256 : k16 * 2 * B_PLANE);
+      const uint64_t da_hi = A_MN ? make_sdesc(a, 128, A_PLANE) : make_sdesc(a, A_PLANE);
+      const uint64_t da_lo = A_MN ? make_sdesc(a + A_PART, 128, A_PLANE) : make_sdesc(a + A_PART, A_PLANE);
+      const uint64_t db = B_MN ? make_sdesc(b, 128, B_PLANE) : make_sdesc(b, B_PLANE);
+      umma_f16(d_tmem, da_hi, db, idesc2, (s | k16) != 0 ? 1u : 0u);     // a_hi . [b_hi | b_lo]
+      umma_f16(d_tmem, da_lo, db, idesc1, 1u);                            // a_lo . b_hi
     }
   }
-  // ---- epilogue: row m of the tile is N_TILE contiguous floats of D
+  // ---- epilogue: row m of the tile is NT contiguous floats of D
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
     const int m = t.mt * kTileM + row;
     if (m >= g.M) return nullptr;
-    return g.D + (int64_t)t.ks * g.M * g.ldd + (int64_t)m * g.ldd + t.nt * N_TILE;
+    return g.D + (int64_t)t.ks * g.M * g.ldd + (int64_t)m * g.ldd + t.nt * NT;
   }
   static __device__ __forceinline__ bool seg_valid(const Args& g, const TileCoord& t, int sg) {
-    return t.nt * N_TILE + sg * SEG < g.N;
+    return t.nt * NT + sg * SEG < g.N;
   }
-  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int sg) {
-    return sg * SEG;
-  }
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int sg) { return sg * SEG; }
   static __device__ __forceinline__ bool col_valid(const Args& g, const TileCoord& t, int col) {
-    return t.nt * N_TILE + col < g.N;
+    return t.nt * NT + col < g.N;
   }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord& t, const float* dst,
-                                                    int col, int64_t) {
-    if (EPI == EPI_BIAS_RELU) return ldg4(g.extra + t.nt * N_TILE + col);
-    if (EPI == EPI_MASK) return ldg4(g.extra + (dst - g.D));
-    return make_float4(0.f, 0.f, 0.f, 0.f);
+  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord& t, const float*, int col,
+                                                    int64_t) {
+    return ldg4(g.bias + t.nt * NT + col);
   }
   static __device__ __forceinline__ float4 finish(const Args&, float4 o, float4 x) {
     if (EPI == EPI_BIAS_RELU) {
       o.x = fmaxf(o.x + x.x, 0.f); o.y = fmaxf(o.y + x.y, 0.f);
       o.z = fmaxf(o.z + x.z, 0.f); o.w = fmaxf(o.w + x.w, 0.f);
-    } else if (EPI == EPI_MASK) {
-      o.x = x.x > 0.f ? o.x : 0.f; o.y = x.y > 0.f ? o.y : 0.f;
-      o.z = x.z > 0.f ? o.z : 0.f; o.w = x.w > 0.f ? o.w : 0.f;
     }
     return o;
+  }
+  // relu mask, applied in the lane = row arrangement of the TMEM read-out: 8 consecutive columns
+  // = one chunk = one 16-byte vector of the mask's hi part; a warp reads 512 contiguous bytes
+  static __device__ __forceinline__ int64_t pre_row(const Args& g, const TileCoord& t, int row) {
+    const int m = t.mt * kTileM + row;
+    if (m >= g.M) return -1;
+    const int blk = m / g.mask.block_rows, off = m - blk * g.mask.block_rows;
+    return (int64_t)blk * 2 * split_part_bytes(g.mask) + (int64_t)off * 16;
+  }
+  static __device__ __forceinline__ uint4 pre_load(const Args& g, const TileCoord& t, int64_t prow, int col) {
+    const int n = t.nt * NT + col;
+    if (prow < 0 || n >= g.N) return make_uint4(0u, 0u, 0u, 0u);
+    return __ldg(reinterpret_cast<const uint4*>(g.mask.base + prow + (int64_t)(n >> 3) * g.mask.block_rows * 16));
+  }
+  static __device__ __forceinline__ void pre_apply(float (&v)[8], const uint4& m) {
+    const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((int16_t)(w[i] & 0xFFFFu) <= 0) v[2 * i] = 0.f;          // bf16 > 0  <=>  its bits as int16 > 0
+      if ((int32_t)w[i] < 0x10000) v[2 * i + 1] = 0.f;
+    }
   }
 };
 

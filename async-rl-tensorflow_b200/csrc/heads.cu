@@ -5,9 +5,20 @@
 //   sampling  : network.py:72 batch_sample -> Philox4x32-10 + inverse CDF (oracle/philox.py)
 //   returns   : Algorithm 3 + agent.py:154,188-190;  loss grads: network.py:81-94 (repaired)
 //   heads bwd : d_h, d p_w/p_b/q_w/q_b
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace arl {
+
+// two floats -> packed bf16 hi parts and packed bf16 lo parts (value = hi + lo to ~2^-17)
+__device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream);
@@ -255,14 +266,19 @@ __global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
 // CTA = 256 threads (thread k owns hidden unit k).  Per sample: d_h[n][k] = (h>0) * sum_j
 // dz[n][j]*Wcat[k][j];  dWcat[k][j] += h[n][k]*dz[n][j];  dbcat[j] += dz[n][j].
 // Partials per CTA -> workspace [grid][256*J + J], reduced deterministically afterwards.
-constexpr int kHbChunk = 64;
+// d_h leaves as split bf16 in 16-byte chunk vectors, one block of num_samples rows
+// ([hi|lo][32 chunks][num_samples][8], gemm_tc.cuh SplitMat): the layout the fc256 backward kernels
+// fetch with cp.async.bulk.  32 samples are staged in shared memory so that a warp writes the 32
+// consecutive rows of one chunk = 512 contiguous bytes.
+constexpr int kHbChunk = 64, kHbSub = 32;
 template <int JMAX>
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
                  const float* __restrict__ h, const float* __restrict__ dlogits,
-                 const float* __restrict__ dvalue, float* __restrict__ d_h,
+                 const float* __restrict__ dvalue, uint8_t* __restrict__ dhs,
                  float* __restrict__ partials, int64_t num_samples, int A) {
   __shared__ float dzs[kHbChunk][JMAX];
+  __shared__ float dt[kHbSub][257];
   const int J = A + 1;
   const int k = threadIdx.x;
   float w[JMAX], acc[JMAX];
@@ -275,6 +291,7 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
   const int64_t per = (num_samples + gridDim.x - 1) / gridDim.x;
   const int64_t beg = per * blockIdx.x;
   const int64_t end = beg + per < num_samples ? beg + per : num_samples;
+  const int64_t lo_part = (int64_t)32 * num_samples * 16;
   for (int64_t c0 = beg; c0 < end; c0 += kHbChunk) {
     const int nc = (int)(end - c0 < kHbChunk ? end - c0 : kHbChunk);
     __syncthreads();
@@ -283,18 +300,37 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
       dzs[s][j] = j < A ? dlogits[(c0 + s) * A + j] : dvalue[c0 + s];
     }
     __syncthreads();
-    for (int s = 0; s < nc; ++s) {
-      const float hv = h[(c0 + s) * 256 + k];
-      float d = 0.f;
+    for (int s0 = 0; s0 < nc; s0 += kHbSub) {
+      const int ns = nc - s0 < kHbSub ? nc - s0 : kHbSub;
+      for (int s = 0; s < ns; ++s) {
+        const float hv = h[(c0 + s0 + s) * 256 + k];
+        float d = 0.f;
 #pragma unroll
-      for (int j = 0; j < JMAX; ++j) {
-        if (j < J) {
-          const float g = dzs[s][j];
-          d = fmaf(g, w[j], d);
-          acc[j] = fmaf(hv, g, acc[j]);
+        for (int j = 0; j < JMAX; ++j) {
+          if (j < J) {
+            const float g = dzs[s0 + s][j];
+            d = fmaf(g, w[j], d);
+            acc[j] = fmaf(hv, g, acc[j]);
+          }
+        }
+        dt[s][k] = hv > 0.f ? d : 0.f;
+      }
+      __syncthreads();
+      for (int v = k; v < 32 * kHbSub; v += 256) {
+        const int s = v % kHbSub, kc = v / kHbSub;
+        if (s < ns) {
+          const float* x = &dt[s][kc * 8];
+          uint4 hi, lo;
+          tc_split2(x[0], x[1], hi.x, lo.x);
+          tc_split2(x[2], x[3], hi.y, lo.y);
+          tc_split2(x[4], x[5], hi.z, lo.z);
+          tc_split2(x[6], x[7], hi.w, lo.w);
+          uint8_t* d = dhs + ((int64_t)kc * num_samples + c0 + s0 + s) * 16;
+          *reinterpret_cast<uint4*>(d) = hi;
+          *reinterpret_cast<uint4*>(d + lo_part) = lo;
         }
       }
-      d_h[(c0 + s) * 256 + k] = hv > 0.f ? d : 0.f;
+      __syncthreads();
     }
     if (k < J)
       for (int s = 0; s < nc; ++s) bacc += dzs[s][k];
@@ -448,13 +484,13 @@ extern "C" int arl_heads_backward(const float* params, int action_size, const fl
   float* part = (float*)workspace;
   if (J <= 8)
     heads_bwd_kernel<8><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
-                                             dvalue, d_h, part, num_samples, A);
+                                             dvalue, (uint8_t*)d_h, part, num_samples, A);
   else if (J <= 20)
     heads_bwd_kernel<20><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h,
-                                              dlogits, dvalue, d_h, part, num_samples, A);
+                                              dlogits, dvalue, (uint8_t*)d_h, part, num_samples, A);
   else
     heads_bwd_kernel<ARL_MAX_ACTIONS + 1><<<grid, 256, 0, st>>>(
-        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, d_h, part, num_samples, A);
+        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, (uint8_t*)d_h, part, num_samples, A);
   ARL_LAUNCH_CHECK("heads_bwd_kernel");
   return reduce_partials(part, g, grid, 256 * J + J, st);
 }

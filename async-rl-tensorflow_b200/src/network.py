@@ -32,6 +32,14 @@ def decode_a1(raw):
     return v.permute(0, 4, 1, 5, 2, 3, 6).reshape(n, 20, 20, 16)
 
 
+def decode_split(raw, rows, cols):
+    """A "split block" (include/asyncrl_b200.h: [hi|lo][cols/8 chunks][rows][8] bf16, the operand
+    layout of the fc256 tensor-core kernels) -> float32 [rows, cols].  ``raw`` is the float32
+    storage of rows*cols elements the C-ABI filled."""
+    b = raw.reshape(-1).view(torch.bfloat16).reshape(2, cols // 8, rows, 8)
+    return (b[0].float() + b[1].float()).permute(1, 0, 2).reshape(rows, cols)
+
+
 def param_shapes(action_size):
     return OrderedDict([
         ("l1_w", (8, 8, 4, 16)), ("l1_b", (16,)), ("l2_w", (4, 4, 16, 32)), ("l2_b", (32,)),
@@ -91,13 +99,18 @@ class Network(object):
         for i, (name, shape) in enumerate(param_shapes(A).items()):
             self.w[name] = self.params[self.offsets[i]:self.offsets[i + 1]].view(shape)
             self.g[name] = self.grads[self.offsets[i]:self.offsets[i + 1]].view(shape)
+        # l4_w as the split block the fc256 kernels read (arl_fc_prepare); refreshed lazily: the key
+        # is (tensor version, number of C-ABI writes) of the parameters it was made from
+        self.fc_w = torch.empty(A2_ELEMS * FC, device=dev)
+        self._fc_w_key = None
+        self._param_writes = 0
         self.set_weights(initial_weights(A, seed))
 
         N = B * T
         f32 = dict(device=dev, dtype=torch.float32)
         # rollout activations, t-major: sample n = t*B + b
         self.l1 = torch.empty(N, 20, 20, 16, **f32)           # network.py:47-48, stored split-bf16 blocked: see a1()
-        self.l2 = torch.empty(N, A2_ELEMS, **f32)             # network.py:49-50 (flattened NHWC)
+        self.l2 = torch.empty(N, A2_ELEMS, **f32)             # network.py:49-50 (flattened NHWC), one split block per step: see a2()
         self.l4 = torch.empty(N, FC, **f32)                   # network.py:51-52
         self.policy_logits = torch.empty(N, A, **f32)         # network.py:62
         self.policy = torch.empty(N, A, **f32)                # network.py:65
@@ -111,7 +124,7 @@ class Network(object):
         # backward scratch
         self.d_logits = torch.empty(N, A, **f32)
         self.d_value = torch.empty(N, **f32)
-        self.d_l4 = torch.empty(N, FC, **f32)
+        self.d_l4 = torch.empty(N, FC, **f32)                 # one split block: see d_h()
         self.d_l2 = torch.empty(N, A2_ELEMS, **f32)
         self.d_l1 = torch.empty(N, 20, 20, 16, **f32)
         self.workspace = torch.empty(_cabi.workspace_bytes(A), dtype=torch.uint8, device=dev)
@@ -153,18 +166,29 @@ class Network(object):
         else:
             _cabi.call(name, *args)
 
+    def _fc_w_stale(self):
+        """True (once) when l4_w has changed since fc_w was made: torch bumps ``_version`` on every
+        in-place write to params or to a view of it, C-ABI writes are counted by hand."""
+        key = (self.params._version, self._param_writes)
+        stale = key != self._fc_w_key
+        self._fc_w_key = key
+        return stale
+
     def _forward_into(self, history, l1, l2, l4, logits, probs, value):
         P, st = _cabi.ptr, _cabi.stream_ptr()
         B, A = self.num_envs, self.action_size
+        refresh = 1 if self._fc_w_stale() else 0
         if self.timed is None:
-            _cabi.call("arl_forward", P(self.params), A, P(history.ring), B, history.ring_slots,
-                       history.first_slot(0), 1, P(l1), P(l2), P(l4), P(logits), P(probs),
-                       P(value), st)
+            _cabi.call("arl_forward", P(self.params), P(self.fc_w), refresh, A, P(history.ring), B,
+                       history.ring_slots, history.first_slot(0), 1, P(l1), P(l2), P(l4),
+                       P(logits), P(probs), P(value), st)
             return
+        if refresh:
+            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
         self._timed_call("arl_conv1_forward", P(self.params), P(history.ring), P(l1), B,
                          history.ring_slots, history.first_slot(0), 1, st)
         self._timed_call("arl_conv2_forward", P(self.params), P(l1), P(l2), B, st)
-        self._timed_call("arl_fc_forward", P(self.params), P(l2), P(l4), B, st)
+        self._timed_call("arl_fc_forward", P(self.params), P(self.fc_w), P(l2), P(l4), B, st)
         self._timed_call("arl_heads_forward", P(self.params), A, P(l4), P(logits), P(probs),
                          P(value), B, st)
 
@@ -178,6 +202,16 @@ class Network(object):
     def a1(self):
         """conv1 activations of the rollout as float32 [N,20,20,16] (decoded from the device layout)."""
         return decode_a1(self.l1)
+
+    def a2(self):
+        """conv2 activations of the rollout as float32 [N,2592] (NHWC flatten, agent.py:231-232),
+        decoded from the per-step split blocks."""
+        B = self.num_envs
+        return torch.cat([decode_split(self.l2[self._rows(t)], B, A2_ELEMS) for t in range(self.t_max)])
+
+    def d_h(self):
+        """Gradient w.r.t. the fc256 output of the last backward as float32 [N,256]."""
+        return decode_split(self.d_l4, self.d_l4.shape[0], FC)
 
     def sample(self, t, step, seed, env_id_base=0):
         """network.py:72-73 sampled_action for rollout slot t."""
@@ -222,16 +256,18 @@ class Network(object):
                    _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
                    self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
         P = _cabi.ptr
+        if self._fc_w_stale():                                 # (a forward normally did this already)
+            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
         if self.timed is None:
-            _cabi.call("arl_backward", P(self.params), A, P(history.ring), B, history.ring_slots,
-                       history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
-                       P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
+            _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
+                       history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2),
+                       P(self.l4), P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
                        P(self.d_l1), P(self.grads), P(self.workspace), st)
             return self.grads
         N = T * B
         self._timed_call("arl_heads_backward", P(self.params), A, P(self.l4), P(self.d_logits),
                          P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, st)
-        self._timed_call("arl_fc_backward", P(self.params), P(self.l2), P(self.d_l4), P(self.d_l2),
+        self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), B, P(self.d_l4), P(self.d_l2),
                          P(self.grads), P(self.workspace), N, st)
         self._timed_call("arl_conv2_backward", P(self.params), P(self.l1), P(self.d_l2),
                          P(self.d_l1), P(self.grads), P(self.workspace), N, st)
@@ -248,6 +284,7 @@ class Network(object):
         self.target_q = torch.empty(N, A, **f32)              # agent.py:186 q_t_plus_1
         self.target_q_t = torch.empty(N, **f32)               # agent.py:190
         self._tq_scratch = (torch.empty(N, A, **f32), torch.empty(N, **f32))
+        self.target_fc_w = torch.empty(A2_ELEMS * FC, device=self.device)
         return self.target_params
 
     def update_target(self):
@@ -268,17 +305,19 @@ class Network(object):
         T, B, A = self.t_max, self.num_envs, self.action_size
         P, st = _cabi.ptr, _cabi.stream_ptr()
         probs, value = self._tq_scratch
-        _cabi.call("arl_forward", P(self.target_params), A, P(history.ring), B, history.ring_slots,
-                   history.first_slot(T - 1), T, P(self.d_l1), P(self.d_l2), P(self.d_l4),
-                   P(self.target_q), P(probs), P(value), st)
+        _cabi.call("arl_forward", P(self.target_params), P(self.target_fc_w), 1, A, P(history.ring),
+                   B, history.ring_slots, history.first_slot(T - 1), T, P(self.d_l1), P(self.d_l2),
+                   P(self.d_l4), P(self.target_q), P(probs), P(value), st)
         self.loss_sums.zero_()
         _cabi.call("arl_q_lossgrad", P(rewards), P(terminals), P(self.sampled_action),
                    P(self.policy_logits), P(self.target_q), P(self.target_q_t), P(self.d_logits),
                    P(self.loss_sums), T * B, A, self.gamma, self.min_reward, self.max_reward,
                    float(grad_scale), st)
         self.d_value.zero_()                                   # the value head is unused
-        _cabi.call("arl_backward", P(self.params), A, P(history.ring), B, history.ring_slots,
-                   history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
+        if self._fc_w_stale():
+            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
+        _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
+                   history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
                    P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
                    P(self.d_l1), P(self.grads), P(self.workspace), st)
         return self.grads
@@ -293,6 +332,7 @@ class Network(object):
                    _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
                    self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
                    _cabi.stream_ptr())
+        self._param_writes += 1                                # the kernel wrote params: fc_w is stale
 
     # -- checkpoints (network.py:109-127), reference variable names + the rms slot ----------
     def save_model(self, saver=None, checkpoint_dir='checkpoints', step=None):

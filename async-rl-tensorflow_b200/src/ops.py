@@ -45,8 +45,11 @@ def linear(input_, params, output_size, out=None, name='l4'):
         n = x.shape[0]
         if out is None:
             out = torch.empty(n, FC, device=params.device)
-        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(x), _cabi.ptr(out), n,
-                   _cabi.stream_ptr())
+        # x is the split block conv2d(name='l2') wrote; l4_w is split into scratch on every call
+        w_split = torch.empty(A2_ELEMS * FC, device=params.device)
+        _cabi.call("arl_fc_prepare", _cabi.ptr(params), _cabi.ptr(w_split), _cabi.stream_ptr())
+        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(w_split), _cabi.ptr(x),
+                   _cabi.ptr(out), n, _cabi.stream_ptr())
         return out
     raise NotImplementedError("linear %s: only the fc256 layer is exposed stand-alone; the "
                               "policy/value heads run fused in heads()" % name)

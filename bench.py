@@ -37,10 +37,10 @@ ENTRY_WORK = {
     "arl_preprocess_push": ("preprocess_kernel", 0.0, 80640 + 7056),
     "arl_conv1_forward": ("tc_kernel<Conv1Fwd> (kind::i8, bulk-copied ring)", 2.0 * 1638400, 28224 + 25600),
     "arl_conv2_forward": ("tc_kernel<Conv2Fwd>", 2.0 * 663552, 25600 + 10368),
-    "arl_fc_forward": ("tc_kernel<GemmPolicy fc fwd>", 2.0 * 663552, 10368 + 1024),
+    "arl_fc_forward": ("tc_kernel<BulkGemm fc fwd>", 2.0 * 663552, 10368 + 1024),
     "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * 7, 1024 + 56),
     "arl_heads_backward": ("heads_bwd_kernel", 4.0 * 256 * 7, 2048 + 28),
-    "arl_fc_backward": ("tc_kernel<GemmPolicy fc dgrad> + <fc wgrad>", 4.0 * 663552,
+    "arl_fc_backward": ("tc_kernel<BulkGemm fc dgrad> + <fc wgrad>", 4.0 * 663552,
                         2 * 10368 + 1024 + 10368 + 1024),
     "arl_conv2_backward": ("tc_kernel<Conv2Wgrad> + <Conv2Dgrad>", 4.0 * 663552,
                            2 * (25600 + 10368) + 25600),

@@ -25,6 +25,16 @@
  *     (y,x) = (2yp+i, 2xp+j); value = hi + lo.  Only arl_conv1_forward writes it and only
  *     arl_conv2_forward / arl_conv2_backward read it (as tensor-core operand and relu mask);
  *     src/network.py:decode_a1 turns it back into f32 NHWC.
+ *   - the fc256 layer's tensors are kept as "split blocks": a logical f32 matrix [rows][8*chunks]
+ *     stored as [part (hi, lo)][chunk][row][8 bf16] (16-byte vectors, value = hi + lo, same bytes
+ *     as the f32 matrix), which the tcgen05 kernels fetch with cp.async.bulk and never convert:
+ *       a2  (the f32 [N,2592]-sized buffer): one block per arl_conv2_forward call, rows = the
+ *           call's num_samples, 324 chunks in NHWC-flatten order (agent.py:231-232);
+ *       d_h (the f32 [N,256]-sized buffer): one block of N rows, 32 chunks, written by
+ *           arl_heads_backward;
+ *       fc_w_split (2592*256 floats): l4_w as one block of 2592 rows, 32 chunks, written by
+ *           arl_fc_prepare -- must be refreshed whenever l4_w changes.
+ *     src/network.py:decode_split turns a block back into f32 [rows][cols].
  *   - parameters / gradients / RMSProp slots are flat f32 buffers in the
  *     reference's own variable order and layouts (see arl_param_layout).
  */
@@ -113,25 +123,34 @@ ARL_API int arl_history_reset(uint8_t* ring, int num_envs, int ring_slots, void*
  * agent.py:226-232,251 (s_t/255 -> conv 8x8s4 relu -> conv 4x4s2 relu -> NHWC flatten ->
  * fc256 relu), network.py:62 (policy logits), network.py:79 (value), network.py:65
  * (softmax).  steps*num_envs samples.  a1 [N,20,20,16], a2 [N,2592], h [N,256] are
- * written for the backward pass; logits/probs [N,A], value [N]. */
+ * written for the backward pass (a1 and a2 in the device layouts described at the top of this
+ * file); logits/probs [N,A], value [N]. */
 ARL_API int arl_conv1_forward(const float* params, const uint8_t* ring, float* a1, int num_envs,
                       int ring_slots, int first_slot, int steps, void* stream);
+/* a2 = ONE split block of num_samples rows. */
 ARL_API int arl_conv2_forward(const float* params, const float* a1, float* a2, int64_t num_samples,
                       void* stream);
-ARL_API int arl_fc_forward(const float* params, const float* a2, float* h, int64_t num_samples,
-                   void* stream);
+/* l4_w (agent.py:251) -> fc_w_split, the split block the fc256 kernels read.  Call after every
+ * change of the parameters (arl_clip_rmsprop, a checkpoint load, ...). */
+ARL_API int arl_fc_prepare(const float* params, float* fc_w_split, void* stream);
+/* a2 = one split block of num_samples rows (as arl_conv2_forward wrote it); h f32 [N,256]. */
+ARL_API int arl_fc_forward(const float* params, const float* fc_w_split, const float* a2, float* h,
+                   int64_t num_samples, void* stream);
 ARL_API int arl_heads_forward(const float* params, int action_size, const float* h, float* logits,
                       float* probs, float* value, int64_t num_samples, void* stream);
-/* The four above back to back. */
-ARL_API int arl_forward(const float* params, int action_size, const uint8_t* ring, int num_envs,
-                int ring_slots, int first_slot, int steps, float* a1, float* a2, float* h,
-                float* logits, float* probs, float* value, void* stream);
+/* The four above back to back, after arl_fc_prepare when refresh_fc_w != 0 (pass 1 unless
+ * fc_w_split was filled from these very parameters by an earlier call). */
+ARL_API int arl_forward(const float* params, float* fc_w_split, int refresh_fc_w, int action_size,
+                const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
+                float* a1, float* a2, float* h, float* logits, float* probs, float* value,
+                void* stream);
 
-/* Test hook for the tcgen05 GEMM behind arl_fc_forward/backward (fp32 operands, bf16x3 split,
- * fp32 accumulation in TMEM), on caller-chosen shapes.  N % 16 == 0, K % 8 == 0.
- *   variant 0/1: D[M,N] = relu(A[M,K] . B[K,N] + extra[N])            (N tile 256 / 64)
- *   variant 2  : D[M,N] = (A[M,K] . B[N,K]^T) where extra[M,N] > 0, else 0
- *   variant 3  : D[z][M,N] = A[K,M]^T . B[K,N] over split-K slice z  (M % 8 == 0) */
+/* Test hook for the tcgen05 GEMM behind arl_fc_forward/backward (fp32 inputs are split into
+ * scratch blocks first; bf16x3 products, fp32 accumulation in TMEM), on caller-chosen shapes.
+ * N % 16 == 0, K % 8 == 0.  Synchronises the stream.
+ *   variant 0/1: D[M,N] = relu(A[M,K] . B[K,N] + extra[N])            (forward instantiation)
+ *   variant 2  : D[M,N] = (A[M,K] . B[N,K]^T) where extra[M,N] > 0, else 0        (dgrad)
+ *   variant 3/4: D[z][M,N] = A[K,M]^T . B[K,N] over split-K slice z  (M % 8 == 0)  (wgrad) */
 ARL_API int arl_debug_gemm(int variant, const float* A, const float* B, float* D, const float* extra,
                            int M, int N, int K, int k_splits, void* stream);
 
@@ -177,19 +196,24 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
 /* ---- backward: agent.py:317 compute_gradients ---------------------------------------
  * Accumulation over the T steps of Algorithm 3 is the reduction over samples inside the
  * weight-gradient kernels.  grads is the flat buffer (overwritten).  Scratch buffers are
- * caller-owned: d_h [N,256], d_a2 [N,2592], d_a1 [N,6400], workspace >= arl_backward_workspace_bytes. */
+ * caller-owned: d_h [N,256] (a split block, see the top of this file), d_a2 [N,2592], d_a1 [N,6400],
+ * workspace >= arl_backward_workspace_bytes.  a2 = the rollout's conv2 outputs as a sequence of
+ * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);
+ * fc_w_split must hold arl_fc_prepare of the parameters the forward used. */
 ARL_API int64_t arl_backward_workspace_bytes(int action_size);
 ARL_API int arl_heads_backward(const float* params, int action_size, const float* h,
                        const float* dlogits, const float* dvalue, float* d_h, float* grads,
                        void* workspace, int64_t num_samples, void* stream);
-ARL_API int arl_fc_backward(const float* params, const float* a2, const float* d_h, float* d_a2,
-                    float* grads, void* workspace, int64_t num_samples, void* stream);
+ARL_API int arl_fc_backward(const float* fc_w_split, const float* a2, int64_t a2_block_rows,
+                    const float* d_h, float* d_a2, float* grads, void* workspace,
+                    int64_t num_samples, void* stream);
 ARL_API int arl_conv2_backward(const float* params, const float* a1, const float* d_a2, float* d_a1,
                        float* grads, void* workspace, int64_t num_samples, void* stream);
 ARL_API int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads, void* workspace,
                        int num_envs, int ring_slots, int first_slot, int steps, void* stream);
-ARL_API int arl_backward(const float* params, int action_size, const uint8_t* ring, int num_envs,
-                 int ring_slots, int first_slot, int steps, const float* a1, const float* a2,
+ARL_API int arl_backward(const float* params, const float* fc_w_split, int action_size,
+                 const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
+                 const float* a1, const float* a2,
                  const float* h, const float* dlogits, const float* dvalue, float* d_h,
                  float* d_a2, float* d_a1, float* grads, void* workspace, void* stream);
 

@@ -30,7 +30,7 @@ def _run(pkg, variant, M, N, K, k_splits=1, seed=0):
                    pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
     if variant >= 3:
-        kb = 16
+        kb = 64                                   # FcWgrad::KB (csrc/fc.cu)
         per = (K + k_splits - 1) // k_splits
         k_chunk = (per + kb - 1) // kb * kb
         used = (K + k_chunk - 1) // k_chunk
@@ -52,8 +52,8 @@ def test_gemm_variants_vs_float64(pkg, cuda, variant, M, N, K):
 @pytest.mark.parametrize("M,N,K,splits", [(128, 256, 32, 1), (2592, 256, 1280, 7),
                                           (2592, 256, 77, 7), (264, 256, 5000, 3)])
 def test_gemm_wgrad_splitk_vs_float64(pkg, cuda, M, N, K, splits):
-    # K need not be a multiple of 8 for the sample-major operands; variant 3 transposes them in
-    # registers into K-major images, variant 4 uses MN-major images (the conv wgrad path)
+    # K (= samples) need not be a multiple of 8 for the sample-major (MN-major) operands; variants
+    # 3 and 4 are the same instantiation
     for variant in (3, 4):
         e = _run(pkg, variant, M, N, K, k_splits=splits)
         print("gemm wgrad v%d %dx%dx%d/%d rel-err %.3e" % (variant, M, N, K, splits, e))

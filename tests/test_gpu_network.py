@@ -32,7 +32,7 @@ def net_for(pkg, A, B, T, params):
 
 def gpu_masks(net):
     """relu activation pattern of the device forward (see oracle.a3c._relu)."""
-    return dict(a1=(net.a1() > 0).cpu().numpy(), a2=(net.l2 > 0).cpu().numpy(),
+    return dict(a1=(net.a1() > 0).cpu().numpy(), a2=(net.a2() > 0).cpu().numpy(),
                 h=(net.l4 > 0).cpu().numpy())
 
 
@@ -58,11 +58,14 @@ def test_forward_layers_vs_oracle(pkg, cuda, A, B, T, R, first):
     a1 = torch.empty(N, 20, 20, 16, **f32); a2 = torch.empty(N, 2592, **f32)
     h = torch.empty(N, 256, **f32); lg = torch.empty(N, A, **f32)
     pr = torch.empty(N, A, **f32); v = torch.empty(N, **f32)
-    pkg._cabi.call("arl_forward", flat.data_ptr(), A, ring.data_ptr(), B, R, first, T,
-                   a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
+    fc_w = torch.empty(2592 * 256, **f32)
+    pkg._cabi.call("arl_forward", flat.data_ptr(), fc_w.data_ptr(), 1, A, ring.data_ptr(), B, R, first,
+                   T, a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
                    v.data_ptr(), pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
     a1 = pkg.network.decode_a1(a1)                                # device layout: split bf16, blocked
+    a2 = pkg.network.decode_split(a2, N, 2592)                    # one split block of the call's N rows
+    assert rel_err(pkg.network.decode_split(fc_w, 2592, 256).cpu(), params["l4_w"]) <= 1e-5
     logits, value, keep = a3c.forward(a3c.to_torch(params), ring_stacks(ring_np, first, T), keep=True)
     pi, _, _ = a3c.policy_terms(logits)
     errs = dict(a1=rel_err(a1.cpu(), keep["a1"]), a2=rel_err(a2.cpu(), keep["a2"]),
@@ -229,7 +232,7 @@ def test_backward_single_sample_and_zero_samples(pkg, cuda):
     net.grads.fill_(5.0)
     st = pkg._cabi.stream_ptr()
     P = pkg._cabi.ptr
-    assert lib.arl_backward(P(net.params), A, P(hist.ring), 0, hist.ring_slots, 0, 1, P(net.l1),
+    assert lib.arl_backward(P(net.params), P(net.fc_w), A, P(hist.ring), 0, hist.ring_slots, 0, 1, P(net.l1),
                             P(net.l2), P(net.l4), P(net.d_logits), P(net.d_value), P(net.d_l4),
                             P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), st) == 0
     torch.cuda.synchronize()
@@ -359,8 +362,8 @@ def test_full_size_properties_4096_envs_t5(pkg, cuda):
             hist.ring.copy_(ring_full[lo:lo + envs])
         hist.head = T + 3                                         # slots 0..T+3 = f_-3 .. f_T
         for t in range(T):
-            pkg._cabi.call("arl_forward", pkg._cabi.ptr(net.params), A, pkg._cabi.ptr(hist.ring),
-                           envs, hist.ring_slots, t, 1, *[pkg._cabi.ptr(x[t * envs:(t + 1) * envs])
+            pkg._cabi.call("arl_forward", pkg._cabi.ptr(net.params), pkg._cabi.ptr(net.fc_w), 1, A,
+                           pkg._cabi.ptr(hist.ring), envs, hist.ring_slots, t, 1, *[pkg._cabi.ptr(x[t * envs:(t + 1) * envs])
                                                           for x in (net.l1, net.l2, net.l4,
                                                                     net.policy_logits, net.policy,
                                                                     net.value)],
