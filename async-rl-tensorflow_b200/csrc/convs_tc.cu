@@ -119,7 +119,6 @@ __device__ __forceinline__ void stream_pixels(uint8_t* hi, uint8_t* lo, const fl
   }
 }
 
-using GridDy1 = PixelGrid<21, 441, 20, 20, 0, 4>;     // dy1 [N,400,16] on the conv1 X grid
 using GridDy2 = PixelGrid<10, 100, 9, 9, 0, 8>;       // dy2 [N,81,32] on the conv2 X2 grid
 using GridZ   = PixelGrid<11, 121, 9, 9, 1, 8>;       // dy2 zero-padded by one (transposed conv)
 
@@ -350,7 +349,8 @@ struct Conv1Fwd : tc::PolicyBase {
   // epilogue: lane = output pixel; limbs -> fp32 -> /255 + bias, relu -> bf16 hi/lo -> four 16-B
   // vectors straight into the a1s planes (no staging: 16 consecutive lanes write 256 contiguous B)
   static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t,
-                                                         const uint8_t* res, uint32_t taddr, int row) {
+                                                         const uint8_t* res, uint32_t taddr, int row,
+                                                         EpiPre&, EpiState&) {
     const float* sc = reinterpret_cast<const float*>(res + SCALE_OFF);
     float v[16];
     {
@@ -446,7 +446,7 @@ struct Conv2Fwd : tc::PolicyBase {
   // NHWC flatten (agent.py:231-232) = chunks (yp*9+xp)*4 .. +3 of the split-bf16 a2 block
   // [part][324 chunks][num_samples][8] that the fc256 kernels consume with cp.async.bulk
   static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t, const uint8_t*,
-                                                         uint32_t taddr, int row) {
+                                                         uint32_t taddr, int row, EpiPre&, EpiState&) {
     const int xr = t.mt * 128 + row, n = xr / GROWS;
     const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
     const bool ok = n < g.num_samples && yp < 9 && xp < 9;
@@ -475,10 +475,17 @@ struct Conv2DgradArgs {
   const float* params;
   const uint8_t* a1s;    // relu mask of conv1: sign of the hi plane of the split-bf16 output
   const float* dy2;      // [N, 81, 32]
-  float* dy1;            // [N, 400, 16]
+  uint8_t* dy1s;         // conv1 output gradient, split bf16 on the conv1 X grid ("dy1s", see below)
+  float* bias_partials;  // [grid * 8 epilogue warps][16]: column sums of dy1 (= the conv1 bias gradient)
   int64_t rows;          // 121 * num_samples
   int num_samples;
 };
+// dy1s: the gradient w.r.t. conv1's output is only ever the B operand of the conv1 weight-gradient
+// MMA (rows of the 21-wide X grid = the reduction index), so conv2 dgrad stores it the way that
+// kernel fetches it with cp.async.bulk:
+//   dy1s[part (hi, lo)][co group (2)][grid row n*441 + y*21 + x][8 channels]      (16-B vectors)
+// with the rows y = 20 / x = 20 (no conv1 output there) written as zeros: 28 224 B per sample.
+constexpr int kDy1sRows = 441;
 struct Conv2Dgrad : tc::PolicyBase {
   using Args = Conv2DgradArgs;
   static constexpr int GW = 11, GROWS = 121, TROWS = 140;
@@ -490,7 +497,7 @@ struct Conv2Dgrad : tc::PolicyBase {
   // tile of a tap, and lo follows hi), 16 k-chunk planes (tap*4 + co8)
   static constexpr int PLB = 129 * 16, RES_BYTES = 16 * PLB;
   static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 64, SEG = 32;   // 4 classes x 16 ch
-  static constexpr bool HAS_AUX = true, AUX_ROW_INVARIANT = false;
+  static constexpr bool CUSTOM_EPI = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
@@ -530,36 +537,68 @@ struct Conv2Dgrad : tc::PolicyBase {
       }
     }
   }
-  // row (yy, xx) on the 11-wide grid -> the 2x2 block of dy1 pixels (2yy+dy, 2xx+dx); segment dy =
-  // parity classes (dy,0),(dy,1) = two adjacent pixels = 32 contiguous floats
-  static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
+  // epilogue: lane = row (yy, xx) of the 11-wide grid = the 2x2 block of dy1 pixels (2yy+dy, 2xx+dx),
+  // accumulator columns cls*16 + c with cls = dy*2 + dx.  Per pixel and channel half: relu mask
+  // (sign of a1's hi part, prefetched before the accumulator wait), bias-gradient sums, bf16 split,
+  // one hi and one lo vector into dy1s.  Rows yy = 10 / xx = 10 write the zero rows y = 20 / x = 20.
+  // Lanes of a warp write 16-B vectors 32 B apart, the dx = 0/1 stores interleave: 8 lines each.
+  struct EpiPre { uint4 m[8]; };
+  struct EpiState { float b[16]; };
+  static __device__ __forceinline__ void epi_begin(EpiState& s) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s.b[c] = 0.f;
+  }
+  static __device__ __forceinline__ void epi_prefetch(const Args& g, const TileCoord& t, int row, EpiPre& pre) {
     const int pr = t.mt * 128 + row, n = pr / GROWS;
     const int q = pr - n * GROWS, yy = q / GW, xx = q - yy * GW;
-    if (n >= g.num_samples || yy >= 10 || xx >= 10) return nullptr;
-    return g.dy1 + (int64_t)n * ARL_A1_ELEMS + ((2 * yy) * 20 + 2 * xx) * 16;
+    const bool ok = n < g.num_samples && yy < 10 && xx < 10;
+    const uint8_t* p = g.a1s + (int64_t)n * kA1sSample + (yy * 10 + xx) * 16;     // plane = cls*2 + chalf
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pre.m[i] = ok ? __ldg(reinterpret_cast<const uint4*>(p + i * kA1sPlane)) : make_uint4(0u, 0u, 0u, 0u);
   }
-  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int dy) {
-    return dy * 20 * 16;
-  }
-  // relu mask = sign of a1's hi plane.  Row (yy,xx) covers pixels (2yy+dy, 2xx+dx): all four share
-  // q = yy*10 + xx, so one byte offset per row serves its loads; lane (dy, col) adds its plane:
-  // kc = (dy*2 + dx)*2 + chalf, and 8 bytes = 4 channels inside the 16-B vector.
-  static __device__ __forceinline__ int64_t row_aux(const Args& g, const TileCoord& t, int row) {
+  static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t, const uint8_t*,
+                                                         uint32_t taddr, int row, EpiPre& pre, EpiState& st) {
     const int pr = t.mt * 128 + row, n = pr / GROWS;
     const int q = pr - n * GROWS, yy = q / GW, xx = q - yy * GW;
-    return (int64_t)n * kA1sSample + (yy * 10 + xx) * 16;
+    const bool live = n < g.num_samples;
+    const int64_t R = (int64_t)g.num_samples * kDy1sRows;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int y = 2 * yy + (cls >> 1), x = 2 * xx + (cls & 1);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[8];
+        tc::tmem_ld8_sum(taddr + cls * 16 + half * 8, taddr + 64 + cls * 16 + half * 8, v);
+        if (!live || y > 20 || x > 20) continue;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (y < 20 && x < 20) {
+          const uint4 m = pre.m[cls * 2 + half];
+          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if ((int16_t)(w[i] & 0xFFFFu) <= 0) v[2 * i] = 0.f;        // bf16 > 0 <=> its bits as int16 > 0
+            if ((int32_t)w[i] < 0x10000) v[2 * i + 1] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) st.b[half * 8 + e] += v[e];
+          tc::split2(v[0], v[1], hi.x, lo.x);
+          tc::split2(v[2], v[3], hi.y, lo.y);
+          tc::split2(v[4], v[5], hi.z, lo.z);
+          tc::split2(v[6], v[7], hi.w, lo.w);
+        }
+        uint8_t* d = g.dy1s + ((int64_t)half * R + (int64_t)n * kDy1sRows + y * 21 + x) * 16;
+        *reinterpret_cast<uint4*>(d) = hi;
+        *reinterpret_cast<uint4*>(d + 2 * R * 16) = lo;
+      }
+    }
   }
-  static __device__ __forceinline__ float4 aux_load(const Args& g, const TileCoord&, const float*, int col,
-                                                    int64_t row_off) {
-    // col = dy*32 + dx*16 + channel (a multiple of 4)
-    const int kc = (col >> 4) * 2 + ((col >> 3) & 1);
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(g.a1s + row_off + kc * kA1sPlane + (col & 7) * 2));
-    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
-                       __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
-  }
-  static __device__ __forceinline__ float4 finish(const Args&, float4 v, float4 m) {
-    return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f,
-                       m.w > 0.f ? v.w : 0.f);
+  static __device__ __forceinline__ void epi_end(const Args& g, EpiState& st, int warp, int lane) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float s = warp_sum(st.b[c]);
+      if (lane == 0) g.bias_partials[((size_t)blockIdx.x * 8 + warp) * 16 + c] = s;
+    }
   }
 };
 
@@ -670,19 +709,23 @@ struct Conv2Wgrad : tc::PolicyBase {
 
 struct Conv1WgradArgs {
   RingGeo geo;
-  const float* dy1;
+  const uint8_t* dy1s;   // split bf16 on the X grid, written by conv2 dgrad (see dy1s above)
   float* partials;       // [items][4096]
-  float* bias_partials;  // [items * PROD_WARPS][16]  column sums of dy1 (= db1), per producer warp
   int64_t rows;          // 441 * num_samples
   int num_samples, k_chunk, items;
 };
 struct Conv1Wgrad : tc::PolicyBase {
   using Args = Conv1WgradArgs;
-  struct Prod { float acc[4]; };    // running column sums of dy1 (bias gradient)
-  static constexpr int GW = 21, GROWS = 441, TROWS = 150;
+  // dW1[(a,b) tap][ch][co] = sum_P X[P + a*21 + b][ch] * dy1[P][co] over the rows P of the X grid.
+  // Tap b is folded into M (a second copy of the X image shifted by one row), tap a into N (a
+  // second copy of the dy1 image shifted BACK by 21 rows: sum_Q X[Q + b][ch] * dy1[Q - 21][co]),
+  // so one N = 64 MMA per 16 rows covers all four taps and the wide X tile is read from shared
+  // memory once.  The dy1 images arrive by cp.async.bulk from dy1s (8 copies of 2 KB per stage).
+  static constexpr int GW = 21, TROWS = 129;
   static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // exact bf16: hi only
-  static constexpr int PLB = 132 * 16, B_IMG = 2 * PLB;            // dy1z: 2 co groups
-  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = A_IMG + 2 * B_IMG, RES_BYTES = 0;
+  static constexpr int PLB = 128 * 16, B_IMG = 2 * PLB;            // dy1: 2 co groups
+  // stage = [A | dy hi | dy lo | dy' hi | dy' lo]  (dy' = shifted copy = tap a = 1)
+  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = A_IMG + 4 * B_IMG, RES_BYTES = 0;
   // accumulator columns: a*32 + part*16 + co
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 16, SEG = 16;
   static __device__ __forceinline__ int acc_col(int c) { return (c >> 4) * 32 + (c & 15); }
@@ -694,36 +737,46 @@ struct Conv1Wgrad : tc::PolicyBase {
     return (t.k_end - t.k_begin + 127) / 128;
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
-  static __device__ __forceinline__ void prod_begin(Prod& ps) {
-    ps.acc[0] = ps.acc[1] = ps.acc[2] = ps.acc[3] = 0.f;
-  }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int gsize, Prod& ps) {
+                                                    uint8_t* st, int glane, int gsize, Prod&) {
     const int p0 = t.k_begin + s * 128;
-    uint8_t* a_img = st, *b_hi = st + A_IMG, *b_lo = b_hi + B_IMG;
-    // A: X rows p0 .. p0+149 (exact in bf16: one image); planes 8..15 = shifted copy (tap b = 1)
-    stream_x1<TROWS, PLA, 5, true>(a_img, g.geo, p0, g.num_samples, glane, gsize);
-    // B: dy1 on the 21-wide grid, zero at y'=20 / x'=20 and outside [k_begin, k_end)
-    stream_pixels<GridDy1, 4, 128, PLB, 6, true>(b_hi, b_lo, g.dy1, p0, t.k_end, g.num_samples, glane,
-                                                 gsize, ps.acc);
+    // A: X rows p0 .. p0+128 (exact in bf16: one image); planes 8..15 = shifted copy (tap b = 1)
+    stream_x1<TROWS, PLA, 5, true>(st, g.geo, p0, g.num_samples, glane, gsize);
+    // B: image row r of planes 0..3 = dy1 row p0 + r, of planes 4..7 = dy1 row p0 + r - 21; rows
+    // with p0 + r >= k_end (the next work item's) and rows before the first sample are zero
+    const int valid = t.k_end - p0, lead = p0 < GW ? GW - p0 : 0;
+    if (valid < 128 || lead > 0) {
+      for (int i = glane; i < 8 * 128; i += gsize) {
+        const int plane = i >> 7, r = i & 127;
+        if (r >= valid || (plane >= 4 && r < lead))
+          *reinterpret_cast<uint4*>(st + A_IMG + plane * PLB + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   }
-  static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
-                                                  int lane) {
-    bias_partial_store<4>(g.bias_partials + ((size_t)t.ks * PROD_WARPS + pw) * 16, ps.acc, lane);
+  // lanes 0..7 of the stage's group own one dy1 plane each: plane = copy*4 + part*2 + co group
+  static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
+                                                    int glane, int, uint64_t* full) {
+    if (glane >= 8) return false;
+    const int p0 = t.k_begin + s * 128;
+    int cnt = t.k_end - p0 < 128 ? t.k_end - p0 : 128, src = p0, dst = 0;
+    if (glane >= 4) {
+      src = p0 - GW;
+      if (src < 0) { dst = -src; cnt -= dst; src = 0; }
+    }
+    const uint32_t bytes = cnt > 0 ? (uint32_t)cnt * 16u : 0u;
+    mbar_expect_tx(full, bytes);
+    if (cnt > 0)
+      bulk_g2s(st + A_IMG + glane * PLB + dst * 16, g.dy1s + ((int64_t)(glane & 3) * g.rows + src) * 16, bytes, full);
+    return true;
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(32, true, true);     // x . [dy_hi | dy_lo]
-    const uint32_t a_img = st, b_hi = st + A_IMG;                  // b_lo = b_hi + B_IMG
+    constexpr uint32_t idesc = tc::make_idesc(64, true, true);     // x . [dy_hi | dy_lo | dy'_hi | dy'_lo]
+    const uint32_t a_img = st, b_hi = st + A_IMG;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-#pragma unroll
-      for (int k16 = 0; k16 < 8; ++k16) {
-        const uint64_t da = tc::make_sdesc(a_img + (a * GW + k16 * 16) * 16, 128, PLA);
-        tc::umma_f16(d + a * 32, da, tc::make_sdesc(b_hi + k16 * 256, 128, PLB), idesc,
-                     (s | k16) != 0 ? 1u : 0u);
-      }
-    }
+    for (int k16 = 0; k16 < 8; ++k16)
+      tc::umma_f16(d, tc::make_sdesc(a_img + k16 * 256, 128, PLA), tc::make_sdesc(b_hi + k16 * 256, 128, PLB),
+                   idesc, (s | k16) != 0 ? 1u : 0u);
   }
   // row = b*64 + ch, ch = (cin*4 + i)*4 + j ; segment a = 16 co of tap (kh = 4a+i, kw = 4b+j)
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
@@ -795,24 +848,20 @@ extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float*
   const int64_t N = (int64_t)num_envs * steps;
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) {
-    ARL_CUDA(cudaMemsetAsync(grads, 0, (4096 + 16) * sizeof(float), st));
+    ARL_CUDA(cudaMemsetAsync(grads, 0, 4096 * sizeof(float), st));
     return ARL_OK;
   }
   ARL_REQUIRE(N * 441 < (1LL << 31) - 256, "arl_conv1_backward: too many samples");
   Conv1WgradArgs g;
   g.geo = {ring, num_envs, ring_slots, first_slot};
-  g.dy1 = d_a1;
+  g.dy1s = reinterpret_cast<const uint8_t*>(d_a1);
   g.partials = (float*)workspace;
   g.rows = N * 441;
   g.num_samples = (int)N;
   g.items = split_rows(g.rows, num_sms(), &g.k_chunk);
-  g.bias_partials = (float*)workspace + (size_t)g.items * 4096;
   int rc = tc::launch<Conv1Wgrad>(g, g.items, st);
   if (rc) return rc;
-  rc = reduce_partials(g.partials, grads, g.items, 4096, st);                    // l1_w
-  if (rc) return rc;
-  // l1_b = column sums of d_a1, accumulated by the wgrad producers while they stream d_a1
-  return reduce_partials(g.bias_partials, grads + 4096, g.items * Conv1Wgrad::PROD_WARPS, 16, st);
+  return reduce_partials(g.partials, grads, g.items, 4096, st);                  // l1_w
 }
 
 extern "C" int arl_conv2_backward(const float* params, const float* a1, const float* d_a2,
@@ -827,7 +876,7 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
   cudaStream_t st = (cudaStream_t)stream;
   float* g2 = grads + 4096 + 16;                                                 // l2_w | l2_b
   if (num_samples == 0) {
-    ARL_CUDA(cudaMemsetAsync(g2, 0, (8192 + 32) * sizeof(float), st));
+    ARL_CUDA(cudaMemsetAsync(grads + 4096, 0, (16 + 8192 + 32) * sizeof(float), st));   // l1_b | l2_w | l2_b
     return ARL_OK;
   }
   Conv2WgradArgs w;
@@ -845,6 +894,12 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
   // l2_b = column sums of d_a2, accumulated by the wgrad producers while they stream d_a2
   rc = reduce_partials(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, st);
   if (rc) return rc;
-  Conv2DgradArgs d{params, reinterpret_cast<const uint8_t*>(a1), d_a2, d_a1, num_samples * 121, (int)num_samples};
-  return tc::launch<Conv2Dgrad>(d, (int)((d.rows + 127) / 128), st);
+  // dgrad; its epilogue also sums the columns of d_a1 = the conv1 bias gradient l1_b
+  float* db1 = (float*)workspace + (size_t)w.items * (8192 + Conv2Wgrad::PROD_WARPS * 32);
+  Conv2DgradArgs d{params, reinterpret_cast<const uint8_t*>(a1), d_a2, reinterpret_cast<uint8_t*>(d_a1), db1,
+                   num_samples * 121, (int)num_samples};
+  const int items = (int)((d.rows + 127) / 128);
+  rc = tc::launch<Conv2Dgrad>(d, items, st);
+  if (rc) return rc;
+  return reduce_partials(db1, grads + 4096, (items < num_sms() ? items : num_sms()) * 8, 16, st);
 }

@@ -249,10 +249,22 @@ struct TileCoord {
 // column sums of the operand a producer streams through its registers anyway = a bias gradient).
 struct PolicyBase {
   static constexpr int EPI_SETS = 1;
-  static constexpr bool CUSTOM_EPI = false;    // policy provides custom_epilogue(g, tc, res, taddr, row)
-  template <class Args>
+  // policy provides custom_epilogue(g, tc, res, taddr, row, pre, state): reads its accumulator row
+  // (lane = row) and writes its output itself.  EpiPre = registers filled by epi_prefetch BEFORE the
+  // accumulator is waited for (operands the finishing op needs from HBM); EpiState = per-thread
+  // state that lives across the tiles of the CTA (epi_begin / epi_end), e.g. running column sums
+  static constexpr bool CUSTOM_EPI = false;
+  struct EpiPre {};
+  struct EpiState {};
+  template <class Args, class Pre>
+  static __device__ __forceinline__ void epi_prefetch(const Args&, const TileCoord&, int, Pre&) {}
+  template <class St>
+  static __device__ __forceinline__ void epi_begin(St&) {}
+  template <class Args, class St>
+  static __device__ __forceinline__ void epi_end(const Args&, St&, int, int) {}
+  template <class Args, class Pre, class St>
   static __device__ __forceinline__ void custom_epilogue(const Args&, const TileCoord&, const uint8_t*,
-                                                         uint32_t, int) {}
+                                                         uint32_t, int, Pre&, St&) {}
   template <class Args>
   static __device__ __forceinline__ float* row_ptr(const Args&, const TileCoord&, int) { return nullptr; }
   static constexpr bool ACC_LIMBS3 = false;    // accumulators are 3 s32 limb sets (int8 path)
@@ -432,16 +444,20 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     constexpr int NI = 32 / RPI;
     const int c4 = lane % LPR, rsub = lane / LPR, quad = warp & 3, set = warp >> 2;
     int k = 0;
+    typename P::EpiState est;
+    P::epi_begin(est);
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
       if (P::EPI_SETS > 1 && (k % P::EPI_SETS) != set) continue;
       const uint32_t acc = k % NUM_ACC, acc_phase = (k / NUM_ACC) & 1;
       const TileCoord tc = P::coord(g, item);
       if constexpr (P::CUSTOM_EPI) {
         // the policy reads its accumulator row (lane = row) and writes its output itself
+        typename P::EpiPre pre;
+        P::epi_prefetch(g, tc, quad * 32 + lane, pre);
         mbar_wait_backoff<64>(&tfull[acc], acc_phase);
         tc_fence_after();
         P::custom_epilogue(g, tc, res, tmem_base + ((uint32_t)(quad * 32) << 16) + acc * P::ACC_COLS,
-                           quad * 32 + lane);
+                           quad * 32 + lane, pre, est);
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
         continue;
@@ -519,6 +535,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
     }
+    P::epi_end(g, est, warp, lane);
   }
 
   tc_fence_before();

@@ -35,6 +35,12 @@
  *       fc_w_split (2592*256 floats): l4_w as one block of 2592 rows, 32 chunks, written by
  *           arl_fc_prepare -- must be refreshed whenever l4_w changes.
  *     src/network.py:decode_split turns a block back into f32 [rows][cols].
+ *   - d_a1, the gradient w.r.t. conv1's output, is the reduction operand of the conv1 weight
+ *     gradient: split bf16 on conv1's 21x21 space-to-depth grid,
+ *     [part (hi, lo)][channel group (2)][row n*441 + y*21 + x][8 channels], rows y = 20 / x = 20
+ *     zero: ARL_DA1_ELEMS = 7056 floats per sample.  arl_conv2_backward writes it (and, since it
+ *     has the values in registers, the conv1 bias gradient l1_b); arl_conv1_backward reads it.
+ *     src/network.py:decode_da1 turns it into f32 [N,20,20,16].
  *   - parameters / gradients / RMSProp slots are flat f32 buffers in the
  *     reference's own variable order and layouts (see arl_param_layout).
  */
@@ -54,6 +60,7 @@ extern "C" {
 #define ARL_HISTORY 4            /* config.py:22 history_length                  */
 #define ARL_A1_ELEMS 6400        /* 20*20*16  conv1 output per sample            */
 #define ARL_A2_ELEMS 2592        /* 9*9*32    conv2 output per sample (flatten)  */
+#define ARL_DA1_ELEMS 7056       /* 21*21*16  floats of d_a1 per sample (grid)   */
 #define ARL_FC 256               /* agent.py:251 / network.py:51                 */
 #define ARL_NUM_TENSORS 10       /* l1_w l1_b l2_w l2_b l4_w l4_b p_w p_b q_w q_b */
 #define ARL_MAX_ACTIONS 32
@@ -196,7 +203,8 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
 /* ---- backward: agent.py:317 compute_gradients ---------------------------------------
  * Accumulation over the T steps of Algorithm 3 is the reduction over samples inside the
  * weight-gradient kernels.  grads is the flat buffer (overwritten).  Scratch buffers are
- * caller-owned: d_h [N,256] (a split block, see the top of this file), d_a2 [N,2592], d_a1 [N,6400],
+ * caller-owned: d_h [N,256] (a split block, see the top of this file), d_a2 [N,2592],
+ * d_a1 [N,ARL_DA1_ELEMS] (grid layout, see the top of this file),
  * workspace >= arl_backward_workspace_bytes.  a2 = the rollout's conv2 outputs as a sequence of
  * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);
  * fc_w_split must hold arl_fc_prepare of the parameters the forward used. */
@@ -207,8 +215,10 @@ ARL_API int arl_heads_backward(const float* params, int action_size, const float
 ARL_API int arl_fc_backward(const float* fc_w_split, const float* a2, int64_t a2_block_rows,
                     const float* d_h, float* d_a2, float* grads, void* workspace,
                     int64_t num_samples, void* stream);
+/* l2_w, l2_b, d_a1 and l1_b (the column sums of d_a1). */
 ARL_API int arl_conv2_backward(const float* params, const float* a1, const float* d_a2, float* d_a1,
                        float* grads, void* workspace, int64_t num_samples, void* stream);
+/* l1_w only (l1_b comes from arl_conv2_backward). */
 ARL_API int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads, void* workspace,
                        int num_envs, int ring_slots, int first_slot, int steps, void* stream);
 ARL_API int arl_backward(const float* params, const float* fc_w_split, int action_size,

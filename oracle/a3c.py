@@ -108,7 +108,8 @@ def forward(p, s_nhwc, keep=False, masks=None):
     logits = h @ p["p_w"] + p["p_b"]
     value = (h @ p["q_w"] + p["q_b"]).reshape(-1)
     if keep:
-        return logits, value, dict(a1=a1.permute(0, 2, 3, 1), a2=flat, h=h)
+        # _a1 is the tensor the graph continues from (NCHW): the one whose .grad is d loss / d a1
+        return logits, value, dict(a1=a1.permute(0, 2, 3, 1), a2=flat, h=h, _a1=a1)
     return logits, value
 
 
@@ -176,7 +177,9 @@ def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=tor
     stacks [N,84,84,4] (N = T*B, t-major), actions [N], R [N].
     ``num_envs`` = B of the mean (global env count); None -> pure sum."""
     p = to_torch(params_np, dtype, requires_grad=True)
-    logits, value = forward(p, stacks, masks=masks)
+    logits, value, keep = forward(p, stacks, masks=masks, keep=True)
+    for k in ("_a1", "a2", "h"):
+        keep[k].retain_grad()
     Rt = torch.as_tensor(np.asarray(R), dtype=dtype)
     at = torch.as_tensor(np.asarray(actions))
     total, pl, vl = loss_per_sample(logits, value, at, Rt, beta)
@@ -187,6 +190,12 @@ def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=tor
     aux = dict(logits=logits.detach().numpy(), value=value.detach().numpy(),
                loss=float(loss.detach()), policy_loss=pl.detach().numpy(),
                value_loss=vl.detach().numpy())
+    # gradients w.r.t. the PRE-relu layer outputs (what the backward kernels hand from layer to
+    # layer): d loss / d post-relu activation, times the activation pattern
+    for name, k in (("d_a1", "_a1"), ("d_a2", "a2"), ("d_h", "h")):
+        act, g = keep[k].detach(), keep[k].grad
+        d = (g * (act > 0).to(g.dtype)).numpy()
+        aux[name] = d.transpose(0, 2, 3, 1) if name == "d_a1" else d
     return grads, aux
 
 

@@ -194,6 +194,14 @@ def test_backward_gradients_vs_oracle(pkg, cuda, A, B, T):
     errs = {k: rel_err(net.g[k].cpu(), grads[k]) for k in a3c.PARAM_NAMES}
     print("grad rel-err", errs)
     assert max(errs.values()) <= REL_TOL, errs
+    # the gradients handed from layer to layer, decoded from their device layouts
+    N = T * B
+    ierrs = dict(d_h=rel_err(net.d_h().cpu(), aux["d_h"]), d_a2=rel_err(net.d_l2.cpu(), aux["d_a2"]),
+                 d_a1=rel_err(pkg.network.decode_da1(net.d_l1, N).cpu(), aux["d_a1"]))
+    print("layer-gradient rel-err", ierrs)
+    assert max(ierrs.values()) <= REL_TOL, ierrs
+    raw = net.d_l1.reshape(-1)[:N * 7056].view(torch.bfloat16).reshape(2, 2, N, 21, 21, 8)
+    assert float(raw[:, :, :, 20].abs().max()) == 0.0 and float(raw[:, :, :, :, 20].abs().max()) == 0.0
     # (2) free oracle: a pre-activation within rounding distance (~1e-5 relative, bf16x3 operands)
     # of 0 may flip one relu and with it one gradient column; with only T*B samples in the sums
     # one flip is visible, so this comparison is reported in the 2-norm and gated at 1e-2
