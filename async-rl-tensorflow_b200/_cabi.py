@@ -26,7 +26,7 @@ SIGNATURES = {
     "arl_history_reset": [c_vp, c_int, c_int, c_vp],
     "arl_conv1_forward": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_conv2_forward": [c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_fc_prepare": [c_vp, c_vp, c_vp],
+    "arl_prepare_weights": [c_vp, c_vp, c_vp],
     "arl_fc_forward": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_heads_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_forward": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
@@ -51,6 +51,7 @@ OTHER = {
     "arl_last_error": ([], ctypes.c_char_p),
     "arl_version": ([], c_int),
     "arl_backward_workspace_bytes": ([c_int], c_i64),
+    "arl_prepared_floats": ([], c_i64),
     "arl_launch_count": ([c_int], c_i64),
 }
 EXPORTS = tuple(SIGNATURES) + tuple(OTHER)
@@ -130,6 +131,11 @@ def param_layout(action_size):
 def launch_count(reset=False):
     """Kernels launched by the library so far in this process."""
     return int(load().arl_launch_count(1 if reset else 0))
+
+
+def prepared_floats():
+    """Size (floats) of the prepared-weights buffer arl_prepare_weights fills."""
+    return int(load().arl_prepared_floats())
 
 
 def workspace_bytes(action_size):

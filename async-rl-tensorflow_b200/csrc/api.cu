@@ -80,24 +80,24 @@ extern "C" int64_t arl_backward_workspace_bytes(int action_size) {
   return (int64_t)8 * ARL_A2_ELEMS * ARL_FC * sizeof(float) + (1 << 20);
 }
 
-extern "C" int arl_forward(const float* params, float* fc_w_split, int refresh_fc_w, int action_size,
+extern "C" int arl_forward(const float* params, float* prepared, int refresh_prepared, int action_size,
                            const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                            float* a1, float* a2, float* h, float* logits, float* probs, float* value,
                            void* stream) {
   const int64_t N = (int64_t)num_envs * steps;
   int rc = ARL_OK;
-  if (refresh_fc_w) rc = arl_fc_prepare(params, fc_w_split, stream);
+  if (refresh_prepared) rc = arl_prepare_weights(params, prepared, stream);
   if (rc) return rc;
-  rc = arl_conv1_forward(params, ring, a1, num_envs, ring_slots, first_slot, steps, stream);
+  rc = arl_conv1_forward(prepared, ring, a1, num_envs, ring_slots, first_slot, steps, stream);
   if (rc) return rc;
-  rc = arl_conv2_forward(params, a1, a2, N, stream);
+  rc = arl_conv2_forward(prepared, a1, a2, N, stream);
   if (rc) return rc;
-  rc = arl_fc_forward(params, fc_w_split, a2, h, N, stream);
+  rc = arl_fc_forward(params, prepared, a2, h, N, stream);
   if (rc) return rc;
   return arl_heads_forward(params, action_size, h, logits, probs, value, N, stream);
 }
 
-extern "C" int arl_backward(const float* params, const float* fc_w_split, int action_size,
+extern "C" int arl_backward(const float* params, const float* prepared, int action_size,
                             const uint8_t* ring, int num_envs, int ring_slots, int first_slot,
                             int steps, const float* a1,
                             const float* a2, const float* h, const float* dlogits,
@@ -107,9 +107,9 @@ extern "C" int arl_backward(const float* params, const float* fc_w_split, int ac
   int rc = arl_heads_backward(params, action_size, h, dlogits, dvalue, d_h, grads, workspace, N,
                               stream);
   if (rc) return rc;
-  rc = arl_fc_backward(fc_w_split, a2, num_envs, d_h, d_a2, grads, workspace, N, stream);
+  rc = arl_fc_backward(prepared, a2, num_envs, d_h, d_a2, grads, workspace, N, stream);
   if (rc) return rc;
-  rc = arl_conv2_backward(params, a1, d_a2, d_a1, grads, workspace, N, stream);
+  rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, stream);
   if (rc) return rc;
   return arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps,
                             stream);

@@ -52,6 +52,18 @@ inline ParamLayout param_layout(int A) {
 
 constexpr int kPlane = ARL_SCREEN * ARL_SCREEN;  // 7056 bytes, 441 x 16 B
 
+// "prepared" weights (arl_prepare_weights): the operand images the tensor-core kernels keep
+// resident, built once per parameter change instead of in every kernel prologue.  Byte offsets:
+constexpr int64_t kPrepFcW = 0;                                   // l4_w as a split block (fc.cu)
+constexpr int64_t kPrepFcWBytes = (int64_t)ARL_A2_ELEMS * ARL_FC * 4;
+constexpr int64_t kPrepW1 = kPrepFcW + kPrepFcWBytes;             // conv1 fwd: s8 limbs | scales | bias
+constexpr int64_t kPrepW1Bytes = 12800;
+constexpr int64_t kPrepW2F = kPrepW1 + kPrepW1Bytes;              // conv2 fwd: [hi | lo] image | bias
+constexpr int64_t kPrepW2FBytes = 33408;
+constexpr int64_t kPrepW2D = kPrepW2F + kPrepW2FBytes;            // conv2 dgrad: transposed [hi | lo] image
+constexpr int64_t kPrepW2DBytes = 33024;
+constexpr int64_t kPrepBytes = kPrepW2D + kPrepW2DBytes;
+
 // ---- small device helpers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

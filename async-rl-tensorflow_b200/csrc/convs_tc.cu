@@ -122,6 +122,15 @@ __device__ __forceinline__ void stream_pixels(uint8_t* hi, uint8_t* lo, const fl
 using GridDy2 = PixelGrid<10, 100, 9, 9, 0, 8>;       // dy2 [N,81,32] on the conv2 X2 grid
 using GridZ   = PixelGrid<11, 121, 9, 9, 1, 8>;       // dy2 zero-padded by one (transposed conv)
 
+// resident operand image: built once per parameter change by arl_prepare_weights (build_image of
+// the policy), copied into shared memory by the producer threads in the kernel prologue
+template <int BYTES>
+__device__ __forceinline__ void copy_image(uint8_t* res, const uint8_t* __restrict__ img, int ptid, int nthr) {
+  static_assert(BYTES % 16 == 0, "image size");
+  for (int i = ptid; i < BYTES / 16; i += nthr)
+    reinterpret_cast<uint4*>(res)[i] = __ldg(reinterpret_cast<const uint4*>(img) + i);
+}
+
 // ---- conv1 A operand: space-to-depth rows of the u8 ring ---------------------------------------
 // The ring stores every 84x84 plane in 4x4 blocks (K1 writes it that way): the 16 bytes at
 // plane + q*16 are block q = y'*21 + x' = frame rows 4y'..4y'+3, columns 4x'..4x'+3 = the 16
@@ -230,7 +239,7 @@ __device__ __forceinline__ void a1s_zero_tail(uint8_t* st, int xr0, int num_samp
 
 // =================================== conv1 forward ============================================
 struct Conv1FwdArgs {
-  const float* params;
+  const uint8_t* w_img;  // prepared: s8 limb image of l1_w | 3 limb scales | l1_b
   RingGeo geo;
   uint8_t* a1s;          // split-bf16 blocked output (see a1s above), 25 600 B per sample
   int64_t rows;          // 441 * num_samples (grid rows)
@@ -252,7 +261,8 @@ struct Conv1Fwd : tc::PolicyBase {
   static constexpr int EPI_SETS = 2, PROD_WARPS = 8, STAGES = 8, STAGE_BYTES = 4 * PL;   // u8: 4 planes
   // resident W1 image (s8): rows = limb*16 + co (N = 48), 16 k-chunk planes (tap*4 + c); then
   // the three limb scales
-  static constexpr int PLB = 49 * 16, B_IMG = 16 * PLB, SCALE_OFF = B_IMG, RES_BYTES = B_IMG + 16;
+  static constexpr int PLB = 49 * 16, B_IMG = 16 * PLB, SCALE_OFF = B_IMG, BIAS_OFF = B_IMG + 16;
+  static constexpr int RES_BYTES = B_IMG + 16 + 64;
   static constexpr int ACC_COLS = 64, OUT_COLS = 16, LO_DELTA = 16, SEG = 16;
   static constexpr bool CUSTOM_EPI = true, ACC_LIMBS3 = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
@@ -260,7 +270,12 @@ struct Conv1Fwd : tc::PolicyBase {
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
   static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
-    // (1) s = max |w1| over the tensor, by all producer threads (named barrier 1)
+    copy_image<RES_BYTES>(res, g.w_img, ptid, nthr);
+  }
+  // (arl_prepare_weights) params = the flat parameter buffer; all nthr threads of the CTA take part
+  static __device__ __forceinline__ void build_image(const float* params, uint8_t* res, int ptid, int nthr) {
+    struct { const float* params; } g{params};
+    // (1) s = max |w1| over the tensor, by all threads (named barrier 1)
     uint32_t* smax = reinterpret_cast<uint32_t*>(res + SCALE_OFF + 12);
     if (ptid == 0) *smax = 0u;
     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
@@ -293,6 +308,7 @@ struct Conv1Fwd : tc::PolicyBase {
       *reinterpret_cast<uint4*>(d + 16 * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
       *reinterpret_cast<uint4*>(d + 32 * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
     }
+    if (ptid < 16) reinterpret_cast<float*>(res + BIAS_OFF)[ptid] = g.params[4096 + ptid];
   }
   // rows of the window that belong to no sample (only in the last tile) are zero-filled here
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
@@ -363,11 +379,11 @@ struct Conv1Fwd : tc::PolicyBase {
     const int xr = t.mt * 128 + row, n = xr / GROWS;
     const int q = xr - n * GROWS, y = q / GW, x = q - y * GW;
     if (n >= g.num_samples || y >= 20 || x >= 20) return;
-    const float* bias = g.params + 4096;
+    const float2* bias = reinterpret_cast<const float2*>(res + BIAS_OFF);
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(bias) + e);
+      const float2 bb = bias[e];
       const float o0 = fmaxf(fmaf(v[2 * e], 1.0f / 255.0f, bb.x), 0.f);
       const float o1 = fmaxf(fmaf(v[2 * e + 1], 1.0f / 255.0f, bb.y), 0.f);
       tc::split2(o0, o1, hi[e], lo[e]);
@@ -382,7 +398,7 @@ struct Conv1Fwd : tc::PolicyBase {
 
 // =================================== conv2 forward ============================================
 struct Conv2FwdArgs {
-  const float* params;
+  const uint8_t* w_img;  // prepared: [hi | lo] image of l2_w | l2_b
   const uint8_t* a1s;    // split-bf16 blocked conv1 output
   uint8_t* a2s;          // split-bf16 chunked output, one block of num_samples rows (gemm_tc.cuh SplitMat)
   int64_t rows;          // 100 * num_samples
@@ -396,7 +412,7 @@ struct Conv2Fwd : tc::PolicyBase {
   // lanes 0..15 own one (part, kc) plane each; two epilogue sets
   static constexpr int EPI_SETS = 2, PROD_WARPS = 4, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
   // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
-  static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, RES_BYTES = B_IMG;
+  static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, BIAS_OFF = B_IMG, RES_BYTES = B_IMG + 128;
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
   static constexpr bool CUSTOM_EPI = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
@@ -404,7 +420,11 @@ struct Conv2Fwd : tc::PolicyBase {
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
   static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
-    const float* w2 = g.params + 4112;
+    copy_image<RES_BYTES>(res, g.w_img, ptid, nthr);
+  }
+  static __device__ __forceinline__ void build_image(const float* params, uint8_t* res, int ptid, int nthr) {
+    const float* w2 = params + 4112;
+    if (ptid < 32) reinterpret_cast<float*>(res + BIAS_OFF)[ptid] = params[4112 + 8192 + ptid];
     for (int ch = ptid; ch < 32 * 32; ch += nthr) {
       const int co = ch & 31, kc = ch >> 5;                    // kc = tap*8 + (i*2+j)*2 + chalf
       const int tap = kc >> 3, ij = (kc >> 1) & 3, chalf = kc & 1;
@@ -445,12 +465,12 @@ struct Conv2Fwd : tc::PolicyBase {
   // epilogue: lane = output pixel (n, yp, xp); its 32 channels = features (yp*9+xp)*32 .. +31 of the
   // NHWC flatten (agent.py:231-232) = chunks (yp*9+xp)*4 .. +3 of the split-bf16 a2 block
   // [part][324 chunks][num_samples][8] that the fc256 kernels consume with cp.async.bulk
-  static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t, const uint8_t*,
+  static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t, const uint8_t* res,
                                                          uint32_t taddr, int row, EpiPre&, EpiState&) {
     const int xr = t.mt * 128 + row, n = xr / GROWS;
     const int q = xr - n * GROWS, yp = q / GW, xp = q - yp * GW;
     const bool ok = n < g.num_samples && yp < 9 && xp < 9;
-    const float* bias = g.params + 4112 + 8192;
+    const float4* bias = reinterpret_cast<const float4*>(res + BIAS_OFF);
     const int64_t plane = (int64_t)g.num_samples * 16, part = 324 * plane;
     uint8_t* d = g.a2s + (int64_t)((yp * 9 + xp) * 4) * plane + (int64_t)n * 16;
 #pragma unroll
@@ -458,7 +478,7 @@ struct Conv2Fwd : tc::PolicyBase {
       float v[8];
       tc::tmem_ld8_sum(taddr + c8 * 8, taddr + 32 + c8 * 8, v);          // x_hi.w_hi + x_lo.w_hi, x_hi.w_lo
       if (!ok) continue;
-      const float4 b0 = tc::ldg4(bias + c8 * 8), b1 = tc::ldg4(bias + c8 * 8 + 4);
+      const float4 b0 = bias[c8 * 2], b1 = bias[c8 * 2 + 1];
       uint4 h, l;
       tc::split2(fmaxf(v[0] + b0.x, 0.f), fmaxf(v[1] + b0.y, 0.f), h.x, l.x);
       tc::split2(fmaxf(v[2] + b0.z, 0.f), fmaxf(v[3] + b0.w, 0.f), h.y, l.y);
@@ -472,7 +492,7 @@ struct Conv2Fwd : tc::PolicyBase {
 
 // =================================== conv2 input gradient =====================================
 struct Conv2DgradArgs {
-  const float* params;
+  const uint8_t* w_img;  // prepared: transposed [hi | lo] image of l2_w
   const uint8_t* a1s;    // relu mask of conv1: sign of the hi plane of the split-bf16 output
   const float* dy2;      // [N, 81, 32]
   uint8_t* dy1s;         // conv1 output gradient, split bf16 on the conv1 X grid ("dy1s", see below)
@@ -503,7 +523,10 @@ struct Conv2Dgrad : tc::PolicyBase {
   static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
   static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
-    const float* w2 = g.params + 4112;
+    copy_image<RES_BYTES>(res, g.w_img, ptid, nthr);
+  }
+  static __device__ __forceinline__ void build_image(const float* params, uint8_t* res, int ptid, int nthr) {
+    const float* w2 = params + 4112;
     for (int ch = ptid; ch < 4 * 16 * 16; ch += nthr) {
       const int c = ch & 15, kc = (ch >> 4) & 15, cls = ch >> 8;   // kc = tap*4 + co8
       const int tap = kc >> 2, co8 = kc & 3;
@@ -793,6 +816,29 @@ struct Conv1Wgrad : tc::PolicyBase {
   }
 };
 
+// arl_prepare_weights: CTA 0 / 1 / 2 builds the resident image of conv1 fwd / conv2 fwd / conv2 dgrad
+// in shared memory (the same code the kernels used to run in their prologues) and writes it out
+__global__ void __launch_bounds__(256) build_images_kernel(const float* __restrict__ params, uint8_t* prepared) {
+  extern __shared__ __align__(128) uint8_t img[];
+  const int tid = threadIdx.x;
+  int bytes = 0;
+  uint8_t* out = prepared;
+  if (blockIdx.x == 0) {
+    Conv1Fwd::build_image(params, img, tid, 256);
+    bytes = Conv1Fwd::RES_BYTES; out += kPrepW1;
+  } else if (blockIdx.x == 1) {
+    Conv2Fwd::build_image(params, img, tid, 256);
+    bytes = Conv2Fwd::RES_BYTES; out += kPrepW2F;
+  } else {
+    Conv2Dgrad::build_image(params, img, tid, 256);
+    bytes = Conv2Dgrad::RES_BYTES; out += kPrepW2D;
+  }
+  __syncthreads();
+  for (int i = tid; i < bytes / 16; i += 256) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(img)[i];
+}
+static_assert(Conv1Fwd::RES_BYTES <= kPrepW1Bytes && Conv2Fwd::RES_BYTES <= kPrepW2FBytes &&
+                  Conv2Dgrad::RES_BYTES <= kPrepW2DBytes, "prepared-weight layout");
+
 int split_rows(int64_t rows, int want, int* k_chunk) {
   int64_t per = (rows + want - 1) / want;
   per = (per + 127) / 128 * 128;
@@ -801,14 +847,22 @@ int split_rows(int64_t rows, int want, int* k_chunk) {
 }
 
 }  // namespace
+
+int conv_prepare(const float* params, void* prepared, cudaStream_t st) {
+  build_images_kernel<<<3, 256, 33536, st>>>(params, (uint8_t*)prepared);
+  ARL_LAUNCH_CHECK("build_images_kernel");
+  return ARL_OK;
+}
+
 }  // namespace arl
 
 using namespace arl;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int arl_conv1_forward(const float* params, const uint8_t* ring, float* a1, int num_envs,
+extern "C" int arl_conv1_forward(const float* prepared, const uint8_t* ring, float* a1, int num_envs,
                                  int ring_slots, int first_slot, int steps, void* stream) {
+  const float* params = prepared;
   ARL_REQUIRE(params && ring && a1, "arl_conv1_forward: null pointer");
   ARL_REQUIRE(num_envs >= 0 && steps >= 0, "arl_conv1_forward: negative size");
   ARL_REQUIRE(ring_slots >= steps + 3 && first_slot >= 0 && first_slot < ring_slots,
@@ -819,19 +873,21 @@ extern "C" int arl_conv1_forward(const float* params, const uint8_t* ring, float
   const int64_t N = (int64_t)num_envs * steps;
   if (N == 0) return ARL_OK;
   ARL_REQUIRE(N * 441 < (1LL << 31) - 256, "arl_conv1_forward: too many samples");
-  Conv1FwdArgs g{params, {ring, num_envs, ring_slots, first_slot}, reinterpret_cast<uint8_t*>(a1), N * 441, (int)N};
+  Conv1FwdArgs g{reinterpret_cast<const uint8_t*>(prepared) + kPrepW1, {ring, num_envs, ring_slots, first_slot},
+                 reinterpret_cast<uint8_t*>(a1), N * 441, (int)N};
   return tc::launch<Conv1Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 
-extern "C" int arl_conv2_forward(const float* params, const float* a1, float* a2,
+extern "C" int arl_conv2_forward(const float* prepared, const float* a1, float* a2,
                                  int64_t num_samples, void* stream) {
+  const float* params = prepared;
   ARL_REQUIRE(params && a1 && a2, "arl_conv2_forward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 24), "arl_conv2_forward: bad num_samples");
   ARL_REQUIRE(aligned16(params) && aligned16(a1) && aligned16(a2),
               "arl_conv2_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
-  Conv2FwdArgs g{params, reinterpret_cast<const uint8_t*>(a1), reinterpret_cast<uint8_t*>(a2),
-                 num_samples * 100, (int)num_samples};
+  Conv2FwdArgs g{reinterpret_cast<const uint8_t*>(prepared) + kPrepW2F, reinterpret_cast<const uint8_t*>(a1),
+                 reinterpret_cast<uint8_t*>(a2), num_samples * 100, (int)num_samples};
   return tc::launch<Conv2Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 
@@ -864,9 +920,10 @@ extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float*
   return reduce_partials(g.partials, grads, g.items, 4096, st);                  // l1_w
 }
 
-extern "C" int arl_conv2_backward(const float* params, const float* a1, const float* d_a2,
+extern "C" int arl_conv2_backward(const float* prepared, const float* a1, const float* d_a2,
                                   float* d_a1, float* grads, void* workspace, int64_t num_samples,
                                   void* stream) {
+  const float* params = prepared;
   ARL_REQUIRE(params && a1 && d_a2 && d_a1 && grads && workspace,
               "arl_conv2_backward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 24), "arl_conv2_backward: bad num_samples");
@@ -896,8 +953,8 @@ extern "C" int arl_conv2_backward(const float* params, const float* a1, const fl
   if (rc) return rc;
   // dgrad; its epilogue also sums the columns of d_a1 = the conv1 bias gradient l1_b
   float* db1 = (float*)workspace + (size_t)w.items * (8192 + Conv2Wgrad::PROD_WARPS * 32);
-  Conv2DgradArgs d{params, reinterpret_cast<const uint8_t*>(a1), d_a2, reinterpret_cast<uint8_t*>(d_a1), db1,
-                   num_samples * 121, (int)num_samples};
+  Conv2DgradArgs d{reinterpret_cast<const uint8_t*>(prepared) + kPrepW2D, reinterpret_cast<const uint8_t*>(a1),
+                   d_a2, reinterpret_cast<uint8_t*>(d_a1), db1, num_samples * 121, (int)num_samples};
   const int items = (int)((d.rows + 127) / 128);
   rc = tc::launch<Conv2Dgrad>(d, items, st);
   if (rc) return rc;

@@ -150,37 +150,44 @@ extern "C" int arl_debug_gemm(int variant, const float* A, const float* B, float
   return ARL_OK;
 }
 
-extern "C" int arl_fc_prepare(const float* params, float* w_split, void* stream) {
-  ARL_REQUIRE(params && w_split, "arl_fc_prepare: null pointer");
-  ARL_REQUIRE(aligned16(params) && aligned16(w_split), "arl_fc_prepare: pointers must be 16-byte aligned");
+namespace arl { int conv_prepare(const float* params, void* prepared, cudaStream_t st); }
+
+extern "C" int64_t arl_prepared_floats(void) { return kPrepBytes / 4; }
+
+extern "C" int arl_prepare_weights(const float* params, float* prepared, void* stream) {
+  ARL_REQUIRE(params && prepared, "arl_prepare_weights: null pointer");
+  ARL_REQUIRE(aligned16(params) && aligned16(prepared), "arl_prepare_weights: pointers must be 16-byte aligned");
   const ParamLayout L = param_layout(1);
-  return split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8, w_split, (cudaStream_t)stream);
+  int rc = split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8,
+                      reinterpret_cast<uint8_t*>(prepared) + kPrepFcW, (cudaStream_t)stream);
+  if (rc) return rc;
+  return conv_prepare(params, prepared, (cudaStream_t)stream);
 }
 
-extern "C" int arl_fc_forward(const float* params, const float* w_split, const float* a2, float* h,
+extern "C" int arl_fc_forward(const float* params, const float* prepared, const float* a2, float* h,
                               int64_t num_samples, void* stream) {
-  ARL_REQUIRE(params && w_split && a2 && h, "arl_fc_forward: null pointer");
+  ARL_REQUIRE(params && prepared && a2 && h, "arl_fc_forward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_forward: bad num_samples");
-  ARL_REQUIRE(aligned16(params) && aligned16(w_split) && aligned16(a2) && aligned16(h),
+  ARL_REQUIRE(aligned16(params) && aligned16(prepared) && aligned16(a2) && aligned16(h),
               "arl_fc_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
   const ParamLayout L = param_layout(1);
   const int M = (int)num_samples;
   tc::BulkGemmArgs g;
   g.A = mat(a2, M, M, ARL_A2_ELEMS / 8);
-  g.B = mat(w_split, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
+  g.B = mat(prepared, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
   g.mask = mat(nullptr, 0, 1, 0);
   g.D = h; g.bias = params + L.off[T_L4B];
   g.M = M; g.N = ARL_FC; g.K = ARL_A2_ELEMS; g.ldd = ARL_FC;
   return run_gemm<FcFwd>(g, 1, (cudaStream_t)stream);
 }
 
-extern "C" int arl_fc_backward(const float* w_split, const float* a2, int64_t a2_block_rows,
+extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,
                                const float* d_h, float* d_a2, float* grads, void* workspace,
                                int64_t num_samples, void* stream) {
-  ARL_REQUIRE(w_split && a2 && d_h && d_a2 && grads && workspace, "arl_fc_backward: null pointer");
+  ARL_REQUIRE(prepared && a2 && d_h && d_a2 && grads && workspace, "arl_fc_backward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_backward: bad num_samples");
-  ARL_REQUIRE(aligned16(w_split) && aligned16(a2) && aligned16(d_h) && aligned16(d_a2) &&
+  ARL_REQUIRE(aligned16(prepared) && aligned16(a2) && aligned16(d_h) && aligned16(d_a2) &&
                   aligned16(grads) && aligned16(workspace),
               "arl_fc_backward: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -197,7 +204,7 @@ extern "C" int arl_fc_backward(const float* w_split, const float* a2, int64_t a2
   const int M = (int)num_samples;
   const tc::SplitMat a2s = mat(a2, M, (int)a2_block_rows, ARL_A2_ELEMS / 8);
   const tc::SplitMat dhs = mat(d_h, M, M, ARL_FC / 8);
-  const tc::SplitMat ws = mat(w_split, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
+  const tc::SplitMat ws = mat(prepared, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
   // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
   tc::BulkGemmArgs g;
   g.A = dhs; g.B = ws; g.mask = a2s;

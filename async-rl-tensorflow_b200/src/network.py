@@ -107,9 +107,9 @@ class Network(object):
         for i, (name, shape) in enumerate(param_shapes(A).items()):
             self.w[name] = self.params[self.offsets[i]:self.offsets[i + 1]].view(shape)
             self.g[name] = self.grads[self.offsets[i]:self.offsets[i + 1]].view(shape)
-        # l4_w as the split block the fc256 kernels read (arl_fc_prepare); refreshed lazily: the key
-        # is (tensor version, number of C-ABI writes) of the parameters it was made from
-        self.fc_w = torch.empty(A2_ELEMS * FC, device=dev)
+        # the weights as the tensor-core kernels keep them resident (arl_prepare_weights); refreshed
+        # lazily: the key is (tensor version, number of C-ABI writes) of the parameters it was made from
+        self.fc_w = torch.empty(_cabi.prepared_floats(), device=dev)
         self._fc_w_key = None
         self._param_writes = 0
         self.set_weights(initial_weights(A, seed))
@@ -192,10 +192,10 @@ class Network(object):
                        P(logits), P(probs), P(value), st)
             return
         if refresh:
-            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
-        self._timed_call("arl_conv1_forward", P(self.params), P(history.ring), P(l1), B,
+            _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
+        self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring), P(l1), B,
                          history.ring_slots, history.first_slot(0), 1, st)
-        self._timed_call("arl_conv2_forward", P(self.params), P(l1), P(l2), B, st)
+        self._timed_call("arl_conv2_forward", P(self.fc_w), P(l1), P(l2), B, st)
         self._timed_call("arl_fc_forward", P(self.params), P(self.fc_w), P(l2), P(l4), B, st)
         self._timed_call("arl_heads_forward", P(self.params), A, P(l4), P(logits), P(probs),
                          P(value), B, st)
@@ -265,7 +265,7 @@ class Network(object):
                    self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
         P = _cabi.ptr
         if self._fc_w_stale():                                 # (a forward normally did this already)
-            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
+            _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
         if self.timed is None:
             _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                        history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2),
@@ -277,7 +277,7 @@ class Network(object):
                          P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, st)
         self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), B, P(self.d_l4), P(self.d_l2),
                          P(self.grads), P(self.workspace), N, st)
-        self._timed_call("arl_conv2_backward", P(self.params), P(self.l1), P(self.d_l2),
+        self._timed_call("arl_conv2_backward", P(self.fc_w), P(self.l1), P(self.d_l2),
                          P(self.d_l1), P(self.grads), P(self.workspace), N, st)
         self._timed_call("arl_conv1_backward", P(history.ring), P(self.d_l1), P(self.grads),
                          P(self.workspace), B, history.ring_slots, history.first_slot(T), T, st)
@@ -292,7 +292,7 @@ class Network(object):
         self.target_q = torch.empty(N, A, **f32)              # agent.py:186 q_t_plus_1
         self.target_q_t = torch.empty(N, **f32)               # agent.py:190
         self._tq_scratch = (torch.empty(N, A, **f32), torch.empty(N, **f32))
-        self.target_fc_w = torch.empty(A2_ELEMS * FC, device=self.device)
+        self.target_fc_w = torch.empty(_cabi.prepared_floats(), device=self.device)
         return self.target_params
 
     def update_target(self):
@@ -323,7 +323,7 @@ class Network(object):
                    float(grad_scale), st)
         self.d_value.zero_()                                   # the value head is unused
         if self._fc_w_stale():
-            _cabi.call("arl_fc_prepare", P(self.params), P(self.fc_w), st)
+            _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
         _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                    history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
                    P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),

@@ -12,6 +12,14 @@ from .. import _cabi
 A1_ELEMS, A2_ELEMS, FC = 6400, 2592, 256
 
 
+def _prepared(params):
+    """params -> the resident operand images of the kernels (arl_prepare_weights), made on every
+    call: these stand-alone wrappers keep no state.  Network caches it per parameter version."""
+    prepared = torch.empty(_cabi.prepared_floats(), device=params.device)
+    _cabi.call("arl_prepare_weights", _cabi.ptr(params), _cabi.ptr(prepared), _cabi.stream_ptr())
+    return prepared
+
+
 def conv2d(x, params, output_dim, kernel_size, stride, out=None, name='l1', steps=1):
     """ops.py:4-30 (VALID, NHWC, bias, relu).
 
@@ -24,14 +32,14 @@ def conv2d(x, params, output_dim, kernel_size, stride, out=None, name='l1', step
         if out is None:
             out = torch.empty(n, 20, 20, 16, device=params.device)
         first = hist.first_slot(steps - 1)
-        _cabi.call("arl_conv1_forward", _cabi.ptr(params), _cabi.ptr(hist.ring), _cabi.ptr(out),
+        _cabi.call("arl_conv1_forward", _cabi.ptr(_prepared(params)), _cabi.ptr(hist.ring), _cabi.ptr(out),
                    hist.num_envs, hist.ring_slots, first, steps, _cabi.stream_ptr())
         return out
     if name == 'l2' and (output_dim, ks, st) == (32, (4, 4), (2, 2)):
         n = x.shape[0]
         if out is None:
             out = torch.empty(n, 9, 9, 32, device=params.device)
-        _cabi.call("arl_conv2_forward", _cabi.ptr(params), _cabi.ptr(x), _cabi.ptr(out), n,
+        _cabi.call("arl_conv2_forward", _cabi.ptr(_prepared(params)), _cabi.ptr(x), _cabi.ptr(out), n,
                    _cabi.stream_ptr())
         return out
     raise NotImplementedError("conv2d %s: only the 'nips' trunk layers are built "
@@ -45,10 +53,8 @@ def linear(input_, params, output_size, out=None, name='l4'):
         n = x.shape[0]
         if out is None:
             out = torch.empty(n, FC, device=params.device)
-        # x is the split block conv2d(name='l2') wrote; l4_w is split into scratch on every call
-        w_split = torch.empty(A2_ELEMS * FC, device=params.device)
-        _cabi.call("arl_fc_prepare", _cabi.ptr(params), _cabi.ptr(w_split), _cabi.stream_ptr())
-        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(w_split), _cabi.ptr(x),
+        # x is the split block conv2d(name='l2') wrote
+        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(_prepared(params)), _cabi.ptr(x),
                    _cabi.ptr(out), n, _cabi.stream_ptr())
         return out
     raise NotImplementedError("linear %s: only the fc256 layer is exposed stand-alone; the "

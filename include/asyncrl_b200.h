@@ -32,8 +32,11 @@
  *           call's num_samples, 324 chunks in NHWC-flatten order (agent.py:231-232);
  *       d_h (the f32 [N,256]-sized buffer): one block of N rows, 32 chunks, written by
  *           arl_heads_backward;
- *       fc_w_split (2592*256 floats): l4_w as one block of 2592 rows, 32 chunks, written by
- *           arl_fc_prepare -- must be refreshed whenever l4_w changes.
+ *       l4_w: one block of 2592 rows, 32 chunks, at the start of the `prepared` buffer.
+ *   - `prepared` (arl_prepared_floats() floats, written by arl_prepare_weights) holds the weights in
+ *     the form the tensor-core kernels keep resident: l4_w as a split block, l1_w as three s8
+ *     limbs + scales + l1_b, l2_w as [hi | lo] bf16 images (forward and transposed) + l2_b.  It
+ *     must be refreshed whenever the parameters change (arl_clip_rmsprop, a checkpoint load, ...).
  *     src/network.py:decode_split turns a block back into f32 [rows][cols].
  *   - d_a1, the gradient w.r.t. conv1's output, is the reduction operand of the conv1 weight
  *     gradient: split bf16 on conv1's 21x21 space-to-depth grid,
@@ -132,22 +135,23 @@ ARL_API int arl_history_reset(uint8_t* ring, int num_envs, int ring_slots, void*
  * (softmax).  steps*num_envs samples.  a1 [N,20,20,16], a2 [N,2592], h [N,256] are
  * written for the backward pass (a1 and a2 in the device layouts described at the top of this
  * file); logits/probs [N,A], value [N]. */
-ARL_API int arl_conv1_forward(const float* params, const uint8_t* ring, float* a1, int num_envs,
+/* params -> prepared (see the top of this file): 2 small kernels.  Call after every change of
+ * the parameters. */
+ARL_API int64_t arl_prepared_floats(void);
+ARL_API int arl_prepare_weights(const float* params, float* prepared, void* stream);
+ARL_API int arl_conv1_forward(const float* prepared, const uint8_t* ring, float* a1, int num_envs,
                       int ring_slots, int first_slot, int steps, void* stream);
 /* a2 = ONE split block of num_samples rows. */
-ARL_API int arl_conv2_forward(const float* params, const float* a1, float* a2, int64_t num_samples,
+ARL_API int arl_conv2_forward(const float* prepared, const float* a1, float* a2, int64_t num_samples,
                       void* stream);
-/* l4_w (agent.py:251) -> fc_w_split, the split block the fc256 kernels read.  Call after every
- * change of the parameters (arl_clip_rmsprop, a checkpoint load, ...). */
-ARL_API int arl_fc_prepare(const float* params, float* fc_w_split, void* stream);
 /* a2 = one split block of num_samples rows (as arl_conv2_forward wrote it); h f32 [N,256]. */
-ARL_API int arl_fc_forward(const float* params, const float* fc_w_split, const float* a2, float* h,
+ARL_API int arl_fc_forward(const float* params, const float* prepared, const float* a2, float* h,
                    int64_t num_samples, void* stream);
 ARL_API int arl_heads_forward(const float* params, int action_size, const float* h, float* logits,
                       float* probs, float* value, int64_t num_samples, void* stream);
-/* The four above back to back, after arl_fc_prepare when refresh_fc_w != 0 (pass 1 unless
- * fc_w_split was filled from these very parameters by an earlier call). */
-ARL_API int arl_forward(const float* params, float* fc_w_split, int refresh_fc_w, int action_size,
+/* The four above back to back, after arl_prepare_weights when refresh_prepared != 0 (pass 1
+ * unless `prepared` was made from these very parameters by an earlier call). */
+ARL_API int arl_forward(const float* params, float* prepared, int refresh_prepared, int action_size,
                 const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                 float* a1, float* a2, float* h, float* logits, float* probs, float* value,
                 void* stream);
@@ -207,21 +211,21 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
  * d_a1 [N,ARL_DA1_ELEMS] (grid layout, see the top of this file),
  * workspace >= arl_backward_workspace_bytes.  a2 = the rollout's conv2 outputs as a sequence of
  * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);
- * fc_w_split must hold arl_fc_prepare of the parameters the forward used. */
+ * prepared must hold arl_prepare_weights of the parameters the forward used. */
 ARL_API int64_t arl_backward_workspace_bytes(int action_size);
 ARL_API int arl_heads_backward(const float* params, int action_size, const float* h,
                        const float* dlogits, const float* dvalue, float* d_h, float* grads,
                        void* workspace, int64_t num_samples, void* stream);
-ARL_API int arl_fc_backward(const float* fc_w_split, const float* a2, int64_t a2_block_rows,
+ARL_API int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,
                     const float* d_h, float* d_a2, float* grads, void* workspace,
                     int64_t num_samples, void* stream);
 /* l2_w, l2_b, d_a1 and l1_b (the column sums of d_a1). */
-ARL_API int arl_conv2_backward(const float* params, const float* a1, const float* d_a2, float* d_a1,
+ARL_API int arl_conv2_backward(const float* prepared, const float* a1, const float* d_a2, float* d_a1,
                        float* grads, void* workspace, int64_t num_samples, void* stream);
 /* l1_w only (l1_b comes from arl_conv2_backward). */
 ARL_API int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads, void* workspace,
                        int num_envs, int ring_slots, int first_slot, int steps, void* stream);
-ARL_API int arl_backward(const float* params, const float* fc_w_split, int action_size,
+ARL_API int arl_backward(const float* params, const float* prepared, int action_size,
                  const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                  const float* a1, const float* a2,
                  const float* h, const float* dlogits, const float* dvalue, float* d_h,

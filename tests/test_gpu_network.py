@@ -58,14 +58,14 @@ def test_forward_layers_vs_oracle(pkg, cuda, A, B, T, R, first):
     a1 = torch.empty(N, 20, 20, 16, **f32); a2 = torch.empty(N, 2592, **f32)
     h = torch.empty(N, 256, **f32); lg = torch.empty(N, A, **f32)
     pr = torch.empty(N, A, **f32); v = torch.empty(N, **f32)
-    fc_w = torch.empty(2592 * 256, **f32)
+    fc_w = torch.empty(pkg._cabi.prepared_floats(), **f32)
     pkg._cabi.call("arl_forward", flat.data_ptr(), fc_w.data_ptr(), 1, A, ring.data_ptr(), B, R, first,
                    T, a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
                    v.data_ptr(), pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
     a1 = pkg.network.decode_a1(a1)                                # device layout: split bf16, blocked
     a2 = pkg.network.decode_split(a2, N, 2592)                    # one split block of the call's N rows
-    assert rel_err(pkg.network.decode_split(fc_w, 2592, 256).cpu(), params["l4_w"]) <= 1e-5
+    assert rel_err(pkg.network.decode_split(fc_w[:2592 * 256], 2592, 256).cpu(), params["l4_w"]) <= 1e-5
     logits, value, keep = a3c.forward(a3c.to_torch(params), ring_stacks(ring_np, first, T), keep=True)
     pi, _, _ = a3c.policy_terms(logits)
     errs = dict(a1=rel_err(a1.cpu(), keep["a1"]), a2=rel_err(a2.cpu(), keep["a2"]),
