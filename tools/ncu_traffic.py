@@ -12,9 +12,10 @@ ENTRY_OF = [
     ("preprocess_kernel", "arl_preprocess_push"),
     ("Conv1Fwd", "arl_conv1_forward"),
     ("Conv2Fwd", "arl_conv2_forward"),
-    ("GemmPolicy<64, 32, 0, 1, 1", "arl_fc_forward"),
-    ("GemmPolicy<256, 16, 0, 0, 2", "arl_fc_backward"),
-    ("GemmPolicy<256, 16, 1, 1, 0", "arl_fc_backward"),
+    ("BulkGemm<64, 32, 0, 1, 1", "arl_fc_forward"),      # (int)/(bool) casts are stripped below
+    ("FcDgrad", "arl_fc_backward"),
+    ("BulkGemm<128, 32, 0, 0, 2", "arl_fc_backward"),
+    ("BulkGemm<128, 64, 1, 1, 0", "arl_fc_backward"),
     ("Conv2Wgrad", "arl_conv2_backward"),
     ("Conv2Dgrad", "arl_conv2_backward"),
     ("Conv1Wgrad", "arl_conv1_backward"),
@@ -30,8 +31,9 @@ def main(src, dst):
     t_i = hdr.index("gpu__time_duration.sum")
     seen, out = set(), {}
     for r in rows[2:]:
+        kname = r[name_i].replace("(int)", "").replace("(bool)", "")
         for pat, entry in ENTRY_OF:
-            if pat in r[name_i] and pat not in seen:
+            if pat in kname and pat not in seen:
                 seen.add(pat)
                 b = float(r[rd_i]) * UNIT[units[rd_i]] + float(r[wr_i]) * UNIT[units[wr_i]]
                 e = out.setdefault(entry, {"dram_bytes_per_launch": 0.0, "kernels": []})
