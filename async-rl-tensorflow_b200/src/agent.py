@@ -201,6 +201,45 @@ class Agent(BaseModel):
             return self.network.egreedy(self.t, self.step, self.seed, ep, self.env_id_base)
         return self.network.sample(self.t, self.step, self.seed, self.env_id_base)
 
+    # -- agent.py:351-391 -------------------------------------------------------------------
+    def play(self, sv=None, is_chief=True, n_step=10000, n_episode=100, test_ep=None, render=False):
+        """Evaluation episodes (agent.py:351-391) on all ``num_envs`` environments at once: a fresh
+        History seeded with 4 copies of the first screen (agent.py:365-366), then predict / act
+        (is_training=False: no life-loss terminal) / add until every env has finished its episode
+        or ``n_step`` steps have passed.  Action selection: epsilon-greedy with ``test_ep``
+        (default ep_end, agent.py:352-353) in async_q mode, a sample from the policy in a3c mode.
+        Returns (best_reward, best_idx, per-episode mean reward over the envs); gym's monitor
+        (agent.py:357-359) is the emulator's business and not reproduced."""
+        if test_ep is None:
+            test_ep = self.ep_end
+        test_history = History(self.config, num_envs=self.num_envs, device=self.device)
+        best_reward, best_idx, means = 0.0, 0, []
+        step = 0
+        for idx in range(int(n_episode)):
+            self.env.new_random_game()
+            test_history.add(self.env.frames, replicate=self.history_length)
+            current = torch.zeros(self.num_envs, device=self.device)
+            alive = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+            for _ in range(int(n_step)):
+                # 1. predict   2. act   3. observe
+                action = self.network.evaluate(test_history, step, self.seed + 1,
+                                               ep=test_ep if self.loss_mode == 'async_q' else None,
+                                               env_id_base=self.env_id_base)
+                screen, reward, terminal = self.env.act(action, is_training=False, fused=True)
+                test_history.add(screen)
+                current += torch.where(alive, reward, torch.zeros_like(reward))
+                alive &= ~terminal.bool()
+                step += 1
+                if render:
+                    self.env.render()
+                if not bool(alive.any()):
+                    break
+            top = float(current.max())
+            means.append(float(current.mean()))
+            if top > best_reward:
+                best_reward, best_idx = top, idx
+        return best_reward, best_idx, means
+
     # -- agent.py:153-167 -------------------------------------------------------------------
     def observe(self, screen, reward, action, terminal, is_chief=False):
         self.history.add(screen)                                 # agent.py:156 (K1 when raw frames)

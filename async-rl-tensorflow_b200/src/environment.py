@@ -132,6 +132,110 @@ class SyntheticAtari(object):
         pass
 
 
+class GymVectorAdapter(object):
+    """Real emulators behind the batched surface above: ``envs`` is a list of gym-style
+    environments, one per env slot, exactly what the reference's ``gym.make(config.env_name)``
+    returns (environment.py:16): ``reset() -> frame`` (or ``(frame, info)``), ``step(a) ->
+    (frame, reward, terminal, info)`` (or gymnasium's 5-tuple), ``ale.lives()``,
+    ``action_space.n`` / ``.sample()``.  The emulators run on the host; each step's frames are
+    gathered into one pinned buffer u8 [B,210,160,3] and cross PCIe once -- on a CUDA device only
+    the 168 of 210 rows K1 reads (arl_upload_frames), double-buffered so that the copy of step
+    i+1 can overlap the kernels of step i.  Finished episodes are reset in place (the reference
+    resets in new_game when lives == 0, environment.py:29-31)."""
+
+    def __init__(self, envs, device='cuda', auto_reset=True):
+        self.envs = list(envs)
+        self.num_envs = len(self.envs)
+        self.device = torch.device(device)
+        self.auto_reset = bool(auto_reset)
+        B = self.num_envs
+        pin = self.device.type == 'cuda'
+        self._host = [torch.zeros((B,) + FRAME_SHAPE, dtype=torch.uint8, pin_memory=pin) for _ in range(2)]
+        self._dev = [torch.zeros((B,) + FRAME_SHAPE, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._k = 0
+        self._rew = torch.zeros(B, dtype=torch.float32)
+        self._term = torch.zeros(B, dtype=torch.bool)
+        self._lives_host = torch.zeros(B, dtype=torch.int32)
+        self.ale = self                                          # ale.lives()
+        self.action_space = self                                 # action_space.n / .sample()
+        self.n = int(self.envs[0].action_space.n)
+        self.h2d_bytes_per_step = B * 168 * FRAME_SHAPE[1] * FRAME_SHAPE[2] if pin else 0
+
+    # -- gym surface of one emulator ---------------------------------------------------------
+    @staticmethod
+    def _reset_one(env):
+        out = env.reset()
+        return out[0] if isinstance(out, tuple) else out
+
+    @staticmethod
+    def _step_one(env, a):
+        out = env.step(int(a))
+        if len(out) == 5:                                        # gymnasium: terminated, truncated
+            frame, reward, terminated, truncated, _ = out
+            return frame, float(reward), bool(terminated or truncated)
+        frame, reward, terminal, _ = out
+        return frame, float(reward), bool(terminal)
+
+    @staticmethod
+    def _lives_one(env):
+        ale = getattr(env, 'ale', None) or getattr(getattr(env, 'unwrapped', env), 'ale', None)
+        return int(ale.lives()) if ale is not None else 1
+
+    # -- batched surface ---------------------------------------------------------------------
+    def lives(self):
+        for b, e in enumerate(self.envs):
+            self._lives_host[b] = self._lives_one(e)
+        return self._lives_host.to(self.device)
+
+    def sample(self):
+        return torch.tensor([int(e.action_space.sample()) for e in self.envs], dtype=torch.int32,
+                            device=self.device)
+
+    def _upload(self):
+        k = self._k
+        self._k ^= 1
+        host, dev = self._host[k], self._dev[k]
+        if self.device.type == 'cuda':
+            _cabi.call("arl_upload_frames", host.data_ptr(), _cabi.ptr(dev), self.num_envs,
+                       _cabi.stream_ptr())
+        else:
+            dev.copy_(host)
+        return dev
+
+    def _host_buffer(self):
+        """The pinned buffer the next upload will read; its previous upload (two steps ago) must
+        have completed before the emulators overwrite it."""
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream().synchronize()
+        return self._host[self._k]
+
+    def reset(self, mask=None):
+        buf = self._host_buffer()
+        if mask is not None:
+            mask = mask.cpu().tolist()
+        prev = self._host[self._k ^ 1]
+        for b, e in enumerate(self.envs):
+            if mask is None or mask[b]:
+                buf[b].copy_(torch.as_tensor(self._reset_one(e)))
+            else:
+                buf[b].copy_(prev[b])
+        return self._upload()
+
+    def step(self, actions):
+        acts = actions.cpu().tolist()
+        buf = self._host_buffer()
+        for b, e in enumerate(self.envs):
+            frame, self._rew[b], self._term[b] = self._step_one(e, acts[b])
+            if self._term[b] and self.auto_reset and self._lives_one(e) == 0:
+                frame = self._reset_one(e)
+            buf[b].copy_(torch.as_tensor(frame))
+        return (self._upload(), self._rew.to(self.device), self._term.to(self.device), {})
+
+    def render(self):
+        for e in self.envs:
+            e.render()
+
+
 class Environment(object):
     def __init__(self, config, env=None, device=None):
         self.device = torch.device(device if device is not None else 'cuda')

@@ -235,6 +235,24 @@ class Network(object):
         self._forward_into(history, b['l1'], b['l2'], b['l4'], b['logits'], b['probs'], b['value'])
         return b['value']
 
+    def evaluate(self, history, step, seed, ep=None, env_id_base=0):
+        """Forward of ``history``'s current stack into the scratch buffers (no rollout slot is
+        touched) and one action per env: epsilon-greedy over the Q values when ``ep`` is given
+        (agent.py:141-151), else a sample from the policy (network.py:72).  Used by Agent.play."""
+        b = self._b
+        self._forward_into(history, b['l1'], b['l2'], b['l4'], b['logits'], b['probs'], b['value'])
+        if 'action' not in b:
+            b['action'] = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        if ep is not None:
+            _cabi.call("arl_egreedy_actions", _cabi.ptr(b['logits']), _cabi.ptr(b['action']),
+                       self.num_envs, self.action_size, float(ep), int(env_id_base), int(step),
+                       int(seed), _cabi.stream_ptr())
+        else:
+            _cabi.call("arl_sample_actions", _cabi.ptr(b['probs']), _cabi.ptr(b['action']),
+                       self.num_envs, self.action_size, int(env_id_base), int(step), int(seed),
+                       _cabi.stream_ptr())
+        return b['action']
+
     @property
     def log_policy(self):                                   # network.py:67 (log OF the softmax)
         return torch.log(self.policy)

@@ -46,3 +46,34 @@ def test_unbuilt_resize_branch_fails_loudly(pkg):
     cfg = pkg.config.get_config({"model": "m1", "resize": "lanczos"})
     with pytest.raises((NotImplementedError, pkg._cabi.ArlError)):
         pkg.GymEnvironment(cfg, env=object(), device="cuda:0")
+
+
+def test_gym_vector_adapter_host_logic(pkg):
+    """GymVectorAdapter (the real-emulator seam of environment.py:14-65) on the CPU: frames of B
+    gym-style emulators are gathered unchanged, rewards / terminals / lives are batched, both the
+    gym 4-tuple and the gymnasium 5-tuple APIs are accepted, a finished game is reset in place."""
+    import numpy as np
+    import torch
+    from util import StubGymEnv
+    envs = [StubGymEnv(1), StubGymEnv(2, gymnasium=True), StubGymEnv(3, episode_len=2, lives=1)]
+    ad = pkg.environment.GymVectorAdapter(envs, device='cpu')
+    assert ad.num_envs == 3 and ad.action_space.n == 4
+    f0 = ad.reset()
+    assert f0.shape == (3, 210, 160, 3) and f0.dtype == torch.uint8
+    for b, e in enumerate(envs):
+        assert np.array_equal(f0[b].numpy(), e.frames[-1]) and e.resets == 1
+    assert ad.ale.lives().tolist() == [2, 2, 1]
+    f1, r1, t1, _ = ad.step(torch.tensor([1, 2, 3], dtype=torch.int32))
+    assert r1.tolist() == [1.0, 2.0, 3.0] and t1.tolist() == [False, False, False]
+    assert all(np.array_equal(f1[b].numpy(), e.frames[-1]) for b, e in enumerate(envs))
+    assert not np.array_equal(f1.numpy(), f0.numpy())             # double buffer: f0 is still intact
+    assert np.array_equal(f0[0].numpy(), envs[0].frames[0])
+    f2, r2, t2, _ = ad.step(torch.tensor([0, 0, 0], dtype=torch.int32))
+    assert t2.tolist() == [False, False, True]                    # env 2: episode_len 2, its only life
+    assert envs[2].resets == 2 and ad.ale.lives().tolist() == [2, 2, 1]   # ... so it was reset in place
+    assert np.array_equal(f2[2].numpy(), envs[2].frames[-1])
+    # masked reset: only env 0 restarts, the others keep their last frame
+    f3 = ad.reset(torch.tensor([True, False, False]))
+    assert envs[0].resets == 2 and envs[1].resets == 1
+    assert np.array_equal(f3[1].numpy(), f2[1].numpy()) and np.array_equal(f3[0].numpy(), envs[0].frames[-1])
+    assert len(ad.action_space.sample()) == 3

@@ -46,3 +46,57 @@ def block(screens):
     order = tuple(range(n)) + (n, n + 2, n + 1, n + 3)
     x = x.transpose(order) if isinstance(x, np.ndarray) else x.permute(*order)
     return x.reshape(lead + (84, 84))
+
+
+class StubGymEnv(object):
+    """A gym-style emulator for the adapter tests (what gym.make(...) returns in the reference,
+    environment.py:16): deterministic 210x160x3 frames, ``episode_len`` steps per life, ``lives``
+    lives, reward = action.  ``gymnasium=True`` switches to the 5-tuple / (obs, info) API."""
+
+    class _Space(object):
+        def __init__(self, n, rng):
+            self.n, self._rng = n, rng
+
+        def sample(self):
+            return int(self._rng.integers(0, self.n))
+
+    class _ALE(object):
+        def __init__(self, env):
+            self._env = env
+
+        def lives(self):
+            return self._env._lives
+
+    def __init__(self, seed, n_actions=4, episode_len=3, lives=2, gymnasium=False):
+        import numpy as np
+        self._np = np
+        self._rng = np.random.default_rng(seed)
+        self._seed, self._len, self._max_lives, self._gymnasium = seed, episode_len, lives, gymnasium
+        self._lives, self._t, self.resets = 0, 0, 0
+        self.action_space = self._Space(n_actions, self._rng)
+        self.ale = self._ALE(self)
+        self.frames = []                                         # every frame handed out, in order
+
+    def _frame(self):
+        f = self._rng.integers(0, 256, (210, 160, 3), dtype=self._np.uint8)
+        self.frames.append(f)
+        return f
+
+    def reset(self):
+        self._lives, self._t = self._max_lives, 0
+        self.resets += 1
+        f = self._frame()
+        return (f, {}) if self._gymnasium else f
+
+    def step(self, a):
+        self._t += 1
+        done = self._t % self._len == 0
+        if done:
+            self._lives -= 1
+        f = self._frame()
+        if self._gymnasium:
+            return f, float(a), done, False, {}
+        return f, float(a), done, {}
+
+    def render(self):
+        pass
