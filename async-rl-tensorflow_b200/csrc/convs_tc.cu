@@ -657,13 +657,17 @@ struct Conv2WgradArgs {
 struct Conv2Wgrad : tc::PolicyBase {
   using Args = Conv2WgradArgs;
   struct Prod { float acc[4]; };    // running column sums of dy2 (bias gradient)
+  // dW2[(a,b) tap][ch][co] = sum_P X2[P + a*10 + b][ch] * dy2[P][co] over the rows P of the X2 grid.
+  // The hi and lo images of X2 (a1s) are the two halves of M (rows part*64 + ch): every a1s byte is
+  // copied into shared memory ONCE, a tap is a row offset of the A descriptor, and the four taps
+  // accumulate into four N = 64 column blocks ([dy_hi | dy_lo]).  The two row halves (x_hi.dy and
+  // x_lo.dy) leave as two partial slices and are summed with the split-K partials.
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // 2 shifted copies x 8 ch groups
+  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 8 * PLA;    // one part: 8 channel groups
   static constexpr int PLB = 130 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
-  static constexpr int PROD_WARPS = 16, STAGES = 2, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
-  // accumulator columns: a*64 + part*32 + co (the lo image of dy2 follows its hi image, so one
-  // N = 64 MMA covers both)
-  static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 32, SEG = 32;
+  static constexpr int PROD_WARPS = 18, STAGES = 3, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
+  // accumulator columns: tap*64 + part*32 + co
+  static constexpr int ACC_COLS = 256, OUT_COLS = 128, LO_DELTA = 32, SEG = 32;
   static __device__ __forceinline__ int acc_col(int c) { return (c >> 5) * 64 + (c & 31); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
@@ -679,23 +683,21 @@ struct Conv2Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
                                                     uint8_t* st, int glane, int gsize, Prod& ps) {
     const int p0 = t.k_begin + s * 128;
-    uint8_t* a_hi = st, *a_lo = st + A_IMG, *b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
+    uint8_t* b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
     // A: X2 rows p0 .. p0+139 arrive by cp.async.bulk (bulk_stage); only the rows beyond the last
     // sample need zeros here
-    a1s_zero_tail<TROWS, PLA, A_IMG, 16>(a_hi, p0, g.num_samples, glane, gsize);
-    (void)a_lo;
+    a1s_zero_tail<TROWS, PLA, A_IMG, 8>(st, p0, g.num_samples, glane, gsize);
     // B: dy2 on the 10-wide grid, zero at y'=9 / x'=9 and outside [k_begin, k_end)
-    stream_pixels<GridDy2, 8, 128, PLB, 5, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
+    stream_pixels<GridDy2, 8, 128, PLB, 7, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
                                                  gsize, ps.acc);
   }
-  // planes 0..7 hold row r at r*16, planes 8..15 the same image shifted by one row (tap b = 1);
-  // lanes 0, 16, 32, ... of the stage's 256 own one (part, kc) plane pair each
+  // 16 lanes of the stage's 192 (every 12th) own one (part, kc) plane each
   static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
                                                     int glane, int, uint64_t* full) {
-    if ((glane & 15) != 0) return false;
-    const int p0 = t.k_begin + s * 128, owner = glane >> 4;          // 0..15
-    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PLA, A_IMG, true>(p0, g.num_samples));
-    a1s_bulk_issue<TROWS, PLA, A_IMG, true>(st, g.a1s, p0, g.num_samples, owner >> 3, owner & 7, full);
+    if (glane % 12 != 0) return false;
+    const int p0 = t.k_begin + s * 128, owner = glane / 12;          // 0..15
+    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PLA, A_IMG, false>(p0, g.num_samples));
+    a1s_bulk_issue<TROWS, PLA, A_IMG, false>(st, g.a1s, p0, g.num_samples, owner >> 3, owner & 7, full);
     return true;
   }
   static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
@@ -704,30 +706,27 @@ struct Conv2Wgrad : tc::PolicyBase {
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc64 = tc::make_idesc(64, true, true), idesc32 = tc::make_idesc(32, true, true);
-    const uint32_t a_hi = st, a_lo = st + A_IMG, b_hi = st + 2 * A_IMG;   // b_lo = b_hi + B_IMG
+    constexpr uint32_t idesc = tc::make_idesc(64, true, true);       // [x_hi ; x_lo] . [dy_hi | dy_lo]
+    const uint32_t a_img = st, b_hi = st + 2 * A_IMG;                 // b_lo = b_hi + B_IMG
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+    for (int tap = 0; tap < 4; ++tap) {
 #pragma unroll
       for (int k16 = 0; k16 < 8; ++k16) {
-        const uint32_t ao = (a * GW + k16 * 16) * 16, bo = k16 * 256;
-        const uint64_t da_hi = tc::make_sdesc(a_hi + ao, 128, PLA), da_lo = tc::make_sdesc(a_lo + ao, 128, PLA);
-        const uint64_t db = tc::make_sdesc(b_hi + bo, 128, PLB);           // 8 co groups: hi | lo
-        tc::umma_f16(d + a * 64, da_hi, db, idesc64, (s | k16) != 0 ? 1u : 0u);
-        tc::umma_f16(d + a * 64, da_lo, db, idesc32, 1u);
+        const uint64_t da = tc::make_sdesc(a_img + ((tap >> 1) * GW + (tap & 1) + k16 * 16) * 16, 128, PLA);
+        const uint64_t db = tc::make_sdesc(b_hi + k16 * 256, 128, PLB);
+        tc::umma_f16(d + tap * 64, da, db, idesc, (s | k16) != 0 ? 1u : 0u);
       }
     }
   }
-  // row = b*64 + ch, ch = (i*2+j)*16 + cin ; segment a = 32 co of tap (kh = 2a+i, kw = 2b+j)
+  // row = part*64 + ch, ch = (i*2+j)*16 + cin ; segment tap (a,b) = 32 co of (kh = 2a+i, kw = 2b+j);
+  // part p of work item ks -> partial slice 2*ks + p
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
-    const int b = row >> 6, ch = row & 63, ij = ch >> 4, cin = ch & 15;
-    const int kh = ij >> 1, kw = 2 * b + (ij & 1);
-    return g.partials + (size_t)t.ks * 8192 + ((kh * 4 + kw) * 16 + cin) * 32;
+    const int part = row >> 6, ch = row & 63, ij = ch >> 4, cin = ch & 15;
+    return g.partials + ((size_t)t.ks * 2 + part) * 8192 + (((ij >> 1) * 4 + (ij & 1)) * 16 + cin) * 32;
   }
-  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int a) {
-    return a * 2 * 4 * 16 * 32;
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int tap) {
+    return ((tap >> 1) * 8 + (tap & 1) * 2) * 16 * 32;
   }
-
 };
 
 struct Conv1WgradArgs {
@@ -943,16 +942,16 @@ extern "C" int arl_conv2_backward(const float* prepared, const float* a1, const 
   w.rows = num_samples * 100;
   w.num_samples = (int)num_samples;
   w.items = split_rows(w.rows, num_sms(), &w.k_chunk);
-  w.bias_partials = (float*)workspace + (size_t)w.items * 8192;
+  w.bias_partials = (float*)workspace + (size_t)w.items * 2 * 8192;
   int rc = tc::launch<Conv2Wgrad>(w, w.items, st);
   if (rc) return rc;
-  rc = reduce_partials(w.partials, g2, w.items, 8192, st);
+  rc = reduce_partials(w.partials, g2, 2 * w.items, 8192, st);       // two row halves (x_hi, x_lo) per item
   if (rc) return rc;
   // l2_b = column sums of d_a2, accumulated by the wgrad producers while they stream d_a2
   rc = reduce_partials(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, st);
   if (rc) return rc;
   // dgrad; its epilogue also sums the columns of d_a1 = the conv1 bias gradient l1_b
-  float* db1 = (float*)workspace + (size_t)w.items * (8192 + Conv2Wgrad::PROD_WARPS * 32);
+  float* db1 = (float*)workspace + (size_t)w.items * (2 * 8192 + Conv2Wgrad::PROD_WARPS * 32);
   Conv2DgradArgs d{reinterpret_cast<const uint8_t*>(prepared) + kPrepW2D, reinterpret_cast<const uint8_t*>(a1),
                    d_a2, reinterpret_cast<uint8_t*>(d_a1), db1, num_samples * 121, (int)num_samples};
   const int items = (int)((d.rows + 127) / 128);
