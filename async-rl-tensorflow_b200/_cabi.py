@@ -35,6 +35,8 @@ SIGNATURES = {
     "arl_sample_actions": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_u64, c_vp],
     "arl_greedy_actions": [c_vp, c_vp, c_int, c_int, c_vp],
     "arl_egreedy_actions": [c_vp, c_vp, c_int, c_int, c_f32, c_i64, c_i64, c_u64, c_vp],
+    "arl_act_update": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp],
+    "arl_observe_store": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     "arl_q_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32,
                        c_f32, c_f32, c_vp],
     "arl_returns_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,

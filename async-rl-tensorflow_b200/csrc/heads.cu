@@ -346,6 +346,30 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
   else if (k == A) out[256 * A + A + 256] = bacc;
 }
 
+// ------------------------------- env-step bookkeeping --------------------------------------
+// GymEnvironment.act for action_repeat == 1 (environment.py:78-96): a life lost in training costs
+// one reward point and ends the episode.  One launch instead of five elementwise ones.
+__global__ void act_update_kernel(const float* __restrict__ step_reward,
+                                  const uint8_t* __restrict__ step_terminal,
+                                  const int32_t* __restrict__ lives_before,
+                                  const int32_t* __restrict__ lives_after, int is_training,
+                                  float* __restrict__ reward, uint8_t* __restrict__ terminal, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const bool lost = is_training && lives_before[b] > lives_after[b];
+  reward[b] = step_reward[b] - (lost ? 1.0f : 0.0f);
+  terminal[b] = (step_terminal[b] != 0 || lost) ? 1 : 0;
+}
+// Agent.observe's rollout append (agent.py:158-160): reward and terminal of this step -> slot t
+__global__ void observe_store_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ terminal,
+                                     float* __restrict__ reward_slot, uint8_t* __restrict__ terminal_slot,
+                                     int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  reward_slot[b] = reward[b];
+  terminal_slot[b] = terminal[b] != 0 ? 1 : 0;
+}
+
 int heads_init() {
   const int J = ARL_MAX_ACTIONS + 1;
   ARL_CUDA(cudaFuncSetAttribute(
@@ -456,6 +480,30 @@ extern "C" int arl_returns_lossgrad(const float* rewards, const uint8_t* termina
       rewards, terminals, actions, logits, value, v_boot, returns, dlogits, dvalue, loss_sums,
       t_max, num_envs, action_size, gamma, beta, reward_min, reward_max, grad_scale);
   ARL_LAUNCH_CHECK("returns_lossgrad_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_act_update(const float* step_reward, const uint8_t* step_terminal,
+                              const int32_t* lives_before, const int32_t* lives_after, int is_training,
+                              float* reward, uint8_t* terminal, int num_envs, void* stream) {
+  ARL_REQUIRE(step_reward && step_terminal && lives_before && lives_after && reward && terminal,
+              "arl_act_update: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_act_update: negative size");
+  if (num_envs == 0) return ARL_OK;
+  act_update_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      step_reward, step_terminal, lives_before, lives_after, is_training, reward, terminal, num_envs);
+  ARL_LAUNCH_CHECK("act_update_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_observe_store(const float* reward, const uint8_t* terminal, float* reward_slot,
+                                 uint8_t* terminal_slot, int num_envs, void* stream) {
+  ARL_REQUIRE(reward && terminal && reward_slot && terminal_slot, "arl_observe_store: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_observe_store: negative size");
+  if (num_envs == 0) return ARL_OK;
+  observe_store_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reward, terminal, reward_slot, terminal_slot, num_envs);
+  ARL_LAUNCH_CHECK("observe_store_kernel");
   return ARL_OK;
 }
 

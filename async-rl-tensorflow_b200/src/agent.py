@@ -243,8 +243,15 @@ class Agent(BaseModel):
     # -- agent.py:153-167 -------------------------------------------------------------------
     def observe(self, screen, reward, action, terminal, is_chief=False):
         self.history.add(screen)                                 # agent.py:156 (K1 when raw frames)
-        self.batch_reward[self.t].copy_(reward)                  # clip happens in K4 (agent.py:154)
-        self.batch_terminal[self.t].copy_(terminal)
+        if reward.dtype == torch.float32 and terminal.dtype in (torch.bool, torch.uint8) \
+                and reward.is_contiguous() and terminal.is_contiguous():
+            # one kernel for both appends; the clip happens in K4 (agent.py:154)
+            _cabi.call("arl_observe_store", _cabi.ptr(reward), _cabi.ptr(terminal),
+                       _cabi.ptr(self.batch_reward[self.t]), _cabi.ptr(self.batch_terminal[self.t]),
+                       self.num_envs, _cabi.stream_ptr())
+        else:
+            self.batch_reward[self.t].copy_(reward)
+            self.batch_terminal[self.t].copy_(terminal)
         self.t += 1
         if self.t == self.t_max:                                 # agent.py:162-163
             self.batch_update(is_chief)

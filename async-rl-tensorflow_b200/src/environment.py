@@ -326,15 +326,19 @@ class GymEnvironment(Environment):
         84x84 screen so that History.add can run preprocess+push as one kernel."""
         start_lives = self.lives.clone()
         if self.action_repeat == 1:
-            # config.py:50 default: the loop body once, without the masks that only matter from
-            # the second repeat on (same arithmetic, 5 small launches instead of 14)
+            # config.py:50 default: the loop body once; the life-loss rule of environment.py:86-88
+            # is one kernel (arl_act_update) writing into two alternating result buffers
             self._step(action)
-            cumulated, done = self.reward, self.terminal
-            if is_training:
-                lost = start_lives > self.lives                   # environment.py:86-88
-                cumulated = cumulated - lost.float()
-                done = done | lost
-            self.reward, self.terminal = cumulated, done
+            k = self._act_k = getattr(self, '_act_k', 0) ^ 1
+            if not hasattr(self, '_act_out'):
+                self._act_out = [(torch.empty(self.num_envs, device=self.device),
+                                  torch.empty(self.num_envs, dtype=torch.bool, device=self.device))
+                                 for _ in range(2)]
+            rew, term = self._act_out[k]
+            _cabi.call("arl_act_update", _cabi.ptr(self.reward.float()), _cabi.ptr(self.terminal.bool()),
+                       _cabi.ptr(start_lives), _cabi.ptr(self.lives.int()), 1 if is_training else 0,
+                       _cabi.ptr(rew), _cabi.ptr(term), self.num_envs, _cabi.stream_ptr())
+            self.reward, self.terminal = rew, term
             self.after_act(action)
             if fused:
                 return self.frames, self.reward, self.terminal

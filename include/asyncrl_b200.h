@@ -181,6 +181,17 @@ ARL_API int arl_greedy_actions(const float* scores, int32_t* actions, int num_en
 ARL_API int arl_egreedy_actions(const float* q, int32_t* actions, int num_envs, int action_size, float ep,
                         int64_t env_id_base, int64_t step, uint64_t seed, void* stream);
 
+/* GymEnvironment.act for action_repeat == 1 (environment.py:78-96), batched: with is_training, an
+ * env whose lives dropped during the step loses one reward point and its episode ends
+ * (environment.py:86-88).  step_terminal / terminal are bytes (0/1; torch.bool storage). */
+ARL_API int arl_act_update(const float* step_reward, const uint8_t* step_terminal,
+                   const int32_t* lives_before, const int32_t* lives_after, int is_training,
+                   float* reward, uint8_t* terminal, int num_envs, void* stream);
+/* Agent.observe's rollout append (agent.py:158-160): this step's reward / terminal -> slot t of
+ * the [T,B] rollout buffers (the reward clip of agent.py:154 happens in arl_returns_lossgrad). */
+ARL_API int arl_observe_store(const float* reward, const uint8_t* terminal, float* reward_slot,
+                      uint8_t* terminal_slot, int num_envs, void* stream);
+
 /* agent.py:186-190 + 310-314 (async 1-step Q learning with a target network):
  *   target = clip(r) + (1-terminal) * discount * max_a q_next[n][a]
  *   delta  = target - q[n][actions[n]];   dq[n][a] = -2 * delta * grad_scale  (0 elsewhere)
