@@ -390,6 +390,12 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   const int items = P::num_items(g);
+  // Programmatic dependent launch: everything above (barriers, TMEM, the resident weight image --
+  // written by arl_prepare_weights, never by the kernel just before this one) overlaps the tail of
+  // the previous kernel in the stream; its results are touched only after the wait.  The next
+  // kernel may begin its own prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp >= kEpiWarps && warp < kMmaWarp) {
     // ===================== producers: warp group pg owns stage pg =====================
@@ -558,7 +564,17 @@ int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   }
   if (items <= 0) return ARL_OK;
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, cta_threads<P>(), S::TOTAL, stream>>>(g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(cta_threads<P>());
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ARL_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   ARL_LAUNCH_CHECK("tc_kernel");
   return ARL_OK;
 }

@@ -149,6 +149,9 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     fence_mbar_init();
   }
   __syncthreads();
+  // the next kernel in the stream (conv1 forward, launched with programmatic stream serialization)
+  // may run its prologue on SMs this kernel has left; it waits for this grid before reading the ring
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kComputeWarps) {
