@@ -33,6 +33,25 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int64_t ld, int r
   *reinterpret_cast<uint4*>(d) = h;
   *reinterpret_cast<uint4*>(d + (int64_t)chunks * rows * 16) = l;
 }
+// X fp32 [cols][rows] (row stride ld; i.e. the TRANSPOSE of the matrix to split) -> one split block
+// [part][chunk][row][8 bf16].  Thread = (chunk, row), rows fastest: reads are coalesced over rows.
+__global__ void split_cols_kernel(const float* __restrict__ X, int64_t ld, int rows, int chunks,
+                                  uint8_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * chunks) return;
+  const int c = (int)(idx / rows), row = (int)(idx - (int64_t)c * rows);
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = __ldg(X + (int64_t)(c * 8 + e) * ld + row);
+  uint4 h, l;
+  tc::split2(x[0], x[1], h.x, l.x);
+  tc::split2(x[2], x[3], h.y, l.y);
+  tc::split2(x[4], x[5], h.z, l.z);
+  tc::split2(x[6], x[7], h.w, l.w);
+  uint8_t* d = out + idx * 16;
+  *reinterpret_cast<uint4*>(d) = h;
+  *reinterpret_cast<uint4*>(d + (int64_t)chunks * rows * 16) = l;
+}
 int split_rows(const float* X, int64_t ld, int rows, int chunks, void* out, cudaStream_t st) {
   const int64_t n = (int64_t)rows * chunks;
   if (n == 0) return ARL_OK;
@@ -78,6 +97,55 @@ colsum_split256_kernel(const uint8_t* __restrict__ xs, float* __restrict__ parti
 using FcFwd = tc::BulkGemm<64, 32, false, true, tc::EPI_BIAS_RELU, 8>;
 using FcDgrad = tc::BulkGemm<128, 32, false, false, tc::EPI_MASK, 4>;
 using FcWgrad = tc::BulkGemm<128, 64, true, true, tc::EPI_PLAIN, 3>;
+
+// forward for up to 37 row tiles (one env step): 128 x 256 tiles, split-K over a cluster of 4 CTAs.
+// A CTA ingests (128 + 256) x K/4 operand rows instead of (128 + 64) x K -- half the bytes through
+// its bulk-copy unit -- and in copies of 2 KB (a2 rows) and 4 KB (l4_w TRANSPOSED, K-major: a run =
+// the 256 output columns of one k chunk): the unit needs ~40 cycles per copy whatever its size, so
+// the MN-major l4_w image (512-B runs of 32 k) made this kernel slower than FcFwd.  Each CTA dumps its fp32 partial tile into its
+// own (by then idle) pipeline stages as [float4 column][row]; after a cluster barrier CTA r sums
+// column quarter r of the four partials through distributed shared memory, adds the bias,
+// applies relu and writes h.
+struct FcFwdCluster : tc::BulkGemm<256, 32, false, false, tc::EPI_PLAIN, 4, false> {
+  static constexpr bool CUSTOM_EPI = true;
+  static constexpr int CLUSTER = 4;
+  static __device__ __forceinline__ void custom_epilogue(const Args&, const tc::TileCoord&, const uint8_t* res,
+                                                         uint32_t taddr, int row, EpiPre&, EpiState&) {
+    float4* part = reinterpret_cast<float4*>(const_cast<uint8_t*>(res) - STAGES * STAGE_BYTES);
+#pragma unroll 4
+    for (int c8 = 0; c8 < N_TILE / 8; ++c8) {
+      float v[8];
+      tc::tmem_ld8(taddr + c8 * 8, v);
+      part[(2 * c8) * tc::kTileM + row] = make_float4(v[0], v[1], v[2], v[3]);
+      part[(2 * c8 + 1) * tc::kTileM + row] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  static __device__ __forceinline__ void cluster_reduce(const Args& g, uint8_t* smem, int warp, int lane) {
+    const uint32_t rank = tc::cluster_ctarank();
+    const int row = warp * 32 + lane, m = (int)(blockIdx.x / CLUSTER) * tc::kTileM + row;
+    const uint32_t base = smem_u32(smem);
+    uint32_t peer[CLUSTER];
+#pragma unroll
+    for (int r = 0; r < CLUSTER; ++r) peer[r] = tc::dsmem_addr(base, (uint32_t)r);
+    constexpr int Q4 = N_TILE / 4 / CLUSTER;                       // float4 columns per CTA
+#pragma unroll 2
+    for (int j = 0; j < Q4; ++j) {
+      const int c4 = (int)rank * Q4 + j;
+      const uint32_t off = (uint32_t)(c4 * tc::kTileM + row) * 16u;
+      float4 a = tc::dsmem_ld4(peer[0] + off);
+#pragma unroll
+      for (int r = 1; r < CLUSTER; ++r) {                          // fixed order: deterministic
+        const float4 b = tc::dsmem_ld4(peer[r] + off);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      const float4 bb = tc::ldg4(g.bias + c4 * 4);
+      if (m < g.M)
+        *reinterpret_cast<float4*>(g.D + (int64_t)m * g.ldd + c4 * 4) =
+            make_float4(fmaxf(a.x + bb.x, 0.f), fmaxf(a.y + bb.y, 0.f), fmaxf(a.z + bb.z, 0.f),
+                        fmaxf(a.w + bb.w, 0.f));
+    }
+  }
+};
 
 template <class P>
 int run_gemm(tc::BulkGemmArgs& g, int k_splits, cudaStream_t st) {
@@ -161,6 +229,13 @@ extern "C" int arl_prepare_weights(const float* params, float* prepared, void* s
   int rc = split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8,
                       reinterpret_cast<uint8_t*>(prepared) + kPrepFcW, (cudaStream_t)stream);
   if (rc) return rc;
+  {   // l4_w^T [256][2592] for the K-major B operand of the clustered forward
+    const int64_t n = (int64_t)ARL_FC * (ARL_A2_ELEMS / 8);
+    split_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        params + L.off[T_L4W], ARL_FC, ARL_FC, ARL_A2_ELEMS / 8,
+        reinterpret_cast<uint8_t*>(prepared) + kPrepFcWT);
+    ARL_LAUNCH_CHECK("split_cols_kernel");
+  }
   return conv_prepare(params, prepared, (cudaStream_t)stream);
 }
 
@@ -179,6 +254,11 @@ extern "C" int arl_fc_forward(const float* params, const float* prepared, const 
   g.mask = mat(nullptr, 0, 1, 0);
   g.D = h; g.bias = params + L.off[T_L4B];
   g.M = M; g.N = ARL_FC; g.K = ARL_A2_ELEMS; g.ldd = ARL_FC;
+  // one env step of up to 37 row tiles: 4-CTA clusters, one split-K slice per CTA
+  if ((M + tc::kTileM - 1) / tc::kTileM * FcFwdCluster::CLUSTER <= num_sms()) {
+    g.B = mat(reinterpret_cast<const uint8_t*>(prepared) + kPrepFcWT, ARL_FC, ARL_FC, ARL_A2_ELEMS / 8);
+    return run_gemm<FcFwdCluster>(g, FcFwdCluster::CLUSTER, (cudaStream_t)stream);
+  }
   return run_gemm<FcFwd>(g, 1, (cudaStream_t)stream);
 }
 

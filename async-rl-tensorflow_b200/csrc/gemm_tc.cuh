@@ -173,6 +173,28 @@ __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr_a, uint32_t taddr_b
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
 }
 
+// ---- thread-block clusters: barrier + distributed shared memory -------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t cta_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // instruction descriptor: bf16 x bf16 -> f32, M=128; operands K-major unless *_mn
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -254,6 +276,12 @@ struct PolicyBase {
   // accumulator is waited for (operands the finishing op needs from HBM); EpiState = per-thread
   // state that lives across the tiles of the CTA (epi_begin / epi_end), e.g. running column sums
   static constexpr bool CUSTOM_EPI = false;
+  // CLUSTER > 1: the CTAs of a cluster work on split-K slices of ONE tile (one work item per CTA);
+  // custom_epilogue leaves each CTA's partial in its own shared memory and, after a cluster
+  // barrier, cluster_reduce (epilogue warps) combines them through distributed shared memory
+  static constexpr int CLUSTER = 1;
+  template <class Args>
+  static __device__ __forceinline__ void cluster_reduce(const Args&, uint8_t*, int, int) {}
   struct EpiPre {};
   struct EpiState {};
   template <class Args, class Pre>
@@ -544,6 +572,13 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     P::epi_end(g, est, warp, lane);
   }
 
+  if constexpr (P::CLUSTER > 1) {
+    __syncwarp();                                        // (the MMA warp ran its loop on one lane)
+    cluster_sync_all();                                  // every CTA's partial is in its shared memory
+    if (warp < kEpiWarps) P::cluster_reduce(g, smem, warp, lane);
+    cluster_sync_all();                                  // nobody reads a peer's shared memory after this
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -569,11 +604,22 @@ int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   cfg.blockDim = dim3(cta_threads<P>());
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (P::CLUSTER > 1) {
+    if (items > grid || grid % P::CLUSTER != 0) {
+      set_error("tc::launch: a cluster policy needs one work item per CTA and whole clusters (%d items)", items);
+      return ARL_ERR_INVALID;
+    }
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = P::CLUSTER;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   ARL_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   ARL_LAUNCH_CHECK("tc_kernel");
   return ARL_OK;
@@ -630,11 +676,12 @@ struct BulkGemmArgs {
 // D[128 x NT] += A . B^T with the three bf16 products of the split:  A_hi.[B_hi | B_lo] as ONE MMA
 // of width 2*NT (the lo image of B sits right behind its hi image along N) and A_lo.B_hi of
 // width NT; output column c = acc[c] + acc[c + NT].
-template <int NT, int KB_, bool A_MN, bool B_MN, int EPI, int STAGES_>
+// CONCAT = false (NT up to 256): three MMAs of width NT into the same NT accumulator columns.
+template <int NT, int KB_, bool A_MN, bool B_MN, int EPI, int STAGES_, bool CONCAT = true>
 struct BulkGemm : PolicyBase {
   using Args = BulkGemmArgs;
   static constexpr int N_TILE = NT, KB = KB_, STAGES = STAGES_, PROD_WARPS = STAGES_;   // one warp per stage
-  static constexpr int ACC_COLS = 2 * NT, OUT_COLS = NT, LO_DELTA = NT, SEG = 32;
+  static constexpr int ACC_COLS = CONCAT ? 2 * NT : NT, OUT_COLS = NT, LO_DELTA = CONCAT ? NT : 0, SEG = 32;
   static constexpr bool HAS_AUX = EPI == EPI_BIAS_RELU, AUX_ROW_INVARIANT = true;
   static constexpr bool HAS_PRE = EPI == EPI_MASK;
   static constexpr int EPI_SETS = EPI == EPI_MASK ? 2 : 1;
@@ -735,7 +782,7 @@ struct BulkGemm : PolicyBase {
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st, uint32_t,
                                                uint32_t d_tmem) {
-    constexpr uint32_t idesc2 = make_idesc(2 * NT, A_MN, B_MN), idesc1 = make_idesc(NT, A_MN, B_MN);
+    constexpr uint32_t idesc2 = make_idesc(CONCAT ? 2 * NT : NT, A_MN, B_MN), idesc1 = make_idesc(NT, A_MN, B_MN);
 #pragma unroll
     for (int k16 = 0; k16 < KB / 16; ++k16) {
       const uint32_t a = st + (A_MN ? k16 * 256 : k16 * 2 * A_PLANE);
@@ -743,8 +790,16 @@ struct BulkGemm : PolicyBase {
       const uint64_t da_hi = A_MN ? make_sdesc(a, 128, A_PLANE) : make_sdesc(a, A_PLANE);
       const uint64_t da_lo = A_MN ? make_sdesc(a + A_PART, 128, A_PLANE) : make_sdesc(a + A_PART, A_PLANE);
       const uint64_t db = B_MN ? make_sdesc(b, 128, B_PLANE) : make_sdesc(b, B_PLANE);
-      umma_f16(d_tmem, da_hi, db, idesc2, (s | k16) != 0 ? 1u : 0u);     // a_hi . [b_hi | b_lo]
-      umma_f16(d_tmem, da_lo, db, idesc1, 1u);                            // a_lo . b_hi
+      if (CONCAT) {
+        umma_f16(d_tmem, da_hi, db, idesc2, (s | k16) != 0 ? 1u : 0u);   // a_hi . [b_hi | b_lo]
+        umma_f16(d_tmem, da_lo, db, idesc1, 1u);                          // a_lo . b_hi
+      } else {
+        const uint32_t bl = b + (B_MN ? (NT / 8) * B_PLANE : NT * 16);    // the lo image follows the hi image
+        const uint64_t db_lo = B_MN ? make_sdesc(bl, 128, B_PLANE) : make_sdesc(bl, B_PLANE);
+        umma_f16(d_tmem, da_hi, db, idesc1, (s | k16) != 0 ? 1u : 0u);   // a_hi . b_hi
+        umma_f16(d_tmem, da_hi, db_lo, idesc1, 1u);                       // a_hi . b_lo
+        umma_f16(d_tmem, da_lo, db, idesc1, 1u);                          // a_lo . b_hi
+      }
     }
   }
   // ---- epilogue: row m of the tile is NT contiguous floats of D
