@@ -6,8 +6,9 @@
 //   forward : h    = relu(a2 [N,2592] . W [2592,256] + b)     A = a2s (K-major), B = Ws (MN-major)
 //   dgrad   : d_a2 = (d_h [N,256] . W^T) * (a2 > 0)           A = dhs (K-major), B = Ws (K-major),
 //                                                             mask = sign of a2s' hi part
-//   wgrad   : dW   = a2^T [2592,N] . d_h [N,256]              A = a2s, B = dhs (both MN-major: k =
-//             sample); split-K over samples, partials summed in a fixed order (deterministic)
+//   wgrad   : dW   = a2^T [2592,N] . d_h [N,256]              A = a2s (MN-major: k = sample), B = dhsT
+//             (d_h's transposed copy, K-major over samples: 4 KB runs); split-K over samples,
+//             partials summed in a fixed order (deterministic)
 //   bgrad   : db   = column sums of d_h
 #include "gemm_tc.cuh"
 
@@ -35,14 +36,14 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int64_t ld, int r
 }
 // X fp32 [cols][rows] (row stride ld; i.e. the TRANSPOSE of the matrix to split) -> one split block
 // [part][chunk][row][8 bf16].  Thread = (chunk, row), rows fastest: reads are coalesced over rows.
-__global__ void split_cols_kernel(const float* __restrict__ X, int64_t ld, int rows, int chunks,
+__global__ void split_cols_kernel(const float* __restrict__ X, int64_t ld, int rows, int chunks, int cols,
                                   uint8_t* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * chunks) return;
   const int c = (int)(idx / rows), row = (int)(idx - (int64_t)c * rows);
   float x[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) x[e] = __ldg(X + (int64_t)(c * 8 + e) * ld + row);
+  for (int e = 0; e < 8; ++e) x[e] = c * 8 + e < cols ? __ldg(X + (int64_t)(c * 8 + e) * ld + row) : 0.f;
   uint4 h, l;
   tc::split2(x[0], x[1], h.x, l.x);
   tc::split2(x[2], x[3], h.y, l.y);
@@ -51,6 +52,14 @@ __global__ void split_cols_kernel(const float* __restrict__ X, int64_t ld, int r
   uint8_t* d = out + idx * 16;
   *reinterpret_cast<uint4*>(d) = h;
   *reinterpret_cast<uint4*>(d + (int64_t)chunks * rows * 16) = l;
+}
+int split_cols(const float* X, int64_t ld, int rows, int cols, void* out, cudaStream_t st) {
+  const int chunks = (cols + 7) / 8;
+  const int64_t n = (int64_t)rows * chunks;
+  if (n == 0) return ARL_OK;
+  split_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, ld, rows, chunks, cols, (uint8_t*)out);
+  ARL_LAUNCH_CHECK("split_cols_kernel");
+  return ARL_OK;
 }
 int split_rows(const float* X, int64_t ld, int rows, int chunks, void* out, cudaStream_t st) {
   const int64_t n = (int64_t)rows * chunks;
@@ -96,7 +105,10 @@ colsum_split256_kernel(const uint8_t* __restrict__ xs, float* __restrict__ parti
 // pipe: 64 CTAs of 128 x 128 tiles move 2/3 of the bytes and take 1.6x as long (measured).
 using FcFwd = tc::BulkGemm<64, 32, false, true, tc::EPI_BIAS_RELU, 8>;
 using FcDgrad = tc::BulkGemm<128, 32, false, false, tc::EPI_MASK, 4>;
-using FcWgrad = tc::BulkGemm<128, 64, true, true, tc::EPI_PLAIN, 3>;
+// wgrad: 128 x 256 tiles (all of d_h's columns: l4_w's gradient rows are read once), three N = 256
+// MMAs per 16 samples; B comes from d_h's transposed copy in 4 KB runs (8 per stage) instead of 64
+// runs of 1 KB: the bulk-copy unit costs ~40 cycles per copy (122 -> @ us)
+using FcWgrad = tc::BulkGemm<256, 32, true, false, tc::EPI_PLAIN, 4, false>;
 
 // forward for up to 37 row tiles (one env step): 128 x 256 tiles, split-K over a cluster of 4 CTAs.
 // A CTA ingests (128 + 256) x K/4 operand rows instead of (128 + 64) x K -- half the bytes through
@@ -194,16 +206,22 @@ extern "C" int arl_debug_gemm(int variant, const float* A, const float* B, float
   // stored shapes [rows][cols] of A, B (and the mask)
   const int ar = variant >= 3 ? K : M, ac = variant >= 3 ? M : K;
   const int br = variant == 2 ? N : K, bc = variant == 2 ? K : N;
+  const int k8 = (K + 7) / 8 * 8;
   uint8_t *as = nullptr, *bs = nullptr, *ms = nullptr;
   ARL_CUDA(cudaMalloc(&as, (size_t)ar * ac * 4));
-  ARL_CUDA(cudaMalloc(&bs, (size_t)br * bc * 4));
+  ARL_CUDA(cudaMalloc(&bs, (size_t)(variant >= 3 ? k8 : br) * bc * 4));
   if (variant == 2) ARL_CUDA(cudaMalloc(&ms, (size_t)M * N * 4));
   int rc = split_rows(A, ac, ar, ac / 8, as, st);
-  if (!rc) rc = split_rows(B, bc, br, bc / 8, bs, st);
-  if (!rc && variant == 2) rc = split_rows(extra, N, M, N / 8, ms, st);
   tc::BulkGemmArgs g;
   g.A = mat(as, ar, ar, ac / 8);
-  g.B = mat(bs, br, br, bc / 8);
+  if (variant >= 3) {          // the wgrad's B is K-major over the samples: the transposed split of B [K][N]
+    if (!rc) rc = split_cols(B, N, N, K, bs, st);
+    g.B = mat(bs, N, N, k8 / 8);
+  } else {
+    if (!rc) rc = split_rows(B, bc, br, bc / 8, bs, st);
+    g.B = mat(bs, br, br, bc / 8);
+  }
+  if (!rc && variant == 2) rc = split_rows(extra, N, M, N / 8, ms, st);
   g.mask = mat(ms, M, M, N / 8);
   g.D = D; g.bias = extra; g.M = M; g.N = N; g.K = K; g.ldd = N;
   if (!rc) {
@@ -229,13 +247,10 @@ extern "C" int arl_prepare_weights(const float* params, float* prepared, void* s
   int rc = split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8,
                       reinterpret_cast<uint8_t*>(prepared) + kPrepFcW, (cudaStream_t)stream);
   if (rc) return rc;
-  {   // l4_w^T [256][2592] for the K-major B operand of the clustered forward
-    const int64_t n = (int64_t)ARL_FC * (ARL_A2_ELEMS / 8);
-    split_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        params + L.off[T_L4W], ARL_FC, ARL_FC, ARL_A2_ELEMS / 8,
-        reinterpret_cast<uint8_t*>(prepared) + kPrepFcWT);
-    ARL_LAUNCH_CHECK("split_cols_kernel");
-  }
+  // l4_w^T [256][2592] for the K-major B operand of the clustered forward
+  rc = split_cols(params + L.off[T_L4W], ARL_FC, ARL_FC, ARL_A2_ELEMS,
+                  reinterpret_cast<uint8_t*>(prepared) + kPrepFcWT, (cudaStream_t)stream);
+  if (rc) return rc;
   return conv_prepare(params, prepared, (cudaStream_t)stream);
 }
 
@@ -284,6 +299,9 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   const int M = (int)num_samples;
   const tc::SplitMat a2s = mat(a2, M, (int)a2_block_rows, ARL_A2_ELEMS / 8);
   const tc::SplitMat dhs = mat(d_h, M, M, ARL_FC / 8);
+  // the transposed copy follows the block: rows = the 256 columns of d_h, chunks = groups of 8 samples
+  const tc::SplitMat dhsT = mat(reinterpret_cast<const uint8_t*>(d_h) + (size_t)M * ARL_FC * sizeof(float),
+                                ARL_FC, ARL_FC, (M + 7) / 8);
   const tc::SplitMat ws = mat(prepared, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
   // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
   tc::BulkGemmArgs g;
@@ -292,9 +310,9 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   g.M = M; g.N = ARL_A2_ELEMS; g.K = ARL_FC; g.ldd = ARL_A2_ELEMS;
   int rc = run_gemm<FcDgrad>(g, 1, st);
   if (rc) return rc;
-  // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles x 2 column tiles = 294 items
+  // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles = 147 items
   float* part = (float*)workspace;
-  g.A = a2s; g.B = dhs; g.mask = mat(nullptr, 0, 1, 0);
+  g.A = a2s; g.B = dhsT; g.mask = mat(nullptr, 0, 1, 0);
   g.D = part;
   g.M = ARL_A2_ELEMS; g.N = ARL_FC; g.K = M; g.ldd = ARL_FC;
   rc = run_gemm<FcWgrad>(g, 7, st);

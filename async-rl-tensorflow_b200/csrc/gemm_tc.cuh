@@ -722,7 +722,7 @@ struct BulkGemm : PolicyBase {
       for (int i = glane; i < 2 * RA * nk; i += gsize)
         *reinterpret_cast<uint4*>(st + (i / nk) * A_PLANE + (kvalid + i % nk) * 16) = z;
     } else {
-      const int c0 = kvalid / 8, nc = KB / 8 - c0;
+      const int c0 = (kvalid + 7) / 8, nc = KB / 8 - c0;          // a partly valid chunk is copied (its tail is zero in HBM)
       for (int i = glane; i < 2 * nc * kTileM; i += gsize) {
         const int part = i / (nc * kTileM), r = i % (nc * kTileM);
         *reinterpret_cast<uint4*>(st + part * A_PART + c0 * A_PLANE + r * 16) = z;
@@ -733,7 +733,7 @@ struct BulkGemm : PolicyBase {
       for (int i = glane; i < 2 * RB * nk; i += gsize)
         *reinterpret_cast<uint4*>(st + B_OFF + (i / nk) * B_PLANE + (kvalid + i % nk) * 16) = z;
     } else {
-      const int c0 = kvalid / 8, nc = KB / 8 - c0;
+      const int c0 = (kvalid + 7) / 8, nc = KB / 8 - c0;
       for (int i = glane; i < nc * 2 * NT; i += gsize)
         *reinterpret_cast<uint4*>(st + B_OFF + c0 * B_PLANE + i * 16) = z;
     }

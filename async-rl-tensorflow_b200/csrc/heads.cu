@@ -266,17 +266,20 @@ __global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
 // CTA = 256 threads (thread k owns hidden unit k).  Per sample: d_h[n][k] = (h>0) * sum_j
 // dz[n][j]*Wcat[k][j];  dWcat[k][j] += h[n][k]*dz[n][j];  dbcat[j] += dz[n][j].
 // Partials per CTA -> workspace [grid][256*J + J], reduced deterministically afterwards.
-// d_h leaves as split bf16 in 16-byte chunk vectors, one block of num_samples rows
-// ([hi|lo][32 chunks][num_samples][8], gemm_tc.cuh SplitMat): the layout the fc256 backward kernels
-// fetch with cp.async.bulk.  32 samples are staged in shared memory so that a warp writes the 32
-// consecutive rows of one chunk = 512 contiguous bytes.
+// d_h leaves as split bf16 in 16-byte chunk vectors (gemm_tc.cuh SplitMat), TWICE, because its two
+// consumers reduce over different axes and a bulk copy wants long contiguous runs:
+//   dhs  [hi|lo][32 column chunks][num_samples rows][8 columns]   fc dgrad's A operand (K-major)
+//   dhsT [hi|lo][ceil(N/8) sample chunks][256 column rows][8 samples]   fc wgrad's B operand
+//        (K-major over samples: one run = all 256 columns of 8 samples = 4 KB; samples >= N zero)
+// 32 samples are staged in shared memory so that a warp writes 512 contiguous bytes either way.
 constexpr int kHbChunk = 64, kHbSub = 32;
 template <int JMAX>
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
                  const float* __restrict__ h, const float* __restrict__ dlogits,
                  const float* __restrict__ dvalue, uint8_t* __restrict__ dhs,
-                 float* __restrict__ partials, int64_t num_samples, int A) {
+                 uint8_t* __restrict__ dhsT, float* __restrict__ partials, int64_t num_samples,
+                 int64_t per, int A) {
   __shared__ float dzs[kHbChunk][JMAX];
   __shared__ float dt[kHbSub][257];
   const int J = A + 1;
@@ -288,10 +291,10 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
     acc[j] = 0.f;
   }
   float bacc = 0.f;                                   // thread j < J: sum of dz[:, j]
-  const int64_t per = (num_samples + gridDim.x - 1) / gridDim.x;
-  const int64_t beg = per * blockIdx.x;
+  const int64_t beg = per * blockIdx.x;                // per is a multiple of 8: sample chunks are not split
   const int64_t end = beg + per < num_samples ? beg + per : num_samples;
   const int64_t lo_part = (int64_t)32 * num_samples * 16;
+  const int64_t lo_partT = ((num_samples + 7) / 8) * 256 * 16;
   for (int64_t c0 = beg; c0 < end; c0 += kHbChunk) {
     const int nc = (int)(end - c0 < kHbChunk ? end - c0 : kHbChunk);
     __syncthreads();
@@ -329,6 +332,20 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
           *reinterpret_cast<uint4*>(d) = hi;
           *reinterpret_cast<uint4*>(d + lo_part) = lo;
         }
+      }
+      // transposed copy: thread k = column k of each of the (up to 4) sample chunks
+      for (int sc = 0; sc * 8 < ns; ++sc) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = sc * 8 + e < ns ? dt[sc * 8 + e][k] : 0.f;
+        uint4 hi, lo;
+        tc_split2(x[0], x[1], hi.x, lo.x);
+        tc_split2(x[2], x[3], hi.y, lo.y);
+        tc_split2(x[4], x[5], hi.z, lo.z);
+        tc_split2(x[6], x[7], hi.w, lo.w);
+        uint8_t* d = dhsT + (((c0 + s0) / 8 + sc) * 256 + k) * 16;
+        *reinterpret_cast<uint4*>(d) = hi;
+        *reinterpret_cast<uint4*>(d + lo_partT) = lo;
       }
       __syncthreads();
     }
@@ -526,19 +543,22 @@ extern "C" int arl_heads_backward(const float* params, int action_size, const fl
   int grid = 2 * num_sms();
   if ((int64_t)grid > (num_samples + kHbChunk - 1) / kHbChunk)
     grid = (int)((num_samples + kHbChunk - 1) / kHbChunk);
-  // empty trailing CTAs would write zero partials, which is fine; keep every CTA non-empty anyway
-  const int64_t per = (num_samples + grid - 1) / grid;
+  // empty trailing CTAs would write zero partials, which is fine; keep every CTA non-empty anyway.
+  // Whole sample chunks (8) per CTA: the transposed copy of d_h is written chunk by chunk.
+  const int64_t per = ((num_samples + grid - 1) / grid + 7) / 8 * 8;
   grid = (int)((num_samples + per - 1) / per);
   float* part = (float*)workspace;
+  uint8_t* dhs = (uint8_t*)d_h;
+  uint8_t* dhsT = dhs + (size_t)num_samples * 256 * sizeof(float);
   if (J <= 8)
     heads_bwd_kernel<8><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
-                                             dvalue, (uint8_t*)d_h, part, num_samples, A);
+                                             dvalue, dhs, dhsT, part, num_samples, per, A);
   else if (J <= 20)
     heads_bwd_kernel<20><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h,
-                                              dlogits, dvalue, (uint8_t*)d_h, part, num_samples, A);
+                                              dlogits, dvalue, dhs, dhsT, part, num_samples, per, A);
   else
     heads_bwd_kernel<ARL_MAX_ACTIONS + 1><<<grid, 256, 0, st>>>(
-        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, (uint8_t*)d_h, part, num_samples, A);
+        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, dhs, dhsT, part, num_samples, per, A);
   ARL_LAUNCH_CHECK("heads_bwd_kernel");
   return reduce_partials(part, g, grid, 256 * J + J, st);
 }

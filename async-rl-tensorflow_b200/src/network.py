@@ -132,7 +132,9 @@ class Network(object):
         # backward scratch
         self.d_logits = torch.empty(N, A, **f32)
         self.d_value = torch.empty(N, **f32)
-        self.d_l4 = torch.empty(N, FC, **f32)                 # one split block: see d_h()
+        # d_h twice (include/asyncrl_b200.h): a split block of N rows, then its transposed copy
+        # (groups of 8 samples x 256 columns) for the fc256 weight gradient: see d_h()
+        self.d_l4 = torch.empty(N + (N + 7) // 8 * 8, FC, **f32)
         self.d_l2 = torch.empty(N, A2_ELEMS, **f32)
         self.d_l1 = torch.empty(N, DA1_ELEMS, **f32)          # split bf16 on the 21x21 grid: see decode_da1
         self.workspace = torch.empty(_cabi.workspace_bytes(A), dtype=torch.uint8, device=dev)
@@ -219,7 +221,15 @@ class Network(object):
 
     def d_h(self):
         """Gradient w.r.t. the fc256 output of the last backward as float32 [N,256]."""
-        return decode_split(self.d_l4, self.d_l4.shape[0], FC)
+        N = self.num_envs * self.t_max
+        return decode_split(self.d_l4[:N], N, FC)
+
+    def d_h_transposed(self):
+        """The same gradient decoded from its second, transposed copy (what fc wgrad reads)."""
+        N = self.num_envs * self.t_max
+        n8 = (N + 7) // 8 * 8
+        b = self.d_l4[N:].reshape(-1).view(torch.bfloat16).reshape(2, n8 // 8, FC, 8)
+        return (b[0].float() + b[1].float()).permute(0, 2, 1).reshape(n8, FC)[:N]
 
     def sample(self, t, step, seed, env_id_base=0):
         """network.py:72-73 sampled_action for rollout slot t."""

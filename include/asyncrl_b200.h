@@ -30,8 +30,10 @@
  *     as the f32 matrix), which the tcgen05 kernels fetch with cp.async.bulk and never convert:
  *       a2  (the f32 [N,2592]-sized buffer): one block per arl_conv2_forward call, rows = the
  *           call's num_samples, 324 chunks in NHWC-flatten order (agent.py:231-232);
- *       d_h (the f32 [N,256]-sized buffer): one block of N rows, 32 chunks, written by
- *           arl_heads_backward;
+ *       d_h ((N + roundup8(N)) * 256 floats): one block of N rows, 32 chunks, followed by its
+ *           transposed copy -- a block of 256 rows (the columns of d_h) with one chunk per 8
+ *           samples, samples >= N zero -- both written by arl_heads_backward: fc dgrad reduces
+ *           over the columns, fc wgrad over the samples, and each gets contiguous KB-sized runs;
  *       l4_w: one block of 2592 rows, 32 chunks, at the start of the `prepared` buffer.
  *   - `prepared` (arl_prepared_floats() floats, written by arl_prepare_weights) holds the weights in
  *     the form the tensor-core kernels keep resident: l4_w as a split block, l1_w as three s8
@@ -218,7 +220,7 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
 /* ---- backward: agent.py:317 compute_gradients ---------------------------------------
  * Accumulation over the T steps of Algorithm 3 is the reduction over samples inside the
  * weight-gradient kernels.  grads is the flat buffer (overwritten).  Scratch buffers are
- * caller-owned: d_h [N,256] (a split block, see the top of this file), d_a2 [N,2592],
+ * caller-owned: d_h [(N + roundup8(N)),256] (two split blocks, see the top of this file), d_a2 [N,2592],
  * d_a1 [N,ARL_DA1_ELEMS] (grid layout, see the top of this file),
  * workspace >= arl_backward_workspace_bytes.  a2 = the rollout's conv2 outputs as a sequence of
  * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);

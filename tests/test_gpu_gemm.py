@@ -30,7 +30,7 @@ def _run(pkg, variant, M, N, K, k_splits=1, seed=0):
                    pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
     if variant >= 3:
-        kb = 64                                   # FcWgrad::KB (csrc/fc.cu)
+        kb = 32                                   # FcWgrad::KB (csrc/fc.cu)
         per = (K + k_splits - 1) // k_splits
         k_chunk = (per + kb - 1) // kb * kb
         used = (K + k_chunk - 1) // k_chunk

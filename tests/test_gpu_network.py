@@ -196,6 +196,7 @@ def test_backward_gradients_vs_oracle(pkg, cuda, A, B, T):
     assert max(errs.values()) <= REL_TOL, errs
     # the gradients handed from layer to layer, decoded from their device layouts
     N = T * B
+    assert bool((net.d_h() == net.d_h_transposed()).all())     # the two device copies of d_h agree
     ierrs = dict(d_h=rel_err(net.d_h().cpu(), aux["d_h"]), d_a2=rel_err(net.d_l2.cpu(), aux["d_a2"]),
                  d_a1=rel_err(pkg.network.decode_da1(net.d_l1, N).cpu(), aux["d_a1"]))
     print("layer-gradient rel-err", ierrs)

@@ -12,10 +12,10 @@ ENTRY_OF = [
     ("preprocess_kernel", "arl_preprocess_push"),
     ("Conv1Fwd", "arl_conv1_forward"),
     ("Conv2Fwd", "arl_conv2_forward"),
-    ("BulkGemm<64, 32, 0, 1, 1", "arl_fc_forward"),      # (int)/(bool) casts are stripped below
-    ("FcDgrad", "arl_fc_backward"),
-    ("BulkGemm<128, 32, 0, 0, 2", "arl_fc_backward"),
-    ("BulkGemm<128, 64, 1, 1, 0", "arl_fc_backward"),
+    ("FcFwdCluster", "arl_fc_forward"),                  # (int)/(bool) casts are stripped below
+    ("BulkGemm<128, 32, 0, 0, 2", "arl_fc_backward"),    # fc dgrad
+    ("BulkGemm<128, 64, 1, 1, 0", "arl_fc_backward"),    # fc wgrad (earlier form)
+    ("BulkGemm<256, 32, 1, 0, 0", "arl_fc_backward"),    # fc wgrad
     ("Conv2Wgrad", "arl_conv2_backward"),
     ("Conv2Dgrad", "arl_conv2_backward"),
     ("Conv1Wgrad", "arl_conv1_backward"),
