@@ -503,7 +503,18 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       if constexpr (P::HAS_PRE) prow = P::pre_row(g, tc, quad * 32 + lane);
       __syncwarp();
       bool waited = false;
-#pragma unroll 1
+      // HAS_PRE: the whole tile's mask vectors are requested before the accumulator is waited for
+      // (per-segment requests left three exposed load latencies per tile); the segment loop is
+      // then fully unrolled so that they stay in registers
+      uint4 pmall[P::HAS_PRE ? NSEG : 1][SEG / 8];
+      if constexpr (P::HAS_PRE) {
+#pragma unroll
+        for (int sg = 0; sg < NSEG; ++sg) {
+#pragma unroll
+          for (int h = 0; h < SEG / 8; ++h) pmall[sg][h] = P::pre_load(g, tc, prow, sg * SEG + h * 8);
+        }
+      }
+#pragma unroll(P::HAS_PRE ? NSEG : 1)
       for (int sg = 0; sg < NSEG; ++sg) {
         if (!P::seg_valid(g, tc, sg)) continue;
         // (1) destination of every float4 this lane will write + the operand its finishing op
@@ -524,11 +535,6 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
 #pragma unroll
           for (int i = 0; i < NI; ++i) aux[i] = a;
         }
-        uint4 pm[SEG / 8];
-        if constexpr (P::HAS_PRE) {
-#pragma unroll
-          for (int h = 0; h < SEG / 8; ++h) pm[h] = P::pre_load(g, tc, prow, sg * SEG + h * 8);
-        }
         if (!waited) {
           mbar_wait_backoff<64>(&tfull[acc], acc_phase);
           tc_fence_after();
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
             tmem_ld8_limbs3(ta, ta + P::LO_DELTA, ta + 2 * P::LO_DELTA, sc[0], sc[1], sc[2], v);
           } else if (P::LO_DELTA > 0) tmem_ld8_sum(ta, ta + P::LO_DELTA, v);
           else tmem_ld8(ta, v);
-          if constexpr (P::HAS_PRE) P::pre_apply(v, pm[h]);
+          if constexpr (P::HAS_PRE) P::pre_apply(v, pmall[sg][h]);
           float4* d = reinterpret_cast<float4*>(stg + lane * (SEG + 4) + h * 8);
           d[0] = make_float4(v[0], v[1], v[2], v[3]);
           d[1] = make_float4(v[4], v[5], v[6], v[7]);
