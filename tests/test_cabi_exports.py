@@ -60,3 +60,34 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "/root/reference" not in txt, f
+
+
+def test_ctypes_prototypes_match_the_header(pkg):
+    """Every prototype in _cabi.SIGNATURES has the argument count and the pointer / integer /
+    float kinds of its declaration in include/asyncrl_b200.h (a drifted ctypes table corrupts
+    the call frame silently)."""
+    src = open(os.path.join(ROOT, "include", "asyncrl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict((m.group(1), m.group(2)) for m in
+                 re.finditer(r"ARL_API\s+int\s+(arl_\w+)\s*\(([^;]*?)\)\s*;", src, re.S))
+    kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64",
+            ctypes.c_uint64: "u64", ctypes.c_float: "f32"}
+
+    def ckind(param):
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        if p.startswith("float"):
+            return "f32"
+        if p.startswith("int64_t"):
+            return "i64"
+        if p.startswith("uint64_t"):
+            return "u64"
+        assert p.startswith("int "), p
+        return "int"
+
+    for name, argtypes in pkg._cabi.SIGNATURES.items():
+        params = [p for p in decls[name].split(",") if p.strip() and p.strip() != "void"]
+        got = ["ptr" if isinstance(a, type) and issubclass(a, ctypes._Pointer) else kind[a]
+               for a in argtypes]
+        assert got == [ckind(p) for p in params], (name, got, params)
