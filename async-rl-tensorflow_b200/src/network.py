@@ -40,6 +40,18 @@ def decode_split(raw, rows, cols):
     return (b[0].float() + b[1].float()).permute(1, 0, 2).reshape(rows, cols)
 
 
+def encode_split(x):
+    """float32 [rows, cols] -> the split block decode_split reads (same element count, float32
+    storage): hi = bf16(x), lo = bf16(x - hi).  Host-side helper for feeding a plain activation
+    matrix to a kernel that expects a block (ops.linear(..., input_is_split=False)) and for tests;
+    the kernels write blocks themselves."""
+    rows, cols = x.shape
+    hi = x.float().to(torch.bfloat16)
+    lo = (x.float() - hi.float()).to(torch.bfloat16)
+    b = torch.stack([hi, lo]).reshape(2, rows, cols // 8, 8).permute(0, 2, 1, 3).contiguous()
+    return b.view(torch.float32).reshape(rows, cols)
+
+
 def decode_da1(raw, n):
     """The gradient w.r.t. conv1's output (include/asyncrl_b200.h: split bf16 on the 21x21 grid,
     [hi|lo][2 channel groups][n*441 + y*21 + x][8]) -> float32 [n,20,20,16]."""

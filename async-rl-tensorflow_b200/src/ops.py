@@ -46,10 +46,15 @@ def conv2d(x, params, output_dim, kernel_size, stride, out=None, name='l1', step
                               "(16,[8,8],[4,4]) and (32,[4,4],[2,2])" % name)
 
 
-def linear(input_, params, output_size, out=None, name='l4'):
-    """ops.py:32-46.  name='l4': relu(x.W + b), [N,2592] -> [N,256] (agent.py:251)."""
+def linear(input_, params, output_size, out=None, name='l4', input_is_split=True):
+    """ops.py:32-46.  name='l4': relu(x.W + b), [N,2592] -> [N,256] (agent.py:251).  ``input_`` is
+    what conv2d(name='l2') returned (a split block, include/asyncrl_b200.h); pass
+    ``input_is_split=False`` for a plain float32 [N,2592] matrix (it is encoded on the host)."""
     if name == 'l4' and output_size == FC:
         x = input_.reshape(input_.shape[0], -1)
+        if not input_is_split:
+            from .network import encode_split
+            x = encode_split(x)
         n = x.shape[0]
         if out is None:
             out = torch.empty(n, FC, device=params.device)

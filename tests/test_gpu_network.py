@@ -89,6 +89,9 @@ def test_ops_wrappers_layer_by_layer(pkg, cuda):
     l1 = ops.conv2d(hist, flat, 16, [8, 8], [4, 4], name='l1')
     l2 = ops.conv2d(l1, flat, 32, [4, 4], [2, 2], name='l2')
     l4 = ops.linear(l2, flat, 256, name='l4')
+    # a plain float32 activation matrix is accepted too (encoded into a split block on the host)
+    l4_plain = ops.linear(pkg.network.decode_split(l2, B, 2592), flat, 256, name='l4', input_is_split=False)
+    assert rel_err(l4_plain.cpu(), l4.cpu().numpy()) <= 1e-6
     lg, pr, v = ops.heads(l4, flat, A)
     act = ops.batch_sample(pr, step=5, seed=123, env_id_base=10)
     torch.cuda.synchronize()

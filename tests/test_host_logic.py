@@ -77,3 +77,19 @@ def test_gym_vector_adapter_host_logic(pkg):
     assert envs[0].resets == 2 and envs[1].resets == 1
     assert np.array_equal(f3[1].numpy(), f2[1].numpy()) and np.array_equal(f3[0].numpy(), envs[0].frames[-1])
     assert len(ad.action_space.sample()) == 3
+
+
+def test_split_block_encode_decode_round_trip(pkg):
+    """The bf16 hi+lo block layout of the fc256 operands (include/asyncrl_b200.h): decode(encode(x))
+    reproduces x to 2^-16 relative, and the block is [hi|lo][chunk of 8 columns][row][8]."""
+    import torch
+    net = pkg.network
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 64, generator=g) * 3.0
+    blk = net.encode_split(x)
+    assert blk.shape == x.shape and blk.dtype == torch.float32
+    y = net.decode_split(blk, 37, 64)
+    assert float((y - x).abs().max() / x.abs().max()) < 2.0 ** -16
+    raw = blk.reshape(-1).view(torch.bfloat16).reshape(2, 8, 37, 8)
+    assert bool((raw[0, 3, 5].float() == x[5, 24:32].to(torch.bfloat16).float()).all())
+    assert float((raw[0].float() + raw[1].float() - x.reshape(37, 8, 8).permute(1, 0, 2)).abs().max()) < 1e-4
