@@ -172,7 +172,7 @@ __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr
       const int un = u0 + u * gsize;
       if (un >= TOTAL) break;
       const int c = un / ROWS, r = un - c * ROWS;
-      const uint4 lo2 = tc::bytes8_to_f16(w[u].x, w[u].y), hi2 = tc::bytes8_to_f16(w[u].z, w[u].w);
+      const uint4 lo2 = tc::bytes8_to_bf16(w[u].x, w[u].y), hi2 = tc::bytes8_to_bf16(w[u].z, w[u].w);
       uint8_t* d = img + (2 * c) * PL + r * 16;
       *reinterpret_cast<uint4*>(d) = lo2;
       *reinterpret_cast<uint4*>(d + PL) = hi2;
@@ -793,8 +793,7 @@ struct Conv1Wgrad : tc::PolicyBase {
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    // x (u8 pixels as exact fp16) . [dy_hi | dy_lo | dy'_hi | dy'_lo] (bf16)
-    constexpr uint32_t idesc = tc::make_idesc(64, true, true, true);
+    constexpr uint32_t idesc = tc::make_idesc(64, true, true);     // x . [dy_hi | dy_lo | dy'_hi | dy'_lo]
     const uint32_t a_img = st, b_hi = st + A_IMG;
 #pragma unroll
     for (int k16 = 0; k16 < 8; ++k16)

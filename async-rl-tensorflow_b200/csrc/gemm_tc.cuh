@@ -196,11 +196,9 @@ __device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
 }
 
 // instruction descriptor: bf16 x bf16 -> f32, M=128; operands K-major unless *_mn
-// (a_f16: the A operand is IEEE fp16 instead of bf16 -- kind::f16 takes the two formats per operand)
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false,
-                                                  bool a_f16 = false) {
-  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
-         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 // instruction descriptor: u8 x s8 -> s32 (kind::i8), M=128, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
@@ -253,24 +251,6 @@ __device__ __forceinline__ uint32_t bytes2bf16x2(uint32_t w, int sel_lo, int sel
   const float b = __uint_as_float(__byte_perm(w, 0x4B000000u, sel_hi)) - 8388608.0f;
   const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&p);
-}
-// 8 bytes -> 8 exact fp16: 0x6400 | byte is 1024 + byte as fp16 (10-bit mantissa), and subtracting
-// 1024 is exact; one PRMT builds two such halves, one HADD2 finishes them (2 instructions per 2
-// bytes instead of 5 for bf16)
-__device__ __forceinline__ uint32_t bytes2_to_f16x2(uint32_t w, int sel) {
-  uint32_t r;
-  const uint32_t v = __byte_perm(w, 0x64646464u, sel);
-  asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0x64006400u));
-  return r;
-}
-__device__ __forceinline__ uint4 bytes8_to_f16(uint32_t w0, uint32_t w1) {
-  // selector: result bytes = (src byte i, 0x64, src byte i+1, 0x64)
-  uint4 o;
-  o.x = bytes2_to_f16x2(w0, 0x4140);
-  o.y = bytes2_to_f16x2(w0, 0x4342);
-  o.z = bytes2_to_f16x2(w1, 0x4140);
-  o.w = bytes2_to_f16x2(w1, 0x4342);
-  return o;
 }
 __device__ __forceinline__ uint4 bytes8_to_bf16(uint32_t w0, uint32_t w1) {
   // selector: result byte0 = src byte i, bytes 1..3 = 0x00,0x00,0x4B of the magic word
