@@ -88,23 +88,26 @@ struct __align__(16) K1Smem {
 };
 
 // luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path: per
-// pixel two dp4a (coefficients held in registers), the exact division by 10000 and one compare;
+// pixel two dp2a (coefficients held in registers), the exact division by 10000 and one compare;
 // the "exact multiple of 10000" flags of the 8 pixels are OR-ed and tested ONCE.  Only then
 // (3384 of 2^24 triples; 774 of them need the -1) the correction bitmap is consulted.
+// s = 2126 R + 7152 G + 722 B with two dp2a (16-bit coefficient x byte): the pixel sits in bytes
+// 0..2 of its word (lo/hi = (2126, 7152) x (b0, b1), then (722, 0) x (b2, b3)) or in bytes 1..3
+// ((0, 2126) x (b0, b1), then (7152, 722) x (b2, b3)).
 struct LumaCoef { uint32_t c0, c1, c0s, c1s; };
 __device__ __forceinline__ LumaCoef luma_coef() {
   LumaCoef k;      // opaque to constant propagation: stays in registers instead of a UMOV per use
-  asm volatile("mov.u32 %0, 0x00D2F04E;" : "=r"(k.c0));
-  asm volatile("mov.u32 %0, 0x00021B08;" : "=r"(k.c1));
-  asm volatile("mov.u32 %0, 0xD2F04E00;" : "=r"(k.c0s));
-  asm volatile("mov.u32 %0, 0x021B0800;" : "=r"(k.c1s));
+  asm volatile("mov.u32 %0, 0x1BF0084E;" : "=r"(k.c0));     // 7152 << 16 | 2126
+  asm volatile("mov.u32 %0, 0x000002D2;" : "=r"(k.c1));     //    0 << 16 |  722
+  asm volatile("mov.u32 %0, 0x084E0000;" : "=r"(k.c0s));    // 2126 << 16 |    0
+  asm volatile("mov.u32 %0, 0x02D21BF0;" : "=r"(k.c1s));    //  722 << 16 | 7152
   return k;
 }
 __device__ __noinline__ uint32_t luma_fix_lookup(uint32_t rg /* G*256 + R */, const uint32_t* fix) {
   return (fix[rg >> 5] >> (rg & 31)) & 1u;
 }
 __device__ __forceinline__ void luma_px(uint32_t w, uint32_t c0, uint32_t c1, uint32_t& q, uint32_t& rem0) {
-  const uint32_t s = __dp4a(w, c0, 0u) + (__dp4a(w, c1, 0u) << 8);
+  const uint32_t s = __dp2a_hi(c1, w, __dp2a_lo(c0, w, 0u));
   q = __umulhi(s, 3518437209u) >> 13;                         // s / 10000, exact for s <= 2 550 000
   rem0 = s - q * 10000u;                                      // 0 <=> exact multiple
 }
