@@ -87,47 +87,61 @@ struct __align__(16) K1Smem {
   uint64_t full[2], empty[2], out_full[2], out_empty[2];
 };
 
-// luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path: per
-// pixel two dp2a (coefficients held in registers), the exact division by 10000 and one compare;
-// the "exact multiple of 10000" flags of the 8 pixels are OR-ed and tested ONCE.  Only then
-// (3384 of 2^24 triples; 774 of them need the -1) the correction bitmap is consulted.
-// s = 2126 R + 7152 G + 722 B with two dp2a (16-bit coefficient x byte): the pixel sits in bytes
-// 0..2 of its word (lo/hi = (2126, 7152) x (b0, b1), then (722, 0) x (b2, b3)) or in bytes 1..3
-// ((0, 2126) x (b0, b1), then (7152, 722) x (b2, b3)).
-struct LumaCoef { uint32_t c0, c1, c0s, c1s; };
+// luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path, ~7
+// instructions per pixel: s = 2126 R + 7152 G + 722 B with two dp2a (16-bit coefficient x byte,
+// taken from whichever words hold the pixel's bytes -- no byte shuffling), the exact division by
+// 10000 as a multiply-high, and the low 13 bits of that product as the "remainder is 0 or 1" test;
+// the 8 tests are OR-ed and branched on ONCE.  Only then (1 group in ~600) the exact remainder is
+// formed and, for the 3384 of 2^24 triples whose sum is a multiple of 10000, the correction
+// bitmap is consulted (774 of them need the -1).
+// The four coefficient words: KA = (2126, 7152), KB = (722, 0), KC = (0, 2126), KD = (7152, 722)
+// as (low half, high half); dp2a_lo pairs them with bytes (b0, b1) of a word, dp2a_hi with (b2, b3).
+struct LumaCoef { uint32_t ka, kb, kc, kd; };
 __device__ __forceinline__ LumaCoef luma_coef() {
   LumaCoef k;      // opaque to constant propagation: stays in registers instead of a UMOV per use
-  asm volatile("mov.u32 %0, 0x1BF0084E;" : "=r"(k.c0));     // 7152 << 16 | 2126
-  asm volatile("mov.u32 %0, 0x000002D2;" : "=r"(k.c1));     //    0 << 16 |  722
-  asm volatile("mov.u32 %0, 0x084E0000;" : "=r"(k.c0s));    // 2126 << 16 |    0
-  asm volatile("mov.u32 %0, 0x02D21BF0;" : "=r"(k.c1s));    //  722 << 16 | 7152
+  asm volatile("mov.u32 %0, 0x1BF0084E;" : "=r"(k.ka));
+  asm volatile("mov.u32 %0, 0x000002D2;" : "=r"(k.kb));
+  asm volatile("mov.u32 %0, 0x084E0000;" : "=r"(k.kc));
+  asm volatile("mov.u32 %0, 0x02D21BF0;" : "=r"(k.kd));
   return k;
 }
 __device__ __noinline__ uint32_t luma_fix_lookup(uint32_t rg /* G*256 + R */, const uint32_t* fix) {
   return (fix[rg >> 5] >> (rg & 31)) & 1u;
 }
-__device__ __forceinline__ void luma_px(uint32_t w, uint32_t c0, uint32_t c1, uint32_t& q, uint32_t& rem0) {
-  const uint32_t s = __dp2a_hi(c1, w, __dp2a_lo(c0, w, 0u));
-  q = __umulhi(s, 3518437209u) >> 13;                         // s / 10000, exact for s <= 2 550 000
-  rem0 = s - q * 10000u;                                      // 0 <=> exact multiple
+// 4 pixels = 12 bytes = words a, b, c -> their sums
+__device__ __forceinline__ void luma_sums4(uint32_t a, uint32_t b, uint32_t c, const LumaCoef& k,
+                                           uint32_t (&s)[4]) {
+  s[0] = __dp2a_hi(k.kb, a, __dp2a_lo(k.ka, a, 0u));          // bytes a0 a1 a2
+  s[1] = __dp2a_lo(k.kd, b, __dp2a_hi(k.kc, a, 0u));          // bytes a3 b0 b1
+  s[2] = __dp2a_lo(k.kb, c, __dp2a_hi(k.ka, b, 0u));          // bytes b2 b3 c0
+  s[3] = __dp2a_hi(k.kd, c, __dp2a_lo(k.kc, c, 0u));          // bytes c1 c2 c3
 }
 __device__ __forceinline__ uint2 luma_8px(const uint32_t (&w)[6], const LumaCoef& k, const uint32_t* fix) {
-  uint32_t px[8], q[8], r[8];
-  px[0] = w[0];                            px[1] = __byte_perm(w[0], w[1], 0x4543);   // bytes 3,4,5
-  px[2] = __byte_perm(w[1], w[2], 0x4432); px[3] = w[2];                              // 6,7,8 | 9,10,11 (<<8)
-  px[4] = w[3];                            px[5] = __byte_perm(w[3], w[4], 0x4543);
-  px[6] = __byte_perm(w[4], w[5], 0x4432); px[7] = w[5];
+  uint32_t s[8], q[8], t[8];
+  {
+    uint32_t lo4[4], hi4[4];
+    luma_sums4(w[0], w[1], w[2], k, lo4);
+    luma_sums4(w[3], w[4], w[5], k, hi4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] = lo4[i]; s[4 + i] = hi4[i]; }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const bool hi = (i & 3) == 3;                             // pixel sits in bytes 1..3 of its word
-    luma_px(px[i], hi ? k.c0s : k.c0, hi ? k.c1s : k.c1, q[i], r[i]);
+    const uint32_t h = __umulhi(s[i], 3518437209u);           // s * ceil(2^45 / 10000) >> 32
+    q[i] = h >> 13;                                           // s / 10000, exact for s <= 2 550 000
+    t[i] = h & 8191u;                                         // 0 <=> s mod 10000 is 0 or 1 (checked exhaustively)
   }
-  const uint32_t any0 = (r[0] == 0) | (r[1] == 0) | (r[2] == 0) | (r[3] == 0) | (r[4] == 0) |
-                        (r[5] == 0) | (r[6] == 0) | (r[7] == 0);
+  const uint32_t any0 = (t[0] == 0) | (t[1] == 0) | (t[2] == 0) | (t[3] == 0) | (t[4] == 0) |
+                        (t[5] == 0) | (t[6] == 0) | (t[7] == 0);
   if (__builtin_expect(any0 != 0, 0)) {
+    // G*256 + R of the 8 pixels (R, G = the first two of a pixel's three bytes)
+    const uint32_t rg[8] = {w[0] & 0xFFFFu, __byte_perm(w[0], w[1], 0x7743) & 0xFFFFu, w[1] >> 16,
+                            (w[2] >> 8) & 0xFFFFu,
+                            w[3] & 0xFFFFu, __byte_perm(w[3], w[4], 0x7743) & 0xFFFFu, w[4] >> 16,
+                            (w[5] >> 8) & 0xFFFFu};
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (r[i] == 0) q[i] -= luma_fix_lookup(((i & 3) == 3 ? px[i] >> 8 : px[i]) & 0xFFFFu, fix);
+      if (t[i] == 0 && s[i] == q[i] * 10000u) q[i] -= luma_fix_lookup(rg[i], fix);
   }
   return make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24),
                     q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
