@@ -27,9 +27,12 @@ constexpr int kYBytes = 2 * kS * kW;              // 26880
 constexpr int kFrameBytes = kH * kW * 3;          // 100800
 constexpr int kBitmapWords = 65536 / 32;          // 2048
 
+constexpr int kPer = 21, kSeg = 40;                // x taps repeat every 21 outputs <-> 40 source pixels
+__host__ __device__ constexpr int tap_sx(int d) { return (80 * d + 19) / 42; }   // floor((d+.5)*160/84 - .5)
 struct TapTables {
-  uint32_t x[kS];      // sx | c0 << 8 | c1 << 20
+  uint32_t x[kS];      // sx | c0 << 8 | c1 << 20   (sx must be tap_sx(d), c periodic in 21: checked at init)
   uint32_t y[kS];      // sy | b0 << 8 | b1 << 20   (sy must be 0,3,5,8,...: checked at init)
+  uint32_t xc[kPer];   // c0 | c1 << 16 of output column r (mod 21): the dp2a coefficient pair
 };
 __constant__ TapTables c_taps;
 __device__ uint32_t g_luma_fix[kBitmapWords];
@@ -87,28 +90,26 @@ struct __align__(16) K1Smem {
   uint64_t full[2], empty[2], out_full[2], out_empty[2];
 };
 
-// luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path, ~7
-// instructions per pixel: s = 2126 R + 7152 G + 722 B with two dp2a (16-bit coefficient x byte,
-// taken from whichever words hold the pixel's bytes -- no byte shuffling), the exact division by
-// 10000 as a multiply-high, and the low 13 bits of that product as the "remainder is 0 or 1" test;
-// the 8 tests are OR-ed and branched on ONCE.  Only then (1 group in ~600) the exact remainder is
-// formed and, for the 3384 of 2^24 triples whose sum is a multiple of 10000, the correction
-// bitmap is consulted (774 of them need the -1).
-// The four coefficient words: KA = (2126, 7152), KB = (722, 0), KC = (0, 2126), KD = (7152, 722)
+// luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path, ~6
+// instructions per pixel: 8 s = 8 (2126 R + 7152 G + 722 B) with two dp2a (16-bit coefficient x
+// byte, taken from whichever words hold the pixel's bytes -- no byte shuffling), then ONE
+// multiply-high h = (8 s * ceil(2^48 / 80000)) >> 32 = floor(s * 2^16 / 10000) (checked for every
+// s <= 2 550 000): byte 2 of h is s / 10000 and the low 16 bits are zero exactly when s is a
+// multiple of 10000.  The 8 zero tests are OR-ed and branched on ONCE; only then (1 group in ~600)
+// the correction bitmap is consulted (774 of the 3384 exact-multiple triples need the -1).  The
+// quotient bytes are gathered with byte permutes.
+// The four coefficient words (x 8): KA = (2126, 7152), KB = (722, 0), KC = (0, 2126), KD = (7152, 722)
 // as (low half, high half); dp2a_lo pairs them with bytes (b0, b1) of a word, dp2a_hi with (b2, b3).
 struct LumaCoef { uint32_t ka, kb, kc, kd; };
 __device__ __forceinline__ LumaCoef luma_coef() {
   LumaCoef k;      // opaque to constant propagation: stays in registers instead of a UMOV per use
-  asm volatile("mov.u32 %0, 0x1BF0084E;" : "=r"(k.ka));
-  asm volatile("mov.u32 %0, 0x000002D2;" : "=r"(k.kb));
-  asm volatile("mov.u32 %0, 0x084E0000;" : "=r"(k.kc));
-  asm volatile("mov.u32 %0, 0x02D21BF0;" : "=r"(k.kd));
+  asm volatile("mov.u32 %0, 0xDF804270;" : "=r"(k.ka));
+  asm volatile("mov.u32 %0, 0x00001690;" : "=r"(k.kb));
+  asm volatile("mov.u32 %0, 0x42700000;" : "=r"(k.kc));
+  asm volatile("mov.u32 %0, 0x1690DF80;" : "=r"(k.kd));
   return k;
 }
-__device__ __noinline__ uint32_t luma_fix_lookup(uint32_t rg /* G*256 + R */, const uint32_t* fix) {
-  return (fix[rg >> 5] >> (rg & 31)) & 1u;
-}
-// 4 pixels = 12 bytes = words a, b, c -> their sums
+// 4 pixels = 12 bytes = words a, b, c -> their sums (x 8)
 __device__ __forceinline__ void luma_sums4(uint32_t a, uint32_t b, uint32_t c, const LumaCoef& k,
                                            uint32_t (&s)[4]) {
   s[0] = __dp2a_hi(k.kb, a, __dp2a_lo(k.ka, a, 0u));          // bytes a0 a1 a2
@@ -117,22 +118,20 @@ __device__ __forceinline__ void luma_sums4(uint32_t a, uint32_t b, uint32_t c, c
   s[3] = __dp2a_hi(k.kd, c, __dp2a_lo(k.kc, c, 0u));          // bytes c1 c2 c3
 }
 __device__ __forceinline__ uint2 luma_8px(const uint32_t (&w)[6], const LumaCoef& k, const uint32_t* fix) {
-  uint32_t s[8], q[8], t[8];
+  uint32_t h[8];
   {
     uint32_t lo4[4], hi4[4];
     luma_sums4(w[0], w[1], w[2], k, lo4);
     luma_sums4(w[3], w[4], w[5], k, hi4);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { s[i] = lo4[i]; s[4 + i] = hi4[i]; }
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __umulhi(lo4[i], 3518437209u);                   // floor(s * 2^16 / 10000)
+      h[4 + i] = __umulhi(hi4[i], 3518437209u);
+    }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t h = __umulhi(s[i], 3518437209u);           // s * ceil(2^45 / 10000) >> 32
-    q[i] = h >> 13;                                           // s / 10000, exact for s <= 2 550 000
-    t[i] = h & 8191u;                                         // 0 <=> s mod 10000 is 0 or 1 (checked exhaustively)
-  }
-  const uint32_t any0 = (t[0] == 0) | (t[1] == 0) | (t[2] == 0) | (t[3] == 0) | (t[4] == 0) |
-                        (t[5] == 0) | (t[6] == 0) | (t[7] == 0);
+  const uint32_t any0 = ((h[0] & 0xFFFFu) == 0) | ((h[1] & 0xFFFFu) == 0) | ((h[2] & 0xFFFFu) == 0) |
+                        ((h[3] & 0xFFFFu) == 0) | ((h[4] & 0xFFFFu) == 0) | ((h[5] & 0xFFFFu) == 0) |
+                        ((h[6] & 0xFFFFu) == 0) | ((h[7] & 0xFFFFu) == 0);
   if (__builtin_expect(any0 != 0, 0)) {
     // G*256 + R of the 8 pixels (R, G = the first two of a pixel's three bytes)
     const uint32_t rg[8] = {w[0] & 0xFFFFu, __byte_perm(w[0], w[1], 0x7743) & 0xFFFFu, w[1] >> 16,
@@ -141,10 +140,11 @@ __device__ __forceinline__ uint2 luma_8px(const uint32_t (&w)[6], const LumaCoef
                             (w[5] >> 8) & 0xFFFFu};
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (t[i] == 0 && s[i] == q[i] * 10000u) q[i] -= luma_fix_lookup(rg[i], fix);
+      if ((h[i] & 0xFFFFu) == 0) h[i] -= ((fix[rg[i] >> 5] >> (rg[i] & 31)) & 1u) << 16;
   }
-  return make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24),
-                    q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+  // byte 2 of each h
+  return make_uint2(__byte_perm(__byte_perm(h[0], h[1], 0x0062), __byte_perm(h[2], h[3], 0x0062), 0x5410),
+                    __byte_perm(__byte_perm(h[4], h[5], 0x0062), __byte_perm(h[6], h[7], 0x0062), 0x5410));
 }
 
 __global__ void __launch_bounds__(kK1Threads, 1)
@@ -208,10 +208,28 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   }
 
   // ===================== compute warps =====================
-  uint32_t xt[3];
-#pragma unroll
-  for (int p = 0; p < 3; ++p) xt[p] = c_taps.x[min(p * 32 + lane, kS - 1)];
+  // phase B lane roles: lane = ry*8 + s*4 + m handles source row 2*ry + s of the warp's Y slice and
+  // output columns 21 m .. 21 m + 20, whose taps lie in the row's bytes 40 m .. 40 m + 39 at
+  // compile-time offsets (the x taps repeat every 21 outputs <-> 40 source pixels).
+  const int ry = lane >> 3, srow = (lane >> 2) & 1, m = lane & 3;
+  uint32_t bw;                                                  // this lane's vertical weight
+  {
+    const uint32_t yt = c_taps.y[warp * 4 + ry];
+    bw = srow ? (yt >> 20) : ((yt >> 8) & 0xFFFu);
+  }
+  const uint32_t sh = srow ? 18u : 2u;                          // lane s stores outputs 2k + s
+  // ring planes are stored in 4x4 blocks (space-to-depth): byte (y,x) of the screen sits at
+  // ((y/4)*21 + x/4)*16 + (y%4)*4 + x%4, so conv1's 8x8-stride-4 windows are 16-B vectors.
+  // x = 21 m + s + 2k = 20 m + q, q = q0 + 2k: offset(k) = base + 16*((q0 + 2k) / 4) + (q0 + 2k) % 4
+  //   = addr[k & 1] + 16 * (k / 2)
+  uint32_t oaddr[2];
+  {
+    const int q0 = m + srow, base = (warp * 21 + 5 * m) * 16 + ry * 4;
+    oaddr[0] = base + (q0 >> 2) * 16 + (q0 & 3);
+    oaddr[1] = base + ((q0 + 2) >> 2) * 16 + ((q0 + 2) & 3);
+  }
   uint8_t* Yw = sm.Y + warp * (8 * kW);
+  const uint2* seg = reinterpret_cast<const uint2*>(Yw + lane * kSeg);   // (2 ry + s) * 160 + 40 m
   const LumaCoef coef = luma_coef();
   for (int f = 0; f < frames_here; ++f) {
     const int stage = f & 1, ob = f & 1;
@@ -227,29 +245,35 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[stage]);               // raw[stage] may be refilled
-    // phase B: cv2 fixed-point bilinear for output rows 4*warp .. 4*warp+3
+    // phase B: cv2 fixed-point bilinear.  Horizontal pass of one source row: 21 dp2a sums
+    // h = c0 Y[sx] + c1 Y[sx+1]; vertical weight applied to pairs of them; the partner row's terms
+    // arrive with one shuffle per pair; ((t0 + t1 + 2) >> 2) on both 16-bit halves at once.
+    uint32_t yw[10];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint2 v = seg[i];
+      yw[2 * i] = v.x;
+      yw[2 * i + 1] = v.y;
+    }
+    uint32_t term[kPer + 1];
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+      const int sx = tap_sx(r), k = sx >> 2, o = sx & 3;        // compile-time after unrolling
+      uint32_t h;
+      if (o == 0) h = __dp2a_lo(c_taps.xc[r], yw[k], 0u);
+      else if (o == 2) h = __dp2a_hi(c_taps.xc[r], yw[k], 0u);
+      else if (o == 1) h = __dp2a_lo(c_taps.xc[r], yw[k] >> 8, 0u);
+      else h = __dp2a_lo(c_taps.xc[r], __funnelshift_r(yw[k], yw[k + 1 < 10 ? k + 1 : 9], 24), 0u);
+      term[r] = (h >> 4) * bw;                                  // < 2^26; its bits 16.. are the cv2 term
+    }
+    term[kPer] = 0;
     mbar_wait(&sm.out_empty[ob], ((f >> 1) & 1) ^ 1);
     uint8_t* out = sm.out[ob];
 #pragma unroll
-    for (int ry = 0; ry < 4; ++ry) {
-      const int dy = warp * 4 + ry;
-      const uint32_t yt = sm.ytab[dy];
-      const int b0 = (yt >> 8) & 0xFFF, b1 = yt >> 20;
-      const uint8_t* row = Yw + (2 * ry) * kW;
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const int dx = p * 32 + lane;
-        if (dx < kS) {
-          const int sx = xt[p] & 0xFF, c0 = (xt[p] >> 8) & 0xFFF, c1 = xt[p] >> 20;
-          const uint8_t* r0 = row + sx;
-          const int h0 = r0[0] * c0 + r0[1] * c1;
-          const int h1 = r0[kW] * c0 + r0[kW + 1] * c1;
-          // ring planes are stored in 4x4 blocks (space-to-depth): byte (y,x) of the screen sits at
-          // ((y/4)*21 + x/4)*16 + (y%4)*4 + x%4, so conv1's 8x8-stride-4 windows are 16-B vectors
-          out[(warp * 21 + (dx >> 2)) * 16 + ry * 4 + (dx & 3)] =
-              (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
-        }
-      }
+    for (int k = 0; k < 11; ++k) {
+      const uint32_t mine = __byte_perm(term[2 * k], term[2 * k + 1], 0x7632);   // (t[2k] >> 16) | (t[2k+1] >> 16) << 16
+      const uint32_t sum = mine + __shfl_xor_sync(0xFFFFFFFFu, mine, 4) + 0x00020002u;
+      if (k < 10 || srow == 0) out[oaddr[k & 1] + 16 * (k >> 1)] = (uint8_t)(sum >> sh);
     }
     fence_proxy_async_smem();                                   // generic writes -> bulk store
     __syncwarp();
@@ -425,6 +449,15 @@ int preprocess_init(int device) {
       return ARL_ERR_UNSUPPORTED;
     }
   }
+  for (int d = 0; d < kS; ++d) {
+    // phase B of K1 relies on sx(d) = (80 d + 19) / 42 and on coefficients periodic in 21 outputs
+    const uint32_t want = (uint32_t)tap_sx(d);
+    if ((t.x[d] & 0xFF) != want || (d >= kPer && (t.x[d] >> 8) != (t.x[d - kPer] >> 8))) {
+      set_error("arl_init: unexpected horizontal tap pattern at column %d", d);
+      return ARL_ERR_UNSUPPORTED;
+    }
+  }
+  for (int r = 0; r < kPer; ++r) t.xc[r] = ((t.x[r] >> 8) & 0xFFFu) | ((t.x[r] >> 20) << 16);
   ARL_CUDA(cudaMemcpyToSymbol(c_taps, &t, sizeof(t)));
   void* fix = nullptr;
   ARL_CUDA(cudaGetSymbolAddress(&fix, g_luma_fix));
