@@ -69,16 +69,18 @@ static void linear_taps(int src, int dst, uint32_t* packed) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------
-// One persistent CTA per SM: 21 compute warps + 1 copy warp, no block-wide barrier in the loop.
-//   copy warp   : per frame 43 cp.async.bulk loads (the 168 source rows cv2 reads: rows 5k+2 are
+// One persistent CTA per SM: 21 compute warps + a load warp + a store warp, no block-wide barrier
+// in the loop.
+//   load warp   : per frame 43 cp.async.bulk loads (the 168 source rows cv2 reads: rows 5k+2 are
 //                 never touched; rows 5k+3 .. 5k+6 are contiguous, so one 1920-B copy feeds two
-//                 output rows) into raw[stage]; later the 7056-B plane store(s) out[ob] -> ring.
+//                 output rows) into raw[stage], issued the moment the stage is released.
+//   store warp  : the 7056-B plane store(s) out[ob] -> ring.
 //   compute warp w owns output rows 4w .. 4w+3: luma of its 8 source rows (160 groups of 8 px =
 //                 5 full warp iterations) into its private Y slice, then the 4 x 84 outputs with
 //                 the x taps of its 3 columns held in registers.  Hand-offs are mbarriers:
 //                 full/empty per raw stage, out_full/out_empty per output buffer.
 constexpr int kComputeWarps = kS / 4;                       // 21
-constexpr int kK1Threads = (kComputeWarps + 1) * 32;        // 704
+constexpr int kK1Threads = (kComputeWarps + 2) * 32;        // 736
 constexpr int kCopies = 43;
 
 struct __align__(16) K1Smem {
@@ -172,24 +174,31 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kComputeWarps) {
-    // ===================== copy warp =====================
-    for (int f = 0; f <= frames_here; ++f) {
-      if (f < frames_here) {                                 // loads of frame f
-        const int stage = f & 1;
-        mbar_wait(&sm.empty[stage], ((f >> 1) & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(&sm.full[stage], kRawBytes);
-        __syncwarp();
-        const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
-        uint8_t* dst = sm.raw[stage];
-        for (int m = lane; m < kCopies; m += 32) {
-          // m = 0: rows 0,1 (dy 0);  m = 1..41: rows 5m-2 .. 5m+1 (dy 2m-1, 2m);  m = 42: rows 208,209
-          const int row = m == 0 ? 0 : 5 * m - 2, dy = m == 0 ? 0 : 2 * m - 1;
-          const uint32_t bytes = (m == 0 || m == kCopies - 1) ? kPairBytes : 2 * kPairBytes;
-          bulk_g2s(dst + dy * kPairBytes, src + row * kRowBytes, bytes, &sm.full[stage]);
-        }
+    // ===================== load warp =====================
+    // loads of frame f are issued as soon as phase A of frame f-2 has released the stage: this warp
+    // never waits for anything else, so up to two frames (160 KB) per SM are in flight
+    for (int f = 0; f < frames_here; ++f) {
+      const int stage = f & 1;
+      mbar_wait(&sm.empty[stage], ((f >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&sm.full[stage], kRawBytes);
+      __syncwarp();
+      const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
+      uint8_t* dst = sm.raw[stage];
+      for (int m = lane; m < kCopies; m += 32) {
+        // m = 0: rows 0,1 (dy 0);  m = 1..41: rows 5m-2 .. 5m+1 (dy 2m-1, 2m);  m = 42: rows 208,209
+        const int row = m == 0 ? 0 : 5 * m - 2, dy = m == 0 ? 0 : 2 * m - 1;
+        const uint32_t bytes = (m == 0 || m == kCopies - 1) ? kPairBytes : 2 * kPairBytes;
+        bulk_g2s(dst + dy * kPairBytes, src + row * kRowBytes, bytes, &sm.full[stage]);
       }
-      if (f >= 1 && lane == 0) {                             // store of frame f-1
-        const int g = f - 1, ob = g & 1;
+      __syncwarp();
+    }
+    return;
+  }
+  if (warp == kComputeWarps + 1) {
+    // ===================== store warp =====================
+    if (lane == 0) {
+      for (int g = 0; g < frames_here; ++g) {
+        const int ob = g & 1;
         mbar_wait(&sm.out_full[ob], (g >> 1) & 1);
         uint8_t* dst = ring + ((size_t)(blockIdx.x + (size_t)g * gridDim.x) * ring_slots) * kPlane;
         for (int r = 0; r < replicate; ++r) {
@@ -201,9 +210,8 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
         bulk_wait_read<0>();                                 // smem has been read: buffer reusable
         mbar_arrive(&sm.out_empty[ob]);
       }
-      __syncwarp();
+      bulk_wait<0>();
     }
-    if (lane == 0) bulk_wait<0>();
     return;
   }
 
