@@ -69,27 +69,23 @@ static void linear_taps(int src, int dst, uint32_t* packed) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------
-// One persistent CTA per SM: 21 compute warps + a load warp + a store warp, no block-wide barrier
-// in the loop.
-//   load warp   : per frame 43 cp.async.bulk loads (the 168 source rows cv2 reads: rows 5k+2 are
-//                 never touched; rows 5k+3 .. 5k+6 are contiguous, so one 1920-B copy feeds two
-//                 output rows) into raw[stage], issued the moment the stage is released.
-//   store warp  : the 7056-B plane store(s) out[ob] -> ring.
-//   compute warp w owns output rows 4w .. 4w+3: luma of its 8 source rows (160 groups of 8 px =
-//                 5 full warp iterations) into its private Y slice, then the 4 x 84 outputs with
-//                 the x taps of its 3 columns held in registers.  Hand-offs are mbarriers:
-//                 full/empty per raw stage, out_full/out_empty per output buffer.
+// One persistent CTA per SM: 21 compute warps + a store warp, no block-wide barrier in the loop.
+//   compute warp w owns 4 output rows and is its own load pipeline: 43 cp.async.bulk loads per
+//                 frame in all (the 168 source rows cv2 reads: rows 5k+2 are never touched; rows
+//                 5k+3 .. 5k+6 are contiguous, so one 1920-B copy feeds two output rows), each
+//                 into the private slice of raw[stage] of the warp that consumes it, behind that
+//                 warp's own mbarrier; luma of its 8 source rows (160 groups of 8 px = 5 full warp
+//                 iterations) into its private Y slice, then its 4 x 84 outputs.
+//   store warp  : the 7056-B plane store(s) out[ob] -> ring (out_full/out_empty mbarriers).
 constexpr int kComputeWarps = kS / 4;                       // 21
-constexpr int kK1Threads = (kComputeWarps + 2) * 32;        // 736
-constexpr int kCopies = 43;
+constexpr int kK1Threads = (kComputeWarps + 1) * 32;        // 704
 
 struct __align__(16) K1Smem {
   uint8_t raw[2][kRawBytes];
   uint8_t Y[kYBytes];
   uint8_t out[2][kPlane];
   uint32_t fix[kBitmapWords];
-  uint32_t ytab[kS];
-  uint64_t full[2], empty[2], out_full[2], out_empty[2];
+  uint64_t full[2][kComputeWarps], out_full[2], out_empty[2];
 };
 
 // luma of 8 pixels (24 bytes = words w[0..5]) -> two packed words.  Branch-free common path, ~6
@@ -157,11 +153,9 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < kBitmapWords; i += kK1Threads) sm.fix[i] = g_luma_fix[i];
-  if (tid < kS) sm.ytab[tid] = c_taps.y[tid];
   if (tid == 0) {
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&sm.full[k], 1);
-      mbar_init(&sm.empty[k], kComputeWarps);
+      for (int w = 0; w < kComputeWarps; ++w) mbar_init(&sm.full[k][w], 1);
       mbar_init(&sm.out_full[k], kComputeWarps);
       mbar_init(&sm.out_empty[k], 1);
     }
@@ -174,27 +168,6 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kComputeWarps) {
-    // ===================== load warp =====================
-    // loads of frame f are issued as soon as phase A of frame f-2 has released the stage: this warp
-    // never waits for anything else, so up to two frames (160 KB) per SM are in flight
-    for (int f = 0; f < frames_here; ++f) {
-      const int stage = f & 1;
-      mbar_wait(&sm.empty[stage], ((f >> 1) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&sm.full[stage], kRawBytes);
-      __syncwarp();
-      const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
-      uint8_t* dst = sm.raw[stage];
-      for (int m = lane; m < kCopies; m += 32) {
-        // m = 0: rows 0,1 (dy 0);  m = 1..41: rows 5m-2 .. 5m+1 (dy 2m-1, 2m);  m = 42: rows 208,209
-        const int row = m == 0 ? 0 : 5 * m - 2, dy = m == 0 ? 0 : 2 * m - 1;
-        const uint32_t bytes = (m == 0 || m == kCopies - 1) ? kPairBytes : 2 * kPairBytes;
-        bulk_g2s(dst + dy * kPairBytes, src + row * kRowBytes, bytes, &sm.full[stage]);
-      }
-      __syncwarp();
-    }
-    return;
-  }
-  if (warp == kComputeWarps + 1) {
     // ===================== store warp =====================
     if (lane == 0) {
       for (int g = 0; g < frames_here; ++g) {
@@ -216,13 +189,19 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   }
 
   // ===================== compute warps =====================
+  // Warp w owns output rows dy = 4w+1 .. 4w+4 (warp 20: 81, 82, 83, 0).  Their source rows are its
+  // private slice of a raw stage, fetched by the warp's own two copies (rows 10w+3 .. 10w+6 and
+  // 10w+8 .. 10w+11, 1920 B each; warp 20: rows 203-206, 208-209 and 0-1) and refilled for frame
+  // f+2 the moment its phase A of frame f is done -- no warp ever waits for another warp's data.
   // phase B lane roles: lane = ry*8 + s*4 + m handles source row 2*ry + s of the warp's Y slice and
   // output columns 21 m .. 21 m + 20, whose taps lie in the row's bytes 40 m .. 40 m + 39 at
   // compile-time offsets (the x taps repeat every 21 outputs <-> 40 source pixels).
   const int ry = lane >> 3, srow = (lane >> 2) & 1, m = lane & 3;
+  int dy = 4 * warp + 1 + ry;
+  if (dy >= kS) dy -= kS;
   uint32_t bw;                                                  // this lane's vertical weight
   {
-    const uint32_t yt = c_taps.y[warp * 4 + ry];
+    const uint32_t yt = c_taps.y[dy];
     bw = srow ? (yt >> 20) : ((yt >> 8) & 0xFFFu);
   }
   const uint32_t sh = srow ? 18u : 2u;                          // lane s stores outputs 2k + s
@@ -232,16 +211,34 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   //   = addr[k & 1] + 16 * (k / 2)
   uint32_t oaddr[2];
   {
-    const int q0 = m + srow, base = (warp * 21 + 5 * m) * 16 + ry * 4;
+    const int q0 = m + srow, base = ((dy >> 2) * 21 + 5 * m) * 16 + (dy & 3) * 4;
     oaddr[0] = base + (q0 >> 2) * 16 + (q0 & 3);
     oaddr[1] = base + ((q0 + 2) >> 2) * 16 + ((q0 + 2) & 3);
+  }
+  auto issue_loads = [&](int f) {                               // lane 0 only
+    const int stage = f & 1;
+    uint64_t* bar = &sm.full[stage][warp];
+    mbar_expect_tx(bar, 4 * kPairBytes);
+    const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
+    uint8_t* dst = sm.raw[stage] + warp * (4 * kPairBytes);
+    bulk_g2s(dst, src + (10 * warp + 3) * kRowBytes, 2 * kPairBytes, bar);
+    if (warp < kComputeWarps - 1) {
+      bulk_g2s(dst + 2 * kPairBytes, src + (10 * warp + 8) * kRowBytes, 2 * kPairBytes, bar);
+    } else {
+      bulk_g2s(dst + 2 * kPairBytes, src + (kH - 2) * kRowBytes, kPairBytes, bar);
+      bulk_g2s(dst + 3 * kPairBytes, src, kPairBytes, bar);
+    }
+  };
+  if (lane == 0) {
+    if (frames_here > 0) issue_loads(0);
+    if (frames_here > 1) issue_loads(1);
   }
   uint8_t* Yw = sm.Y + warp * (8 * kW);
   const uint2* seg = reinterpret_cast<const uint2*>(Yw + lane * kSeg);   // (2 ry + s) * 160 + 40 m
   const LumaCoef coef = luma_coef();
   for (int f = 0; f < frames_here; ++f) {
     const int stage = f & 1, ob = f & 1;
-    mbar_wait(&sm.full[stage], (f >> 1) & 1);
+    mbar_wait(&sm.full[stage][warp], (f >> 1) & 1);
     // phase A: luma of this warp's 8 source rows, 8 pixels (24 B) per lane-iteration
     const uint2* raw2 = reinterpret_cast<const uint2*>(sm.raw[stage] + warp * (4 * kPairBytes));
 #pragma unroll
@@ -252,7 +249,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
       reinterpret_cast<uint2*>(Yw)[u] = luma_8px(w, coef, sm.fix);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[stage]);               // raw[stage] may be refilled
+    if (lane == 0 && f + 2 < frames_here) issue_loads(f + 2);   // the slice has been read: refill it
     // phase B: cv2 fixed-point bilinear.  Horizontal pass of one source row: 21 dp2a sums
     // h = c0 Y[sx] + c1 Y[sx+1]; vertical weight applied to pairs of them; the partner row's terms
     // arrive with one shuffle per pair; ((t0 + t1 + 2) >> 2) on both 16-bit halves at once.
