@@ -2,10 +2,10 @@
 // (src/history.py:13-15).  u8 [B,210,160,3] -> luma (the reference's float64
 // expression, truncated) -> cv2 INTER_LINEAR 84x84 (fixed point) -> ring slot.
 //
-// Layout / data flow per frame (one persistent CTA per SM, 2-stage TMA pipeline):
+// Layout / data flow per frame (one persistent CTA per SM, every compute warp a 2-stage bulk-copy pipeline):
 //   HBM --cp.async.bulk (43 copies: the 168 source rows cv2 actually reads)--> smem raw[stage]
-//   raw --luma, 8 px / lane-iteration, dp4a--> smem Y [168][160] u8 (8 rows private to a warp)
-//   Y   --2x2 fixed-point taps--> smem out[ob] [84*84] u8 --cp.async.bulk--> ring[b][slot]
+//   raw --luma, 8 px / lane-iteration, dp2a--> smem Y [168][160] u8 (8 rows private to a warp)
+//   Y   --dp2a x taps, packed vertical terms--> smem out[ob] [84*84] u8 --cp.async.bulk--> ring[b][slot]
 // Algorithmic HBM bytes per frame: 80 640 read + 7 056 written (x replicate).
 //
 // Luma: the reference computes (0.2126*R + 0.7152*G) + 0.0722*B in float64 and truncates.
@@ -152,27 +152,50 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
   K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < kBitmapWords; i += kK1Threads) sm.fix[i] = g_luma_fix[i];
-  if (tid == 0) {
+  const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // A compute warp's load barriers are private to it: lane 0 initialises them and issues the
+  // copies of its first two frames before anything else happens in the CTA (the 8-KB correction
+  // bitmap and the output barriers are set up while those copies are in flight).
+  auto issue_loads = [&](int f) {                               // lane 0 of a compute warp only
+    const int stage = f & 1;
+    uint64_t* bar = &sm.full[stage][warp];
+    mbar_expect_tx(bar, 4 * kPairBytes);
+    const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
+    uint8_t* dst = sm.raw[stage] + warp * (4 * kPairBytes);
+    bulk_g2s(dst, src + (10 * warp + 3) * kRowBytes, 2 * kPairBytes, bar);
+    if (warp < kComputeWarps - 1) {
+      bulk_g2s(dst + 2 * kPairBytes, src + (10 * warp + 8) * kRowBytes, 2 * kPairBytes, bar);
+    } else {
+      bulk_g2s(dst + 2 * kPairBytes, src + (kH - 2) * kRowBytes, kPairBytes, bar);
+      bulk_g2s(dst + 3 * kPairBytes, src, kPairBytes, bar);
+    }
+  };
+  if (warp < kComputeWarps && lane == 0) {
+    mbar_init(&sm.full[0][warp], 1);
+    mbar_init(&sm.full[1][warp], 1);
+    fence_mbar_init();
+    if (frames_here > 0) issue_loads(0);
+    if (frames_here > 1) issue_loads(1);
+  }
+  if (tid == kK1Threads - 1) {
     for (int k = 0; k < 2; ++k) {
-      for (int w = 0; w < kComputeWarps; ++w) mbar_init(&sm.full[k][w], 1);
       mbar_init(&sm.out_full[k], kComputeWarps);
       mbar_init(&sm.out_empty[k], 1);
     }
     fence_mbar_init();
   }
+  for (int i = tid; i < kBitmapWords; i += kK1Threads) sm.fix[i] = g_luma_fix[i];
   __syncthreads();
   // the next kernel in the stream (conv1 forward, launched with programmatic stream serialization)
   // may run its prologue on SMs this kernel has left; it waits for this grid before reading the ring
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int frames_here = num_envs > (int)blockIdx.x ? (num_envs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kComputeWarps) {
     // ===================== store warp =====================
     if (lane == 0) {
       for (int g = 0; g < frames_here; ++g) {
         const int ob = g & 1;
-        mbar_wait(&sm.out_full[ob], (g >> 1) & 1);
+        mbar_wait_sleep(&sm.out_full[ob], (g >> 1) & 1);
         uint8_t* dst = ring + ((size_t)(blockIdx.x + (size_t)g * gridDim.x) * ring_slots) * kPlane;
         for (int r = 0; r < replicate; ++r) {
           int sl = slot + r;
@@ -215,30 +238,12 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     oaddr[0] = base + (q0 >> 2) * 16 + (q0 & 3);
     oaddr[1] = base + ((q0 + 2) >> 2) * 16 + ((q0 + 2) & 3);
   }
-  auto issue_loads = [&](int f) {                               // lane 0 only
-    const int stage = f & 1;
-    uint64_t* bar = &sm.full[stage][warp];
-    mbar_expect_tx(bar, 4 * kPairBytes);
-    const uint8_t* src = frames + (size_t)(blockIdx.x + (size_t)f * gridDim.x) * kFrameBytes;
-    uint8_t* dst = sm.raw[stage] + warp * (4 * kPairBytes);
-    bulk_g2s(dst, src + (10 * warp + 3) * kRowBytes, 2 * kPairBytes, bar);
-    if (warp < kComputeWarps - 1) {
-      bulk_g2s(dst + 2 * kPairBytes, src + (10 * warp + 8) * kRowBytes, 2 * kPairBytes, bar);
-    } else {
-      bulk_g2s(dst + 2 * kPairBytes, src + (kH - 2) * kRowBytes, kPairBytes, bar);
-      bulk_g2s(dst + 3 * kPairBytes, src, kPairBytes, bar);
-    }
-  };
-  if (lane == 0) {
-    if (frames_here > 0) issue_loads(0);
-    if (frames_here > 1) issue_loads(1);
-  }
   uint8_t* Yw = sm.Y + warp * (8 * kW);
   const uint2* seg = reinterpret_cast<const uint2*>(Yw + lane * kSeg);   // (2 ry + s) * 160 + 40 m
   const LumaCoef coef = luma_coef();
   for (int f = 0; f < frames_here; ++f) {
     const int stage = f & 1, ob = f & 1;
-    mbar_wait(&sm.full[stage][warp], (f >> 1) & 1);
+    mbar_wait_sleep(&sm.full[stage][warp], (f >> 1) & 1);
     // phase A: luma of this warp's 8 source rows, 8 pixels (24 B) per lane-iteration
     const uint2* raw2 = reinterpret_cast<const uint2*>(sm.raw[stage] + warp * (4 * kPairBytes));
 #pragma unroll
