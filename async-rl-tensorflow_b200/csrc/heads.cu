@@ -24,63 +24,52 @@ int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream);
 
 // ------------------------------- heads forward --------------------------------------------
-// CTA = 128 threads, 16 samples.  Wcat [A+1][257] in smem (policy columns then value).
-constexpr int kHfSamples = 16;
-constexpr int kHfThreads = 128;
+// One warp per sample: lane l holds h[8l .. 8l+7] (the warp reads the 1-KB row as 32-byte pieces),
+// the weights sit in shared memory as wt[(j*8 + e)*32 + l] = W[k = 8l + e][j] (conflict-free),
+// every output is 8 FMAs per lane + a butterfly sum; lane j keeps logit j, the softmax runs
+// across the lanes.  (First version: 16 samples per CTA staged in shared memory, one thread per
+// (sample, output) walking 256 k serially: 10 us per 4096 samples, latency-bound.)
+constexpr int kHfThreads = 256;
 __global__ void __launch_bounds__(kHfThreads)
 heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                  const float* __restrict__ qw, const float* __restrict__ qb,
                  const float* __restrict__ h, float* __restrict__ logits,
                  float* __restrict__ probs, float* __restrict__ value, int64_t num_samples, int A) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(16) float sm[];   // [A+1][8][32]
   const int J = A + 1;
-  float* wt = sm;                       // [J][257]
-  float* hs = wt + ((J * 257 + 3) & ~3); // [16][256], 16-byte aligned
-  float* zs = hs + kHfSamples * 256;    // [16][J]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 256 * A; i += kHfThreads) {
-    const int k = i / A, j = i - k * A;
-    wt[j * 257 + k] = pw[i];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 256 * J; i += kHfThreads) {
+    const int j = i >> 8, e = (i >> 5) & 7, l = i & 31, k = l * 8 + e;
+    sm[i] = j < A ? pw[k * A + j] : qw[k];
   }
-  for (int k = tid; k < 256; k += kHfThreads) wt[A * 257 + k] = qw[k];
-
-  const int64_t num_tiles = (num_samples + kHfSamples - 1) / kHfSamples;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t n0 = tile * kHfSamples;
-    const int ns = (int)((num_samples - n0) < kHfSamples ? (num_samples - n0) : kHfSamples);
-    __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(h + n0 * 256);
-    for (int i = tid; i < ns * 64; i += kHfThreads) reinterpret_cast<float4*>(hs)[i] = src[i];
-    __syncthreads();
-    for (int o = tid; o < ns * J; o += kHfThreads) {
-      const int s = o / J, j = o - s * J;
-      const float* hp = hs + s * 256;
-      const float* wp = wt + j * 257;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 256; k += 4) {
-        a0 = fmaf(hp[k], wp[k], a0);
-        a1 = fmaf(hp[k + 1], wp[k + 1], a1);
-        a2 = fmaf(hp[k + 2], wp[k + 2], a2);
-        a3 = fmaf(hp[k + 3], wp[k + 3], a3);
-      }
-      zs[s * J + j] = (a0 + a1) + (a2 + a3) + (j < A ? pb[j] : qb[0]);
+  const float bias = lane < A ? pb[lane] : 0.f, qb0 = qb[0];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * (kHfThreads / 32);
+  for (int64_t n = (int64_t)blockIdx.x * (kHfThreads / 32) + warp; n < num_samples; n += stride) {
+    const float4* hp = reinterpret_cast<const float4*>(h + n * 256) + lane * 2;
+    const float4 x0 = hp[0], x1 = hp[1];
+    float z = 0.f, zv = 0.f;
+    for (int j = 0; j < J; ++j) {
+      const float* w = sm + j * 256 + lane;
+      float a0 = x0.x * w[0], a1 = x0.y * w[32];
+      a0 = fmaf(x0.z, w[64], a0);  a1 = fmaf(x0.w, w[96], a1);
+      a0 = fmaf(x1.x, w[128], a0); a1 = fmaf(x1.y, w[160], a1);
+      a0 = fmaf(x1.z, w[192], a0); a1 = fmaf(x1.w, w[224], a1);
+      const float t = warp_sum(a0 + a1);           // every lane gets the total
+      if (j == lane) z = t;
+      if (j == A) zv = t;
     }
-    __syncthreads();
-    if (tid < ns) {
-      const float* z = zs + tid * J;
-      const int64_t n = n0 + tid;
-      float mx = z[0];
-      for (int j = 1; j < A; ++j) mx = fmaxf(mx, z[j]);
-      float den = 0.f;
-      for (int j = 0; j < A; ++j) den += expf(z[j] - mx);
-      const float inv = 1.0f / den;
-      for (int j = 0; j < A; ++j) {
-        logits[n * A + j] = z[j];
-        probs[n * A + j] = expf(z[j] - mx) * inv;
-      }
-      value[n] = z[A];
+    z += bias;
+    float mx = lane < A ? z : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float ex = lane < A ? expf(z - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(ex);
+    if (lane < A) {
+      logits[n * A + lane] = z;
+      probs[n * A + lane] = ex * inv;
     }
+    if (lane == 0) value[n] = zv + qb0;
   }
 }
 
@@ -388,10 +377,8 @@ __global__ void observe_store_kernel(const float* __restrict__ reward, const uin
 }
 
 int heads_init() {
-  const int J = ARL_MAX_ACTIONS + 1;
-  ARL_CUDA(cudaFuncSetAttribute(
-      heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-      (int)((((J * 257 + 3) & ~3) + kHfSamples * 256 + kHfSamples * J) * sizeof(float))));
+  ARL_CUDA(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((ARL_MAX_ACTIONS + 1) * 256 * sizeof(float))));
   return ARL_OK;
 }
 
@@ -411,11 +398,9 @@ extern "C" int arl_heads_forward(const float* params, int action_size, const flo
   ARL_REQUIRE(aligned16(h), "arl_heads_forward: h must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
   const ParamLayout L = param_layout(action_size);
-  const int J = action_size + 1;
-  const size_t smem =
-      (size_t)(((J * 257 + 3) & ~3) + kHfSamples * 256 + kHfSamples * J) * sizeof(float);
-  const int64_t tiles = (num_samples + kHfSamples - 1) / kHfSamples;
-  const int grid = (int)(tiles < 4LL * num_sms() ? tiles : 4LL * num_sms());
+  const size_t smem = (size_t)(action_size + 1) * 256 * sizeof(float);
+  const int64_t ctas = (num_samples + kHfThreads / 32 - 1) / (kHfThreads / 32);   // one warp per sample
+  const int grid = (int)(ctas < 2LL * num_sms() ? ctas : 2LL * num_sms());
   heads_fwd_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(
       params + L.off[T_PW], params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h,
       logits, probs, value, num_samples, action_size);
