@@ -77,25 +77,40 @@ colsum_split256_kernel(const uint8_t* __restrict__ xs, float* __restrict__ parti
   const int per = (rows + gridDim.x - 1) / gridDim.x;
   const int beg = per * blockIdx.x, end = min(rows, beg + per);
   const int64_t part = (int64_t)32 * rows * 16;
-  for (int c = warp * 4; c < warp * 4 + 4; ++c) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint8_t* p = xs + (int64_t)c * rows * 16;
-    for (int r = beg + lane; r < end; r += 32) {
-      const uint4 h = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)r * 16));
-      const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + part + (int64_t)r * 16));
-      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  // the four chunks of a warp side by side: 8 loads in flight per lane and row (one chunk after
+  // the other, two loads in flight, was latency-bound: 16 us for 21 MB)
+  float acc[4][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[2 * i] += __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-        acc[2 * i + 1] += __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
-      }
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+  const uint8_t* p0 = xs + (int64_t)(warp * 4) * rows * 16;
+  for (int r = beg + lane; r < end; r += 32) {
+    uint4 h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint8_t* p = p0 + (int64_t)q * rows * 16 + (int64_t)r * 16;
+      h[q] = __ldg(reinterpret_cast<const uint4*>(p));
+      l[q] = __ldg(reinterpret_cast<const uint4*>(p + part));
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-      float* d = partials + (size_t)blockIdx.x * 256 + c * 8;
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t hw[4] = {h[q].x, h[q].y, h[q].z, h[q].w}, lw[4] = {l[q].x, l[q].y, l[q].z, l[q].w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = acc[i];
+      for (int i = 0; i < 4; ++i) {
+        acc[q][2 * i] += __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+        acc[q][2 * i + 1] += __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = warp_sum(acc[q][i]);
+    if (lane == 0) {
+      float* d = partials + (size_t)blockIdx.x * 256 + (warp * 4 + q) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = acc[q][i];
     }
   }
 }
