@@ -11,8 +11,14 @@ Pinning status:
     (``src/environment.py:49-53`` through a stub ``gym``; ``src/history.py``
     imported as-is) via ``tests/golden/*.npz`` made by
     ``oracle/make_golden.py``.
-  * network / returns / loss / clip / RMSProp -- "parity unpinned": the
-    arithmetic lives in TensorFlow 0.x (un-vendored, un-pinned, absent here)
-    and the reference ships no tests or golden vectors for it.  The
-    restatement follows the reference call sites cited in each function.
+  * network forward (conv2d / linear wiring: kernel shapes, stride lists, NHWC flatten,
+    [in,out] matrices, bias and activation order) -- pinned against the reference's own
+    ``src/ops.py`` ``conv2d`` / ``linear`` EXECUTED over ``oracle/tf_stub.py`` with the literal
+    arguments of its call sites (``oracle/make_golden_network.py`` ->
+    ``tests/golden/network_golden.npz``).
+  * TensorFlow's numerics, returns / loss / clip / RMSProp -- "parity unpinned": that
+    arithmetic lives in TensorFlow 0.x (un-vendored, un-pinned, absent here; the stub restates
+    tf.nn.conv2d / tf.matmul from their documented semantics) and the reference ships no tests
+    or golden vectors for it.  The restatement follows the reference call sites cited in each
+    function.
 """
