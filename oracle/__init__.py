@@ -16,7 +16,14 @@ Pinning status:
     ``src/ops.py`` ``conv2d`` / ``linear`` EXECUTED over ``oracle/tf_stub.py`` with the literal
     arguments of its call sites (``oracle/make_golden_network.py`` ->
     ``tests/golden/network_golden.npz``).
-  * TensorFlow's numerics, returns / loss / clip / RMSProp -- "parity unpinned": that
+  * heads / loss formulas (softmax, log OF the softmax, entropy, log pi(a), policy / value /
+    total loss: ``src/network.py:60-94``) and the scalar formulas of the as-running learner
+    (epsilon ``agent.py:142-144``, reward clip ``:154``, 1-step Q targets ``:188-190``, async-Q
+    loss ``:310-314``, learning rate ``:395``) -- pinned the same way: the reference's own source
+    lines are cut out by their text and exec'd (one sample at a time for the loss block, which
+    otherwise broadcasts [N]-[N,1]: SURVEY D3) with ``config.M1`` imported unmodified.
+  * TensorFlow's numerics, n-step returns (absent upstream), clip_by_norm / RMSProp (TF ops) --
+    "parity unpinned": that
     arithmetic lives in TensorFlow 0.x (un-vendored, un-pinned, absent here; the stub restates
     tf.nn.conv2d / tf.matmul from their documented semantics) and the reference ships no tests
     or golden vectors for it.  The restatement follows the reference call sites cited in each

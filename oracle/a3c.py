@@ -279,6 +279,15 @@ def q_targets(q_next, rewards, terminals, discount=0.99):
     return (1.0 - term) * discount * q_next.max(axis=1) + clip_rewards(rewards)
 
 
+def async_q_loss(q, actions, targets, scale=None):
+    """agent.py:310-314: q_acted = sum(q * onehot(action)), delta = target - q_acted,
+    loss = mean(delta^2)  (``scale`` replaces the 1/N of the mean).  Returns (loss, delta)."""
+    q_acted = q.gather(1, actions.reshape(-1, 1).long()).reshape(-1)
+    delta = targets - q_acted
+    n = delta.shape[0]
+    return (delta ** 2).sum() * (1.0 / n if scale is None else scale), delta
+
+
 def async_q_gradients(params_np, target_params_np, stacks_t, stacks_tp1, actions, rewards,
                       terminals, discount=0.99, scale=None, dtype=torch.float64, masks=None):
     """agent.py:169-207 + 306-317 with the Q head in the p_w/p_b slot (q = the policy-logit
@@ -295,10 +304,7 @@ def async_q_gradients(params_np, target_params_np, stacks_t, stacks_tp1, actions
                                     np.asarray(terminals).reshape(-1), discount), dtype=dtype)
     q, _ = forward(p, stacks_t, masks=masks)
     at = torch.as_tensor(np.asarray(actions).reshape(-1)).long()
-    q_acted = q.gather(1, at.reshape(-1, 1)).reshape(-1)
-    delta = tgt - q_acted
-    n = delta.shape[0]
-    loss = (delta ** 2).sum() * (1.0 / n if scale is None else scale)
+    loss, delta = async_q_loss(q, at, tgt, scale)
     loss.backward()
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy().copy())
                         for k, v in p.items())

@@ -12,7 +12,9 @@ math; evaluated in float64 so the fixture is not tied to one summation order).  
 reference's executed code is everything ops.py does around those calls: the stride list and
 kernel shape it builds from ``x.get_shape()`` (ops.py:14-19), the variable names and shapes it
 asks for (ops.py:21-24, 36-39), bias_add after the contraction, the activation applied last
-(ops.py:27-28, 43-44) and the ``[in, out]`` orientation of ``linear``'s matrix.
+(ops.py:27-28, 43-44) and the ``[in, out]`` orientation of ``linear``'s matrix.  For the head /
+loss block of ``src/network.py`` (:60-94) the stub adds placeholder (= its fed value), log,
+reduce_sum, one_hot, pow and tensor arithmetic with numpy broadcasting.
 
 Eager: every op computes at once on numpy arrays.  ``get_variable`` hands out the arrays of
 ``VARIABLES`` (keyed by the variable-scope path, e.g. ``"l1/w"``) and asserts that the shape the
@@ -26,6 +28,7 @@ import types
 import numpy as np
 
 VARIABLES = {}        # "scope/name" -> float64 array; filled by the caller
+FEEDS = {}            # placeholder name -> array (eager: a placeholder IS its fed value)
 REQUESTED = []        # (path, shape) in the order the reference created them
 _scope = []
 
@@ -51,10 +54,30 @@ class Tensor(object):
     def get_shape(self):
         return Shape(self.value.shape)
 
+    # numpy broadcasting == TF broadcasting ([N] op [N,1] -> [N,N], the reference's D3 hazard)
     def __truediv__(self, other):
-        return Tensor(self.value / float(other))
+        return Tensor(self.value / _val(other))
 
     __div__ = __truediv__
+
+    def __add__(self, other):
+        return Tensor(self.value + _val(other))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return Tensor(self.value - _val(other))
+
+    def __rsub__(self, other):
+        return Tensor(_val(other) - self.value)
+
+    def __mul__(self, other):
+        return Tensor(self.value * _val(other))
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return Tensor(-self.value)
 
 
 def _val(x):
@@ -132,6 +155,43 @@ def _softmax(x, **k):
     return Tensor(e / e.sum(axis=-1, keepdims=True))
 
 
+def _placeholder(dtype, shape=None, name=None):
+    if name not in FEEDS:
+        raise KeyError("placeholder %r has no fed value" % (name,))
+    v = np.asarray(FEEDS[name], np.float64)
+    if shape is not None:
+        assert v.ndim == len(shape) and all(d is None or int(d) == n for d, n in zip(shape, v.shape)), (
+            name, shape, v.shape)
+    return Tensor(v)
+
+
+def _log(x, **k):
+    return Tensor(np.log(_val(x)))
+
+
+def _reduce_sum(x, reduction_indices=None, keep_dims=False, **k):
+    return Tensor(_val(x).sum(axis=reduction_indices, keepdims=keep_dims))
+
+
+def _one_hot(indices, depth, on_value=1.0, off_value=0.0, **k):
+    idx = np.asarray(_val(indices)).astype(np.int64)
+    out = np.full(idx.shape + (int(depth),), float(off_value))
+    np.put_along_axis(out, idx[..., None], float(on_value), axis=-1)
+    return Tensor(out)
+
+
+def _pow(x, y, **k):
+    return Tensor(_val(x) ** _val(y))
+
+
+def _square(x, **k):
+    return Tensor(_val(x) ** 2)
+
+
+def _reduce_mean(x, reduction_indices=None, keep_dims=False, **k):
+    return Tensor(_val(x).mean(axis=reduction_indices, keepdims=keep_dims))
+
+
 def _initializer(*a, **k):
     return ("initializer", a, tuple(sorted(k.items())))
 
@@ -144,6 +204,13 @@ def install():
     tf.get_variable = get_variable
     tf.matmul = _matmul
     tf.reshape = _reshape
+    tf.placeholder = _placeholder
+    tf.log = _log
+    tf.reduce_sum = _reduce_sum
+    tf.one_hot = _one_hot
+    tf.pow = _pow
+    tf.square = _square
+    tf.reduce_mean = _reduce_mean
     tf.constant_initializer = _initializer
     tf.random_normal_initializer = _initializer
     tf.truncated_normal_initializer = _initializer

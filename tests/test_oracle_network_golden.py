@@ -57,3 +57,40 @@ def test_forward_matches_executed_reference_layers(net_golden):
     # non-degenerate fixture: about half of every relu layer is active
     for k in ("a1", "a2", "h"):
         assert 0.3 < float((net_golden[k] > 0).mean()) < 0.7
+
+
+def test_loss_matches_executed_reference_lines(net_golden):
+    # network.py:60-94 executed verbatim, one sample at a time (see make_golden_network.py)
+    logits = torch.as_tensor(net_golden["logits"])
+    value = torch.as_tensor(net_golden["value"]).reshape(-1)
+    actions = torch.as_tensor(net_golden["actions"])
+    R = torch.as_tensor(net_golden["returns"])
+    total, pol, val = a3c.loss_per_sample(logits, value, actions, R, beta=float(net_golden["beta"]))
+    pi, logpi, ent = a3c.policy_terms(logits)
+    rows = net_golden["loss_rows"]
+    assert rel_err(pol.numpy(), rows[:, 0]) < 1e-12
+    assert rel_err(val.numpy(), rows[:, 1]) < 1e-12
+    assert rel_err(total.numpy(), rows[:, 2]) < 1e-12
+    assert rel_err(ent.numpy(), rows[:, 3]) < 1e-12
+    logp_a = logpi.gather(1, actions.reshape(-1, 1).long()).reshape(-1)
+    assert rel_err(logp_a.numpy(), rows[:, 4]) < 1e-12
+    # the closed-form gradients the CUDA loss kernel emits are the autograd gradients of that loss
+    lg = logits.clone().requires_grad_(True)
+    vv = value.clone().requires_grad_(True)
+    a3c.loss_per_sample(lg, vv, actions, R, beta=float(net_golden["beta"]))[0].sum().backward()
+    dl, dv = a3c.analytic_head_grads(logits, value, actions, R, beta=float(net_golden["beta"]))
+    assert rel_err(dl.numpy(), lg.grad.numpy()) < 1e-12 and rel_err(dv.numpy(), vv.grad.numpy()) < 1e-12
+
+
+def test_agent_scalar_formulas_match_executed_reference_lines(net_golden):
+    # agent.py:142-144, 154, 188-190, 395 and 310-314 executed verbatim with the reference's config.M1
+    g = net_golden
+    assert np.allclose([a3c.epsilon(int(s)) for s in g["steps"]], g["eps"], rtol=1e-15, atol=0)
+    assert np.allclose([a3c.learning_rate(int(s)) for s in g["steps"]], g["lrs"], rtol=1e-15, atol=0)
+    assert np.array_equal(a3c.clip_rewards(g["raw_rewards"]), g["clipped"])
+    tq = a3c.q_targets(g["q_next"], g["tq_rewards"], g["tq_terminals"])
+    assert np.allclose(tq, g["target_q"], rtol=1e-15, atol=0)
+    loss, delta = a3c.async_q_loss(torch.as_tensor(g["q_values"]), torch.as_tensor(g["q_actions"]),
+                                   torch.as_tensor(g["target_q"]))
+    assert abs(float(loss) - float(g["q_loss"])) <= 1e-15 * abs(float(g["q_loss"])) + 1e-18
+    assert np.allclose(delta.numpy(), g["q_delta"], rtol=1e-15, atol=0)
