@@ -36,6 +36,7 @@ and exec'd with ``self`` = the reference's ``config.M1``, imported unmodified):
     agent.py:142-144   epsilon schedule            agent.py:154       reward clip
     agent.py:188-190   1-step Q targets (numpy)    agent.py:395       learning-rate anneal
     agent.py:310-314   async-Q loss (one_hot, q_acted, delta, mean of squares; over the stub)
+    main.py:64-65, agent.py:319   the arguments handed to RMSPropOptimizer / clip_by_norm
 
 Inputs: two u8 stacks from a closed-form pattern and weights from ``golden_weights`` (closed
 form, no RNG), both reproducible anywhere; the fixture stores the inputs' checksums and the
@@ -191,6 +192,24 @@ def main(action_size=6):
     exec(loss_code, dict(self=me, tf=tf))
     q_loss, q_delta = float(me.loss.value), me.delta.value
 
+    # ---- optimizer hyper-parameters as the reference passes them (TF ops themselves: unpinned) --
+    msrc = open(os.path.join(REF, "main.py")).read().split("\n")
+    a = next(i for i, l in enumerate(msrc) if l.strip() == "optimizer = tf.train.RMSPropOptimizer(")
+    assert a + 1 == 64 and msrc[a + 1].strip() == "lr_op, decay=0.99, momentum=0, epsilon=0.1)"
+    rec = {}
+
+    class _Train(object):
+        @staticmethod
+        def RMSPropOptimizer(lr, **kw):
+            rec.update(kw)
+            return "optimizer"
+    tf.train = _Train
+    exec("\n".join(l.strip() for l in msrc[a:a + 2]).replace("(\n", "("), dict(tf=tf, lr_op="lr_op"))
+    clip_line = next(l.strip() for l in asrc if "tf.clip_by_norm(" in l)
+    assert clip_line == "new_grads_and_vars.append((tf.clip_by_norm(grad, 40), var))"      # agent.py:319
+    tf.clip_by_norm = lambda g, c: rec.setdefault("clip_norm", c)
+    exec(clip_line, dict(tf=tf, new_grads_and_vars=[], grad="grad", var="var"))
+
     req = dict(tf_stub.REQUESTED)
     assert req == {"l1/w": (8, 8, 4, 16), "l1/biases": (16,), "l2/w": (4, 4, 16, 32), "l2/biases": (32,),
                    "l3/Matrix": (2592, 256), "l3/bias": (256,),
@@ -206,6 +225,10 @@ def main(action_size=6):
         clipped=np.array(clipped), q_next=q_next, tq_rewards=np.array(tq_rewards),
         tq_terminals=np.array(tq_terminals), target_q=target_q, q_values=me.q.value,
         q_actions=q_actions, q_loss=q_loss, q_delta=q_delta,
+        rms_decay=float(rec["decay"]), rms_momentum=float(rec["momentum"]), rms_epsilon=float(rec["epsilon"]),
+        clip_norm=float(rec["clip_norm"]), base_lr=float(ref_config.M1.learning_rate),
+        max_step=int(ref_config.M1.max_step), discount=float(ref_config.M1.discount),
+        cfg_beta=float(ref_config.M1.beta),
         loss_rows=np.array(loss_rows),   # per sample: policy_loss, value_loss, total_loss, entropy, log pi(a)
         requested=np.array(sorted("%s %s" % kv for kv in req.items())))
     print("wrote", os.path.normpath(OUT), os.path.getsize(OUT), "bytes;",

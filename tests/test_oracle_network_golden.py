@@ -94,3 +94,24 @@ def test_agent_scalar_formulas_match_executed_reference_lines(net_golden):
                                    torch.as_tensor(g["target_q"]))
     assert abs(float(loss) - float(g["q_loss"])) <= 1e-15 * abs(float(g["q_loss"])) + 1e-18
     assert np.allclose(delta.numpy(), g["q_delta"], rtol=1e-15, atol=0)
+
+
+def test_hyperparameters_are_the_ones_the_reference_passes(net_golden, pkg):
+    # main.py:64-65 (RMSPropOptimizer arguments), agent.py:319 (clip_by_norm), config.py (M1):
+    # the oracle's defaults and the product's config mirror carry the same numbers
+    import inspect
+    g = net_golden
+    d = {k: v.default for k, v in inspect.signature(a3c.rmsprop_apply).parameters.items()
+         if v.default is not inspect.Parameter.empty}
+    assert d["decay"] == float(g["rms_decay"]) and d["eps"] == float(g["rms_epsilon"])
+    assert float(g["rms_momentum"]) == 0.0                      # the momentum slot stays zero: not modelled
+    assert inspect.signature(a3c.clip_by_norm).parameters["clip"].default == float(g["clip_norm"])
+    lr = inspect.signature(a3c.learning_rate).parameters
+    assert lr["max_step"].default == int(g["max_step"]) and lr["base"].default == float(g["base_lr"])
+    assert inspect.signature(a3c.nstep_returns).parameters["gamma"].default == float(g["discount"])
+    assert inspect.signature(a3c.loss_per_sample).parameters["beta"].default == float(g["cfg_beta"])
+    cfg = pkg.config.M1
+    assert (cfg.decay, cfg.epsilon, cfg.momentum, cfg.clip_norm) == (
+        float(g["rms_decay"]), float(g["rms_epsilon"]), float(g["rms_momentum"]), float(g["clip_norm"]))
+    assert (cfg.max_step, cfg.learning_rate, cfg.discount, cfg.beta) == (
+        int(g["max_step"]), float(g["base_lr"]), float(g["discount"]), float(g["cfg_beta"]))
