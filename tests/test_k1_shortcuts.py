@@ -86,3 +86,35 @@ def test_packed_vertical_pass_equals_cv2_formula():
         got[1::2] = (s >> 18) & 0xFF
         assert np.array_equal(got, want)
         assert int(want.max()) <= 255
+
+
+def test_store_address_map_covers_the_blocked_plane_once():
+    # phase B: lane (ry, s, m) of warp w stores outputs x = 21 m + s + 2k of row dy = (4w+1+ry) % 84
+    # at addr[k & 1] + 16 (k / 2), addr[] built from q0 = m + s; that must be the 4x4-blocked
+    # position ((dy/4)*21 + x/4)*16 + (dy%4)*4 + x%4 of src/history.py, each byte exactly once
+    seen = np.zeros(7056, np.int32)
+    for w in range(21):
+        for lane in range(32):
+            ry, s, m = lane >> 3, (lane >> 2) & 1, lane & 3
+            dy = (4 * w + 1 + ry) % 84
+            q0 = m + s
+            base = ((dy >> 2) * 21 + 5 * m) * 16 + (dy & 3) * 4
+            addr = [base + (q0 >> 2) * 16 + (q0 & 3), base + ((q0 + 2) >> 2) * 16 + ((q0 + 2) & 3)]
+            for k in range(11):
+                if not (k < 10 or s == 0):
+                    continue
+                x = 21 * m + s + 2 * k
+                a = addr[k & 1] + 16 * (k >> 1)
+                assert a == ((dy // 4) * 21 + x // 4) * 16 + (dy % 4) * 4 + x % 4, (w, lane, k)
+                seen[a] += 1
+    assert seen.min() == 1 and seen.max() == 1
+
+
+def test_phase_b_byte_offsets_stay_inside_the_lanes_ten_words():
+    # tap r of a period reads bytes sx, sx+1 of the lane's 40-byte segment: word k = sx / 4 and,
+    # for byte offset 3, word k + 1 -- never past word 9
+    for r in range(21):
+        sx = (80 * r + 19) // 42
+        k, o = sx >> 2, sx & 3
+        assert sx + 1 <= 39
+        assert k + (1 if o == 3 else 0) <= 9
