@@ -356,13 +356,13 @@ struct Conv1Fwd : tc::PolicyBase {
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
     constexpr uint32_t idesc = tc::make_idesc_i8(48);              // x(u8) . [L0 | L1 | L2](s8)
+    const uint64_t da0 = tc::make_sdesc(st, PL), db0 = tc::make_sdesc(res, PLB);   // one derivation per stage
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
-      const uint32_t a0 = st + ((tap >> 1) * GW + (tap & 1)) * 16;
 #pragma unroll
       for (int k32 = 0; k32 < 2; ++k32) {
-        const uint64_t da = tc::make_sdesc(a0 + 2 * k32 * PL, PL);
-        const uint64_t db = tc::make_sdesc(res + (tap * 4 + 2 * k32) * PLB, PLB);
+        const uint64_t da = tc::sdesc_advance(da0, ((tap >> 1) * GW + (tap & 1)) * 16 + 2 * k32 * PL);
+        const uint64_t db = tc::sdesc_advance(db0, (tap * 4 + 2 * k32) * PLB);
         tc::umma_i8(d, da, db, idesc, (tap | k32) != 0 ? 1u : 0u);
       }
     }
@@ -455,13 +455,15 @@ struct Conv2Fwd : tc::PolicyBase {
                                                uint32_t res, uint32_t d) {
     constexpr uint32_t idesc64 = tc::make_idesc(64), idesc32 = tc::make_idesc(32);
 #pragma unroll
+    const uint64_t da0 = tc::make_sdesc(st, PL), db0 = tc::make_sdesc(res, PLB);   // one derivation per stage
+#pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
-      const uint32_t a0 = st + ((tap >> 1) * GW + (tap & 1)) * 16;
+      const uint32_t aoff = ((tap >> 1) * GW + (tap & 1)) * 16;
 #pragma unroll
       for (int k16 = 0; k16 < 4; ++k16) {
-        const uint64_t da_hi = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
-        const uint64_t da_lo = tc::make_sdesc(a0 + IMG + 2 * k16 * PL, PL);
-        const uint64_t db = tc::make_sdesc(res + (tap * 8 + 2 * k16) * PLB, PLB);
+        const uint64_t da_hi = tc::sdesc_advance(da0, aoff + 2 * k16 * PL);
+        const uint64_t da_lo = tc::sdesc_advance(da0, aoff + IMG + 2 * k16 * PL);
+        const uint64_t db = tc::sdesc_advance(db0, (tap * 8 + 2 * k16) * PLB);
         tc::umma_f16(d, da_hi, db, idesc64, (tap | k16) != 0 ? 1u : 0u);   // x_hi . [w_hi | w_lo]
         tc::umma_f16(d, da_lo, db, idesc32, 1u);                            // x_lo . w_hi
       }
@@ -552,14 +554,16 @@ struct Conv2Dgrad : tc::PolicyBase {
                                                uint32_t res, uint32_t d) {
     constexpr uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
 #pragma unroll
+    const uint64_t da0 = tc::make_sdesc(st, PL), db0 = tc::make_sdesc(res, PLB);   // one derivation per stage
+#pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
       // output (yy,xx) of every class reads Z row P + 12 - 11*dkh - dkw
-      const uint32_t a0 = st + (12 - 11 * (tap >> 1) - (tap & 1)) * 16;
+      const uint32_t aoff = (12 - 11 * (tap >> 1) - (tap & 1)) * 16;
 #pragma unroll
       for (int k16 = 0; k16 < 2; ++k16) {
-        const uint64_t da_hi = tc::make_sdesc(a0 + 2 * k16 * PL, PL);
-        const uint64_t da_lo = tc::make_sdesc(a0 + IMG + 2 * k16 * PL, PL);
-        const uint64_t db = tc::make_sdesc(res + (tap * 4 + 2 * k16) * PLB, PLB);
+        const uint64_t da_hi = tc::sdesc_advance(da0, aoff + 2 * k16 * PL);
+        const uint64_t da_lo = tc::sdesc_advance(da0, aoff + IMG + 2 * k16 * PL);
+        const uint64_t db = tc::sdesc_advance(db0, (tap * 4 + 2 * k16) * PLB);
         tc::umma_f16(d, da_hi, db, idesc128, (tap | k16) != 0 ? 1u : 0u);  // z_hi . [wT_hi | wT_lo]
         tc::umma_f16(d, da_lo, db, idesc64, 1u);                            // z_lo . wT_hi
       }
@@ -712,13 +716,14 @@ struct Conv2Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
     constexpr uint32_t idesc = tc::make_idesc(64, true, true);       // [x_hi ; x_lo] . [dy_hi | dy_lo]
-    const uint32_t a_img = st, b_hi = st + 2 * A_IMG;                 // b_lo = b_hi + B_IMG
+    // a_img = st, b_hi = st + 2 * A_IMG (b_lo = b_hi + B_IMG); one descriptor derivation per stage
+    const uint64_t da0 = tc::make_sdesc(st, 128, PLA), db0 = tc::make_sdesc(st + 2 * A_IMG, 128, PLB);
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
 #pragma unroll
       for (int k16 = 0; k16 < 8; ++k16) {
-        const uint64_t da = tc::make_sdesc(a_img + ((tap >> 1) * GW + (tap & 1) + k16 * 16) * 16, 128, PLA);
-        const uint64_t db = tc::make_sdesc(b_hi + k16 * 256, 128, PLB);
+        const uint64_t da = tc::sdesc_advance(da0, ((tap >> 1) * GW + (tap & 1) + k16 * 16) * 16);
+        const uint64_t db = tc::sdesc_advance(db0, k16 * 256);
         tc::umma_f16(d + tap * 64, da, db, idesc, (s | k16) != 0 ? 1u : 0u);
       }
     }
@@ -799,11 +804,12 @@ struct Conv1Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
     constexpr uint32_t idesc = tc::make_idesc(64, true, true);     // x . [dy_hi | dy_lo | dy'_hi | dy'_lo]
-    const uint32_t a_img = st, b_hi = st + A_IMG;
+    // a_img = st, b_hi = st + A_IMG; one descriptor derivation per stage
+    const uint64_t da0 = tc::make_sdesc(st, 128, PLA), db0 = tc::make_sdesc(st + A_IMG, 128, PLB);
 #pragma unroll
     for (int k16 = 0; k16 < 8; ++k16)
-      tc::umma_f16(d, tc::make_sdesc(a_img + k16 * 256, 128, PLA), tc::make_sdesc(b_hi + k16 * 256, 128, PLB),
-                   idesc, (s | k16) != 0 ? 1u : 0u);
+      tc::umma_f16(d, tc::sdesc_advance(da0, k16 * 256), tc::sdesc_advance(db0, k16 * 256), idesc,
+                   (s | k16) != 0 ? 1u : 0u);
   }
   // row = b*64 + ch, ch = (cin*4 + i)*4 + j ; segment a = 16 co of tap (kh = 4a+i, kw = 4b+j)
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {

@@ -60,6 +60,22 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of a CONVERGED warp (elect.sync over the full mask: always the same lane).  The MMA
+// warp waits for its barriers converged and issues the tcgen05 instructions of a whole stage
+// inside ONE `if (elect_one())`: a region the compiler knows to be single-threaded, so every
+// tcgen05.mma is a bare UTCHMMA on uniform registers.  Inside `if (lane == 0)` it cannot prove
+// that and wraps EVERY UTCHMMA in an ELECT / R2UR / BRA.U.ANY sequence plus a fresh descriptor
+// derivation: 13-18 SASS instructions of one thread's serial chain per MMA (~8 cycles each), which
+// is what bounded the wgrad kernels (ncu: MMA warp 73-83 % busy, 95-173 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] . B[smem desc]
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                          uint32_t idesc, uint32_t accumulate) {
@@ -212,6 +228,12 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
                                                uint32_t sbo_bytes = 128) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+// the descriptor of the same image `bytes` further on (start-address field only; the shared
+// window is < 256 KB, so the 14-bit field cannot carry): one add instead of a re-derivation
+__device__ __forceinline__ uint64_t sdesc_advance(uint64_t d, uint32_t bytes) {
+  return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + (bytes >> 4));
 }
 
 // ---- chunk helpers (a chunk = 8 consecutive k of one row = 16 B of bf16) ---------------------
@@ -447,7 +469,7 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    {                                                    // the whole warp, converged (see elect_one)
       int i = 0, k = 0;                                  // k = this CTA's running tile count
       const uint32_t res_addr = smem_u32(res);
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
@@ -461,10 +483,14 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
           const int stage = i % STAGES;
           mbar_wait_sleep(&full[stage], (i / STAGES) & 1);
           tc_fence_after();
-          P::issue(g, tc, s, smem_u32(smem + stage * P::STAGE_BYTES), res_addr, d_tmem);
-          umma_commit(&empty[stage]);        // frees the smem stage when these MMAs retire
+          if (elect_one()) {
+            P::issue(g, tc, s, smem_u32(smem + stage * P::STAGE_BYTES), res_addr, d_tmem);
+            umma_commit(&empty[stage]);      // frees the smem stage when these MMAs retire
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull[acc]);            // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(&tfull[acc]);       // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -789,19 +815,22 @@ struct BulkGemm : PolicyBase {
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st, uint32_t,
                                                uint32_t d_tmem) {
     constexpr uint32_t idesc2 = make_idesc(CONCAT ? 2 * NT : NT, A_MN, B_MN), idesc1 = make_idesc(NT, A_MN, B_MN);
+    // one descriptor derivation per stage and operand image; every MMA advances them by constants
+    const uint64_t da_hi0 = A_MN ? make_sdesc(st, 128, A_PLANE) : make_sdesc(st, A_PLANE);
+    const uint64_t db0 = B_MN ? make_sdesc(st + B_OFF, 128, B_PLANE) : make_sdesc(st + B_OFF, B_PLANE);
 #pragma unroll
     for (int k16 = 0; k16 < KB / 16; ++k16) {
-      const uint32_t a = st + (A_MN ? k16 * 256 : k16 * 2 * A_PLANE);
-      const uint32_t b = st + B_OFF + (B_MN ? k16 * 256 : k16 * 2 * B_PLANE);
-      const uint64_t da_hi = A_MN ? make_sdesc(a, 128, A_PLANE) : make_sdesc(a, A_PLANE);
-      const uint64_t da_lo = A_MN ? make_sdesc(a + A_PART, 128, A_PLANE) : make_sdesc(a + A_PART, A_PLANE);
-      const uint64_t db = B_MN ? make_sdesc(b, 128, B_PLANE) : make_sdesc(b, B_PLANE);
+      const uint32_t aoff = A_MN ? k16 * 256 : k16 * 2 * A_PLANE;
+      const uint32_t boff = B_MN ? k16 * 256 : k16 * 2 * B_PLANE;
+      const uint64_t da_hi = sdesc_advance(da_hi0, aoff);
+      const uint64_t da_lo = sdesc_advance(da_hi0, aoff + A_PART);
+      const uint64_t db = sdesc_advance(db0, boff);
       if (CONCAT) {
         umma_f16(d_tmem, da_hi, db, idesc2, (s | k16) != 0 ? 1u : 0u);   // a_hi . [b_hi | b_lo]
         umma_f16(d_tmem, da_lo, db, idesc1, 1u);                          // a_lo . b_hi
       } else {
-        const uint32_t bl = b + (B_MN ? (NT / 8) * B_PLANE : NT * 16);    // the lo image follows the hi image
-        const uint64_t db_lo = B_MN ? make_sdesc(bl, 128, B_PLANE) : make_sdesc(bl, B_PLANE);
+        // the lo image follows the hi image
+        const uint64_t db_lo = sdesc_advance(db0, boff + (B_MN ? (NT / 8) * B_PLANE : NT * 16));
         umma_f16(d_tmem, da_hi, db, idesc1, (s | k16) != 0 ? 1u : 0u);   // a_hi . b_hi
         umma_f16(d_tmem, da_hi, db_lo, idesc1, 1u);                       // a_hi . b_lo
         umma_f16(d_tmem, da_lo, db, idesc1, 1u);                          // a_lo . b_hi
