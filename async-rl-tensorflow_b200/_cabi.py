@@ -22,6 +22,7 @@ SIGNATURES = {
     "arl_preprocess_push": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_preprocess_push_pil": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_upload_frames": [c_vp, c_vp, c_int, c_vp],
+    "arl_upload_frames_full": [c_vp, c_vp, c_int, c_vp],
     "arl_history_get": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_history_reset": [c_vp, c_int, c_int, c_vp],
     "arl_conv1_forward": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
@@ -46,7 +47,13 @@ SIGNATURES = {
     "arl_conv2_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_backward": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
-                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "arl_comm_unique_id": [c_vp],
+    "arl_comm_init": [c_vp, c_int, c_int],
+    "arl_comm_destroy": [],
+    "arl_allreduce_grads": [c_vp, c_i64, c_vp],
+    "arl_allreduce_begin": [c_vp, c_i64, c_i64, c_vp],
+    "arl_allreduce_end": [c_vp],
     "arl_clip_rmsprop": [c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
 }
 OTHER = {
@@ -55,6 +62,8 @@ OTHER = {
     "arl_backward_workspace_bytes": ([c_int], c_i64),
     "arl_prepared_floats": ([], c_i64),
     "arl_launch_count": ([c_int], c_i64),
+    "arl_comm_size": ([], c_int),
+    "arl_comm_nccl_version": ([], c_int),
 }
 EXPORTS = tuple(SIGNATURES) + tuple(OTHER)
 
@@ -142,3 +151,30 @@ def prepared_floats():
 
 def workspace_bytes(action_size):
     return int(load().arl_backward_workspace_bytes(int(action_size)))
+
+
+def comm_size():
+    """Ranks of the library's communicator (0 = arl_comm_init has not been called)."""
+    return int(load().arl_comm_size())
+
+
+def comm_init(device):
+    """arl_comm_init for this process from the torch.distributed world: rank 0 makes the NCCL id
+    (arl_comm_unique_id), torch.distributed carries its 128 bytes to the other ranks -- plumbing
+    only; the gradients themselves never go through torch."""
+    import torch.distributed as dist
+    if comm_size():
+        return comm_size()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        check(load().arl_comm_unique_id(buf), "arl_comm_unique_id")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    on_dev = dist.get_backend() == "nccl"
+    if on_dev:
+        t = t.to(device)
+    dist.broadcast(t, 0)
+    idb = ctypes.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+    with torch.cuda.device(device):
+        check(load().arl_comm_init(idb, rank, world), "arl_comm_init")
+    return world

@@ -45,6 +45,7 @@ class AgentConfig(object):
     clip_norm = 40.0                     # agent.py:319
     resize = 'cv2'                       # environment.py:5-12 executed branch
     loss_mode = 'a3c'                    # 'a3c' (network.py heads/loss) | 'async_q' (agent.py as run)
+    collective = 'library'               # gradient all-reduce: 'library' (arl_comm_*, NCCL in the .so) | 'torch'
 
 
 class EnvironmentConfig(object):

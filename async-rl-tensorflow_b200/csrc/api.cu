@@ -23,8 +23,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 static long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
 
-static int g_num_sms = 0;
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+// SM count per device index (arl_init fills it); num_sms() answers for the CURRENT device
+static int g_num_sms[64] = {0};
+int num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const int n = g_num_sms[dev & 63];
+  return n > 0 ? n : 148;
+}
 
 int preprocess_init(int device);
 int conv_init();
@@ -57,7 +63,7 @@ extern "C" int arl_init(int device) {
     cudaSetDevice(prev);
     return ARL_ERR_UNSUPPORTED;
   }
-  g_num_sms = prop.multiProcessorCount;
+  g_num_sms[device & 63] = prop.multiProcessorCount;
   int rc = preprocess_init(device);
   if (rc == ARL_OK) rc = conv_init();
   if (rc == ARL_OK) rc = heads_init();
@@ -102,15 +108,26 @@ extern "C" int arl_backward(const float* params, const float* prepared, int acti
                             int steps, const float* a1,
                             const float* a2, const float* h, const float* dlogits,
                             const float* dvalue, float* d_h, float* d_a2, float* d_a1, float* grads,
-                            void* workspace, void* stream) {
+                            void* workspace, int allreduce, void* stream) {
   const int64_t N = (int64_t)num_envs * steps;
   int rc = arl_heads_backward(params, action_size, h, dlogits, dvalue, d_h, grads, workspace, N,
                               stream);
   if (rc) return rc;
   rc = arl_fc_backward(prepared, a2, num_envs, d_h, d_a2, grads, workspace, N, stream);
   if (rc) return rc;
+  // l4_w .. q_b are final now: 98 % of the gradient bytes travel while the conv kernels run
+  const bool comm = allreduce && arl_comm_size() > 1;
+  const ParamLayout L = param_layout(action_size);
+  if (comm) {
+    rc = arl_allreduce_begin(grads, L.off[T_L4W], L.off[ARL_NUM_TENSORS] - L.off[T_L4W], stream);
+    if (rc) return rc;
+  }
   rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, stream);
   if (rc) return rc;
-  return arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps,
-                            stream);
+  rc = arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps,
+                          stream);
+  if (rc || !comm) return rc;
+  rc = arl_allreduce_begin(grads, 0, L.off[T_L4W], stream);        // l1_w .. l2_b
+  if (rc) return rc;
+  return arl_allreduce_end(stream);
 }

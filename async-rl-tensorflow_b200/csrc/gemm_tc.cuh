@@ -29,6 +29,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace arl {
@@ -624,10 +626,15 @@ int launch(const typename P::Args& g, int items, cudaStream_t stream) {
   using S = Smem<P>;
   static_assert(S::TOTAL <= 227 * 1024, "smem budget");
   auto kern = tc_kernel<P>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one flag per device index (a process may drive several
+  // GPUs through arl_init(device)); racing host threads at worst set the attribute twice
+  static std::atomic<uint64_t> attr_set{0};
+  int dev = 0;
+  ARL_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_set.load(std::memory_order_acquire) & bit)) {
     ARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+    attr_set.fetch_or(bit, std::memory_order_release);
   }
   if (items <= 0) return ARL_OK;
   const int grid = items < num_sms() ? items : num_sms();

@@ -540,12 +540,29 @@ extern "C" int arl_upload_frames(const uint8_t* host_frames, uint8_t* dev_frames
   ARL_REQUIRE(host_frames && dev_frames, "arl_upload_frames: null pointer");
   ARL_REQUIRE(num_envs >= 0, "arl_upload_frames: num_envs %d < 0", num_envs);
   if (num_envs == 0) return ARL_OK;
-  // a frame = 42 groups of 5 rows (2400 B); K1 reads rows 0,1 and 3,4 of every group
+  // a frame = 42 groups of 5 rows (2400 B); K1 reads rows 0,1 and 3,4 of every group.  Because
+  // 210 = 0 (mod 5) those rows form ONE uniform pattern over the whole batch: 4-row runs (1920 B)
+  // at a 5-row pitch starting at row 3 (rows 3..6, 8..11, ...; a run that starts at row 208 of a
+  // frame ends with rows 0, 1 of the next) -- one 2-D copy with half the DMA segments of two
+  // 960-B-run copies -- plus rows 0, 1 of the first frame and rows 208, 209 of the last.
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t pitch = 5 * kRowBytes, groups = (size_t)num_envs * (kH / 5);
-  ARL_CUDA(cudaMemcpy2DAsync(dev_frames, pitch, host_frames, pitch, 2 * kRowBytes, groups,
-                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  ARL_CUDA(cudaMemcpy2DAsync(dev_frames + 3 * kRowBytes, pitch, host_frames + 3 * kRowBytes, pitch,
-                             2 * kRowBytes, groups, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  ARL_CUDA(cudaMemcpyAsync(dev_frames, host_frames, 2 * kRowBytes, cudaMemcpyHostToDevice, st));
+  if (groups > 1)
+    ARL_CUDA(cudaMemcpy2DAsync(dev_frames + 3 * kRowBytes, pitch, host_frames + 3 * kRowBytes, pitch,
+                               4 * kRowBytes, groups - 1, cudaMemcpyHostToDevice, st));
+  const size_t tail = (groups * 5 - 2) * kRowBytes;
+  ARL_CUDA(cudaMemcpyAsync(dev_frames + tail, host_frames + tail, 2 * kRowBytes, cudaMemcpyHostToDevice, st));
+  return ARL_OK;
+}
+
+extern "C" int arl_upload_frames_full(const uint8_t* host_frames, uint8_t* dev_frames, int num_envs,
+                                      void* stream) {
+  ARL_REQUIRE(host_frames && dev_frames, "arl_upload_frames_full: null pointer");
+  ARL_REQUIRE(num_envs >= 0, "arl_upload_frames_full: num_envs %d < 0", num_envs);
+  if (num_envs == 0) return ARL_OK;
+  ARL_CUDA(cudaMemcpyAsync(dev_frames, host_frames, (size_t)num_envs * kH * kRowBytes,
+                           cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return ARL_OK;
 }
 

@@ -48,6 +48,14 @@ class Agent(BaseModel):
             decay=self.decay, epsilon=self.epsilon, clip_norm=self.clip_norm,
             min_reward=self.min_reward, max_reward=self.max_reward)
         self.w = self.network.w
+        # the per-cycle exchange runs inside the library (arl_comm_init / arl_backward(allreduce=1):
+        # NCCL, bucketed so that the fc256 gradient travels while the conv backward kernels run);
+        # collective='torch' keeps the all-reduce in torch.distributed (debugging / gloo)
+        self.collective = getattr(config, 'collective', 'library')
+        if self.collective not in ('library', 'torch'):
+            raise ValueError("collective must be 'library' or 'torch'")
+        if self.world_size > 1 and self.collective == 'library':
+            _cabi.comm_init(self.device)
 
         T, B = self.t_max, self.num_envs
         self.batch_reward = torch.zeros(T, B, device=self.device)
@@ -68,18 +76,22 @@ class Agent(BaseModel):
 
     # -- agent.py:33-50 ---------------------------------------------------------------------
     def before_train(self, is_chief=True):
-        self.T = self.step = self.step_op
+        self.step = self.step_op
+        self.T = self.step_op * self.global_envs                 # agent.py:165 counts every worker's frames
         self.env.new_random_game()
         # agent.py:37-38: the stack starts as 4 copies of the first screen (K1, replicate=4)
         self.history.add(self.env.frames, replicate=self.history_length)
         self.t = 0
         self.update_target_q_network()                           # main.py:92
+        if self.loss_mode == 'async_q':
+            self._last_target_sync = self.T
         return self.env.frames, 0, 0, self.env.terminal, range(self.step, self.max_step)
 
     # -- agent.py:52-67 ---------------------------------------------------------------------
     def train(self, sv=None, is_chief=True, num_steps=None):
         screen, reward, action, terminal, iterator = self.before_train(is_chief)
         end = self.max_step if num_steps is None else min(self.max_step, self.step + num_steps)
+        ran = False
         for self.step in range(self.step, end):
             # 1. predict
             action = self.predict()
@@ -87,9 +99,13 @@ class Agent(BaseModel):
             screen, reward, terminal = self.env.act(action, is_training=True, fused=True)
             # 3. observe
             self.observe(screen, reward, action, terminal)
-            # agent.py:66-67: finished envs restart inside the (batched) backend; like the
-            # reference, the History is NOT reset on terminal.
-        self.step_op = self.step + 1
+            # agent.py:66-67: the envs that died restart (their own random-start draw each); like
+            # the reference, the History is NOT reset on terminal and the restart screen is dropped
+            if self.env.per_env_restart:
+                self.env.new_random_game(mask=terminal)
+            ran = True
+        if ran:
+            self.step_op = self.step + 1
         return self.step_op
 
     # -- agent.py:69-139 --------------------------------------------------------------------
@@ -112,11 +128,15 @@ class Agent(BaseModel):
         test_step = max(1, int(self.test_step))
         records = []
         out = open(log_path, 'a') if (log_path and is_chief) else None
+        ran = False
         for self.step in range(self.step, end):
+            ran = True
             action = self.predict()
             screen, reward, terminal = self.env.act(action, is_training=True, fused=True)
             before = self.update_count
             self.observe(screen, reward, action, terminal, is_chief=True)
+            if self.env.per_env_restart:                         # agent.py:66-67
+                self.env.new_random_game(mask=terminal)
             if self.update_count != before:                      # agent.py:199-201
                 sums = self.network.loss_sums
                 if self.loss_mode == 'async_q':
@@ -164,7 +184,8 @@ class Agent(BaseModel):
                 updates = 0
         if out is not None:
             out.close()
-        self.step_op = self.step + 1
+        if ran:
+            self.step_op = self.step + 1
         return records
 
     # -- checkpoints: agent.py:29 Saver(w + step_op), main.py:74-80 Supervisor autosave ------
@@ -264,17 +285,19 @@ class Agent(BaseModel):
     # -- agent.py:169-207 -------------------------------------------------------------------
     def batch_update(self, is_chief=False):
         net = self.network
+        in_lib = self.world_size > 1 and self.collective == 'library'
         if self.loss_mode == 'async_q':
             # agent.py:312-314 mean over the worker's batch; mean over (global) envs as in a3c mode
             scale = 1.0 / (self.t_max * self.global_envs) if self.reduce_mean else 1.0 / self.t_max
-            net.compute_q_gradients(self.history, self.batch_reward, self.batch_terminal, scale)
+            net.compute_q_gradients(self.history, self.batch_reward, self.batch_terminal, scale,
+                                    allreduce=in_lib)
         else:
             v_boot = net.bootstrap_value(self.history)           # R = V(s_T), masked if terminal
             scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
             net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
-                                  grad_scale=scale)
-        if self.world_size > 1:
-            dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)     # the one exchange per cycle
+                                  grad_scale=scale, allreduce=in_lib)   # the one exchange per cycle
+        if self.world_size > 1 and not in_lib:
+            dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)
         net.apply_gradients(self.lr)
         self.update_count += 1
         self.t = 0

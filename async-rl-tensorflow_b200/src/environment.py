@@ -92,7 +92,18 @@ class SyntheticAtari(object):
         self._i = 0
         self.ale = _ALE(self)
         self.action_space = _ActionSpace(self, int(action_size))
-        self.h2d_bytes_per_step = B * 168 * FRAME_SHAPE[1] * FRAME_SHAPE[2] if host else 0
+        self.set_resize('cv2')
+
+    def set_resize(self, resize):
+        """Called by Environment with its resize branch (environment.py:5-12).  'cv2' reads 168 of
+        the 210 source rows, so only those cross PCIe; 'pil' (scipy.misc.imresize) reads every
+        row, so the whole frame is uploaded."""
+        self.resize = resize
+        rows = 168 if resize == 'cv2' else FRAME_SHAPE[0]
+        self._upload_fn = "arl_upload_frames" if resize == 'cv2' else "arl_upload_frames_full"
+        self.h2d_bytes_per_step = self.num_envs * rows * FRAME_SHAPE[1] * FRAME_SHAPE[2] if self.host else 0
+        if self.host:
+            self._staged_for = [-1, -1]                          # staged frames may lack rows
 
     def _upload(self, i):
         """Queue the pinned-host -> device copy of step i's frames on the copy stream.  The copy
@@ -103,8 +114,8 @@ class SyntheticAtari(object):
             return
         self._copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
-            # only the 168 of 210 rows K1 reads cross PCIe (80 640 B per frame)
-            _cabi.call("arl_upload_frames", self._frames[i % self.pool].data_ptr(),
+            # cv2 branch: only the 168 of 210 rows K1 reads cross PCIe (80 640 B per frame)
+            _cabi.call(self._upload_fn, self._frames[i % self.pool].data_ptr(),
                        _cabi.ptr(self._stage[k]), self.num_envs, self._copy_stream.cuda_stream)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
@@ -140,8 +151,8 @@ class GymVectorAdapter(object):
     ``action_space.n`` / ``.sample()``.  The emulators run on the host; each step's frames are
     gathered into one pinned buffer u8 [B,210,160,3] and cross PCIe once -- on a CUDA device only
     the 168 of 210 rows K1 reads (arl_upload_frames), double-buffered so that the copy of step
-    i+1 can overlap the kernels of step i.  Finished episodes are reset in place (the reference
-    resets in new_game when lives == 0, environment.py:29-31)."""
+    i+1 can overlap the kernels of step i.  ``restart(mask, noop_steps)`` is the per-env
+    new_random_game of the reference's training loop (agent.py:66-67, environment.py:28-40)."""
 
     def __init__(self, envs, device='cuda', auto_reset=True):
         self.envs = list(envs)
@@ -156,10 +167,20 @@ class GymVectorAdapter(object):
         self._rew = torch.zeros(B, dtype=torch.float32)
         self._term = torch.zeros(B, dtype=torch.bool)
         self._lives_host = torch.zeros(B, dtype=torch.int32)
+        self._over = [True] * B                                  # game over, waiting for a reset
+        self._uploaded = [None, None]                            # event after each buffer's upload
         self.ale = self                                          # ale.lives()
         self.action_space = self                                 # action_space.n / .sample()
         self.n = int(self.envs[0].action_space.n)
-        self.h2d_bytes_per_step = B * 168 * FRAME_SHAPE[1] * FRAME_SHAPE[2] if pin else 0
+        self.set_resize('cv2')
+
+    def set_resize(self, resize):
+        """See SyntheticAtari.set_resize: 'pil' needs every source row on the device."""
+        self.resize = resize
+        rows = 168 if resize == 'cv2' else FRAME_SHAPE[0]
+        self._upload_fn = "arl_upload_frames" if resize == 'cv2' else "arl_upload_frames_full"
+        pin = self.device.type == 'cuda'
+        self.h2d_bytes_per_step = self.num_envs * rows * FRAME_SHAPE[1] * FRAME_SHAPE[2] if pin else 0
 
     # -- gym surface of one emulator ---------------------------------------------------------
     @staticmethod
@@ -178,8 +199,10 @@ class GymVectorAdapter(object):
 
     @staticmethod
     def _lives_one(env):
+        """ale.lives(); 0 for emulators without an ALE (no lives: every terminal is a game over,
+        so new_game's ``lives == 0`` reset rule of environment.py:29-31 resets them)."""
         ale = getattr(env, 'ale', None) or getattr(getattr(env, 'unwrapped', env), 'ale', None)
-        return int(ale.lives()) if ale is not None else 1
+        return int(ale.lives()) if ale is not None else 0
 
     # -- batched surface ---------------------------------------------------------------------
     def lives(self):
@@ -196,17 +219,21 @@ class GymVectorAdapter(object):
         self._k ^= 1
         host, dev = self._host[k], self._dev[k]
         if self.device.type == 'cuda':
-            _cabi.call("arl_upload_frames", host.data_ptr(), _cabi.ptr(dev), self.num_envs,
+            _cabi.call(self._upload_fn, host.data_ptr(), _cabi.ptr(dev), self.num_envs,
                        _cabi.stream_ptr())
+            self._uploaded[k] = torch.cuda.Event()
+            self._uploaded[k].record()
         else:
             dev.copy_(host)
         return dev
 
     def _host_buffer(self):
         """The pinned buffer the next upload will read; its previous upload (two steps ago) must
-        have completed before the emulators overwrite it."""
-        if self.device.type == 'cuda':
-            torch.cuda.current_stream().synchronize()
+        have completed before the emulators overwrite it (one event per buffer, not a stream
+        synchronize: the kernels of the previous step keep running while the emulators step)."""
+        ev = self._uploaded[self._k]
+        if ev is not None:
+            ev.synchronize()
         return self._host[self._k]
 
     def reset(self, mask=None):
@@ -217,19 +244,55 @@ class GymVectorAdapter(object):
         for b, e in enumerate(self.envs):
             if mask is None or mask[b]:
                 buf[b].copy_(torch.as_tensor(self._reset_one(e)))
+                self._over[b] = False
             else:
                 buf[b].copy_(prev[b])
         return self._upload()
 
     def step(self, actions):
+        """One emulator step per env.  The frame of a terminal step IS the terminal frame (the
+        reference pushes it into the history, agent.py:62-64, and only then restarts the env).  An
+        emulator whose game is over and that has not been restarted is not stepped again: with
+        ``auto_reset`` it is reset on its next step (reward 0, not terminal), otherwise it idles on
+        its last frame (reward 0, terminal)."""
         acts = actions.cpu().tolist()
         buf = self._host_buffer()
+        prev = self._host[self._k ^ 1]
         for b, e in enumerate(self.envs):
+            if self._over[b]:
+                if self.auto_reset:
+                    buf[b].copy_(torch.as_tensor(self._reset_one(e)))
+                    self._rew[b], self._term[b], self._over[b] = 0.0, False, False
+                else:
+                    buf[b].copy_(prev[b])
+                    self._rew[b], self._term[b] = 0.0, True
+                continue
             frame, self._rew[b], self._term[b] = self._step_one(e, acts[b])
-            if self._term[b] and self.auto_reset and self._lives_one(e) == 0:
-                frame = self._reset_one(e)
+            self._over[b] = bool(self._term[b]) and self._lives_one(e) == 0
             buf[b].copy_(torch.as_tensor(frame))
         return (self._upload(), self._rew.to(self.device), self._term.to(self.device), {})
+
+    def restart(self, mask, noop_steps):
+        """new_random_game for the envs in ``mask`` only (agent.py:66-67 restarts the env that
+        died; environment.py:28-40): reset if the game is over (lives == 0), one no-op step, then
+        ``noop_steps[b]`` further no-op steps -- each env its own count.  The other envs keep their
+        last frame.  Returns (frames, rewards, terminals) like ``step``."""
+        buf = self._host_buffer()
+        prev = self._host[self._k ^ 1]
+        for b, e in enumerate(self.envs):
+            if not mask[b]:
+                buf[b].copy_(prev[b])
+                continue
+            if self._over[b] or self._lives_one(e) == 0:          # environment.py:29-30
+                frame = self._reset_one(e)
+                self._over[b] = False
+            for _ in range(1 + int(noop_steps[b])):               # environment.py:31, 37-38
+                frame, self._rew[b], self._term[b] = self._step_one(e, 0)
+                if self._term[b] and self._lives_one(e) == 0:      # died during its random start
+                    self._over[b] = True
+                    break
+            buf[b].copy_(torch.as_tensor(frame))
+        return self._upload(), self._rew.to(self.device), self._term.to(self.device)
 
     def render(self):
         for e in self.envs:
@@ -250,6 +313,8 @@ class Environment(object):
         self._push = "arl_preprocess_push" if self.resize == 'cv2' else "arl_preprocess_push_pil"
         self.env = env if env is not None else SyntheticAtari(
             self.num_envs, seed=getattr(config, 'seed', 123), device=self.device)
+        if hasattr(self.env, 'set_resize'):                      # host-fed backends: which rows to upload
+            self.env.set_resize(self.resize)
         screen_width, screen_height, self.action_repeat, self.random_start = \
             config.screen_width, config.screen_height, config.action_repeat, config.random_start
         self.display = config.display
@@ -262,6 +327,12 @@ class Environment(object):
         self._scratch = torch.empty(self.num_envs, 4, SCREEN, SCREEN, dtype=torch.uint8,
                                     device=self.device)
 
+    @property
+    def per_env_restart(self):
+        """True when the backend can restart single envs (real emulators): the training loop then
+        calls new_random_game(mask=terminal) after every step, as agent.py:66-67 does."""
+        return hasattr(self.env, 'restart')
+
     def new_game(self, from_random_game=False):
         """environment.py:28-33: reset the envs that are out of lives, then one no-op step."""
         dead = self.lives == 0
@@ -271,8 +342,23 @@ class Environment(object):
         self.render()
         return self.screen, 0, 0, self.terminal
 
-    def new_random_game(self):
-        """environment.py:35-40 (one random_start draw shared by the batch)."""
+    def new_random_game(self, mask=None):
+        """environment.py:35-40.  With a backend that can restart single envs every env in
+        ``mask`` (default: all) draws its OWN ``random.randint(0, random_start - 1)`` no-op count
+        (environment.py:37, in env order) -- one reference worker per env.  Backends that only step
+        in lockstep (SyntheticAtari: frames come from a fixed pool, there is no emulator state to
+        restart) share one draw, and a masked restart is a no-op for them."""
+        if self.per_env_restart:
+            m = [True] * self.num_envs if mask is None else [bool(v) for v in mask.cpu().tolist()]
+            if self._screen is None:
+                m = [True] * self.num_envs
+            steps = [random.randint(0, self.random_start - 1) if v else 0 for v in m]
+            if any(m):
+                self._screen, self.reward, self.terminal = self.env.restart(m, steps)
+            self.render()
+            return self.screen, 0, 0, self.terminal
+        if mask is not None:
+            return self._screen, 0, 0, self.terminal
         self.new_game(True)
         for _ in range(random.randint(0, self.random_start - 1)):
             self._step(self._noop())
@@ -335,9 +421,13 @@ class GymEnvironment(Environment):
                                   torch.empty(self.num_envs, dtype=torch.bool, device=self.device))
                                  for _ in range(2)]
             rew, term = self._act_out[k]
-            _cabi.call("arl_act_update", _cabi.ptr(self.reward.float()), _cabi.ptr(self.terminal.bool()),
-                       _cabi.ptr(start_lives), _cabi.ptr(self.lives.int()), 1 if is_training else 0,
+            # converted copies are bound to names that outlive the launch (a temporary's memory
+            # could be handed to the next allocation before the kernel has read it)
+            rew_in, term_in, lives_now = self.reward.float(), self.terminal.bool(), self.lives.int()
+            _cabi.call("arl_act_update", _cabi.ptr(rew_in), _cabi.ptr(term_in),
+                       _cabi.ptr(start_lives), _cabi.ptr(lives_now), 1 if is_training else 0,
                        _cabi.ptr(rew), _cabi.ptr(term), self.num_envs, _cabi.stream_ptr())
+            self._act_in = (rew_in, term_in, lives_now, start_lives)
             self.reward, self.terminal = rew, term
             self.after_act(action)
             if fused:

@@ -246,9 +246,9 @@ class Network(object):
     def sample(self, t, step, seed, env_id_base=0):
         """network.py:72-73 sampled_action for rollout slot t."""
         r = self._rows(t)
-        _cabi.call("arl_sample_actions", _cabi.ptr(self.policy[r]),
-                   _cabi.ptr(self.sampled_action[r]), self.num_envs, self.action_size,
-                   int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
+        self._timed_call("arl_sample_actions", _cabi.ptr(self.policy[r]),
+                         _cabi.ptr(self.sampled_action[r]), self.num_envs, self.action_size,
+                         int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
         return self.sampled_action[r]
 
     def bootstrap_value(self, history):
@@ -291,18 +291,18 @@ class Network(object):
 
     # -- backward ---------------------------------------------------------------------------
     def compute_gradients(self, history, rewards, terminals, v_boot, actions=None,
-                          grad_scale=1.0):
+                          grad_scale=1.0, allreduce=False):
         """Returns + loss grads (K4) then the full backward (agent.py:317) over the T*B samples
         of the rollout.  ``history`` must have had exactly t_max pushes since s_0."""
         T, B, A = self.t_max, self.num_envs, self.action_size
         acts = self.sampled_action if actions is None else actions
         self.loss_sums.zero_()
         st = _cabi.stream_ptr()
-        _cabi.call("arl_returns_lossgrad", _cabi.ptr(rewards), _cabi.ptr(terminals),
-                   _cabi.ptr(acts), _cabi.ptr(self.policy_logits), _cabi.ptr(self.value),
-                   _cabi.ptr(v_boot), _cabi.ptr(self.R), _cabi.ptr(self.d_logits),
-                   _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
-                   self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
+        self._timed_call("arl_returns_lossgrad", _cabi.ptr(rewards), _cabi.ptr(terminals),
+                         _cabi.ptr(acts), _cabi.ptr(self.policy_logits), _cabi.ptr(self.value),
+                         _cabi.ptr(v_boot), _cabi.ptr(self.R), _cabi.ptr(self.d_logits),
+                         _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
+                         self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
         P = _cabi.ptr
         if self._fc_w_stale():                                 # (a forward normally did this already)
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
@@ -310,17 +310,23 @@ class Network(object):
             _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                        history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2),
                        P(self.l4), P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
-                       P(self.d_l1), P(self.grads), P(self.workspace), st)
+                       P(self.d_l1), P(self.grads), P(self.workspace), 1 if allreduce else 0, st)
             return self.grads
         N = T * B
         self._timed_call("arl_heads_backward", P(self.params), A, P(self.l4), P(self.d_logits),
                          P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, st)
         self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), B, P(self.d_l4), P(self.d_l2),
                          P(self.grads), P(self.workspace), N, st)
+        if allreduce:                                          # same bucket order as arl_backward
+            lo = self.offsets[4]
+            _cabi.call("arl_allreduce_begin", P(self.grads), lo, self.offsets[-1] - lo, st)
         self._timed_call("arl_conv2_backward", P(self.fc_w), P(self.l1), P(self.d_l2),
                          P(self.d_l1), P(self.grads), P(self.workspace), N, st)
         self._timed_call("arl_conv1_backward", P(history.ring), P(self.d_l1), P(self.grads),
                          P(self.workspace), B, history.ring_slots, history.first_slot(T), T, st)
+        if allreduce:
+            _cabi.call("arl_allreduce_begin", P(self.grads), 0, self.offsets[4], st)
+            _cabi.call("arl_allreduce_end", st)
         return self.grads
 
     # -- async-Q mode (agent.py:169-207, 298-314): the Q head lives in the p_w/p_b slot ---------
@@ -347,7 +353,7 @@ class Network(object):
                    int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
         return self.sampled_action[r]
 
-    def compute_q_gradients(self, history, rewards, terminals, grad_scale):
+    def compute_q_gradients(self, history, rewards, terminals, grad_scale, allreduce=False):
         """agent.py:186-197: target-network forward over s_1..s_T, 1-step targets, MSE gradient,
         backward.  The backward scratch buffers hold the target activations meanwhile."""
         T, B, A = self.t_max, self.num_envs, self.action_size
@@ -367,7 +373,7 @@ class Network(object):
         _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                    history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
                    P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
-                   P(self.d_l1), P(self.grads), P(self.workspace), st)
+                   P(self.d_l1), P(self.grads), P(self.workspace), 1 if allreduce else 0, st)
         return self.grads
 
     @property
@@ -376,10 +382,10 @@ class Network(object):
 
     def apply_gradients(self, lr):
         """agent.py:316-321: per-tensor clip_by_norm(40) + shared RMSProp (K5)."""
-        _cabi.call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
-                   _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
-                   self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
-                   _cabi.stream_ptr())
+        self._timed_call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                         _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
+                         self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
+                         _cabi.stream_ptr())
         self._param_writes += 1                                # the kernel wrote params: fc_w is stale
 
     # -- checkpoints (network.py:109-127), reference variable names + the rms slot ----------

@@ -32,14 +32,16 @@ def conv2d(x, params, output_dim, kernel_size, stride, out=None, name='l1', step
         if out is None:
             out = torch.empty(n, 20, 20, 16, device=params.device)
         first = hist.first_slot(steps - 1)
-        _cabi.call("arl_conv1_forward", _cabi.ptr(_prepared(params)), _cabi.ptr(hist.ring), _cabi.ptr(out),
+        prep = _prepared(params)                                 # named: must outlive the launch
+        _cabi.call("arl_conv1_forward", _cabi.ptr(prep), _cabi.ptr(hist.ring), _cabi.ptr(out),
                    hist.num_envs, hist.ring_slots, first, steps, _cabi.stream_ptr())
         return out
     if name == 'l2' and (output_dim, ks, st) == (32, (4, 4), (2, 2)):
         n = x.shape[0]
         if out is None:
             out = torch.empty(n, 9, 9, 32, device=params.device)
-        _cabi.call("arl_conv2_forward", _cabi.ptr(_prepared(params)), _cabi.ptr(x), _cabi.ptr(out), n,
+        prep = _prepared(params)
+        _cabi.call("arl_conv2_forward", _cabi.ptr(prep), _cabi.ptr(x), _cabi.ptr(out), n,
                    _cabi.stream_ptr())
         return out
     raise NotImplementedError("conv2d %s: only the 'nips' trunk layers are built "
@@ -59,7 +61,8 @@ def linear(input_, params, output_size, out=None, name='l4', input_is_split=True
         if out is None:
             out = torch.empty(n, FC, device=params.device)
         # x is the split block conv2d(name='l2') wrote
-        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(_prepared(params)), _cabi.ptr(x),
+        prep = _prepared(params)
+        _cabi.call("arl_fc_forward", _cabi.ptr(params), _cabi.ptr(prep), _cabi.ptr(x),
                    _cabi.ptr(out), n, _cabi.stream_ptr())
         return out
     raise NotImplementedError("linear %s: only the fc256 layer is exposed stand-alone; the "

@@ -31,29 +31,51 @@ if ROOT not in sys.path:
 METRIC = "env_frames_per_sec"
 UNIT = "frames/s"
 
-# algorithmic work per sample / frame (DESIGN.md kernel table)
-ENTRY_WORK = {
-    # entry: (kernels behind it, flop per sample (one exact pass), algorithmic HBM bytes per sample)
-    "arl_preprocess_push": ("preprocess_kernel", 0.0, 80640 + 7056),
-    "arl_conv1_forward": ("tc_kernel<Conv1Fwd> (kind::i8, bulk-copied ring)", 2.0 * 1638400, 28224 + 25600),
-    "arl_conv2_forward": ("tc_kernel<Conv2Fwd> (bulk-copied a1s, split-bf16 a2 blocks out)", 2.0 * 663552, 25600 + 10368),
-    "arl_fc_forward": ("tc_kernel<BulkGemm fc fwd> (bulk-copied split-bf16 operands)", 2.0 * 663552, 10368 + 1024),
-    "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * 7, 1024 + 56),
-    "arl_heads_backward": ("heads_bwd_kernel", 4.0 * 256 * 7, 2048 + 28),
-    # dgrad: d_h + relu mask (hi part of a2: 5184) in, d_a2 out; wgrad: a2 + d_h in
-    "arl_fc_backward": ("tc_kernel<BulkGemm fc dgrad> + <fc wgrad>", 4.0 * 663552,
-                        1024 + 5184 + 10368 + 10368 + 1024),
-    # wgrad: a1 + d_a2 in; dgrad: d_a2 + relu mask (hi part of a1: 12800) in, d_a1 on the 21x21 grid out
-    "arl_conv2_backward": ("tc_kernel<Conv2Wgrad> + <Conv2Dgrad>", 4.0 * 663552,
-                           25600 + 10368 + 10368 + 12800 + 28224),
-    "arl_conv1_backward": ("tc_kernel<Conv1Wgrad> (bulk-copied d_a1 grid)", 2.0 * 1638400, 28224 + 28224),
-}
+# Work per unit (DESIGN.md kernel table).  Two byte counts per entry:
+#   "bytes"      ALGORITHMIC, layout-independent: every distinct tensor the entry touches counted
+#                once at its natural size (u8 frames / stack, float32 activations and gradients as
+#                the reference holds them, no padding, no second read) -- what a fused
+#                implementation of the entry cannot avoid.  roofline.frac uses this.
+#   "impl_bytes" what the kernels behind the entry move as built (a tensor read by two kernels
+#                counts twice, padded grids count their padding) -- the ncu DRAM traffic tracks it.
+def entry_work(A):
+    stack, a1, a2, h = 28224, 25600, 10368, 1024
+    heads_out = 4 * (2 * A + 1)
+    dhead = 4 * (A + 1)
+    return {
+        # entry: (kernels, flop per unit (one exact pass), algorithmic bytes, bytes as built)
+        "arl_preprocess_push": ("preprocess_kernel", 0.0, 80640 + 7056, 80640 + 7056),
+        "arl_conv1_forward": ("tc_kernel<Conv1Fwd> (kind::i8, bulk-copied ring)", 2.0 * 1638400,
+                              stack + a1, stack + a1),
+        "arl_conv2_forward": ("tc_kernel<Conv2Fwd> (bulk-copied a1s, split-bf16 a2 blocks out)",
+                              2.0 * 663552, a1 + a2, a1 + a2),
+        "arl_fc_forward": ("tc_kernel<FcFwdCluster> (bulk-copied split-bf16 operands)", 2.0 * 663552,
+                           a2 + h, a2 + h),
+        "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * (A + 1), h + heads_out, h + heads_out),
+        "arl_sample_actions": ("sample_actions_kernel", 0.0, 4 * A + 4, 4 * A + 4),
+        "arl_returns_lossgrad": ("returns_lossgrad_kernel", 0.0, 4 * (A + 1) + 9 + 4 + 4 * (A + 1),
+                                 4 * (A + 1) + 9 + 4 + 4 * (A + 1)),
+        # d_h is written twice (block + transposed copy for the weight gradient)
+        "arl_heads_backward": ("heads_bwd_kernel", 4.0 * 256 * (A + 1), h + dhead + h, h + dhead + 2 * h),
+        # algorithmic: d_h + a2 (operand and relu mask) in, d_a2 out.  As built: dgrad reads d_h + the
+        # hi half of a2 (mask) and writes d_a2; wgrad reads a2 + d_h again
+        "arl_fc_backward": ("tc_kernel<BulkGemm fc dgrad> + <fc wgrad>", 4.0 * 663552,
+                            h + a2 + a2, h + a2 // 2 + a2 + a2 + h),
+        # algorithmic: a1 + d_a2 in, d_a1 out (61 568).  As built: wgrad reads a1 + d_a2,
+        # dgrad reads d_a2 again + the hi half of a1 and writes d_a1 on the padded 21x21 grid
+        "arl_conv2_backward": ("tc_kernel<Conv2Wgrad> + <Conv2Dgrad>", 4.0 * 663552,
+                               a1 + a2 + a1, a1 + a2 + a2 + a1 // 2 + 28224),
+        "arl_conv1_backward": ("tc_kernel<Conv1Wgrad> (bulk-copied d_a1 grid)", 2.0 * 1638400,
+                               stack + a1, stack + 28224),
+        # per PARAMETER (unit = one parameter): grad, rms, param read; rms, param written
+        "arl_clip_rmsprop": ("sumsq_kernel + rmsprop_kernel", 6.0, 20, 24),
+    }
 
 
 def load_traffic():
     """DRAM bytes per launch of each entry's kernels from the committed ncu capture
-    (profiles/r01_traffic.json, written by tools/ncu_traffic.py) -- null when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py) -- null when absent."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(path):
         return json.load(open(path))
     return {}
@@ -278,7 +300,11 @@ def main():
     # ---- arm 1: inputs resident in HBM ----------------------------------------------------
     agent, env = make_agent(host=False)
     net = agent.network
-    # find the dominant entry with one event-timed cycle (untimed region)
+    work = entry_work(A)
+    n_params = int(net.params.numel())
+    # (a) per-entry pass, untimed region: a CUDA-event pair around EVERY C-ABI entry of the cycle
+    # (the composed arl_forward / arl_backward are issued as their per-layer entries: the same
+    # kernels in the same order) for PROFILE_CYCLES cycles -> roofline.entries
     net.timed, net.events = {"*"}, {}
     k1_events = []
 
@@ -291,16 +317,67 @@ def main():
         cycle(agent, env)
     torch.cuda.synchronize()
     net.events, k1_events[:] = {}, []
-    cycle(agent, env)
+    PROFILE_CYCLES = 5
+    for _ in range(PROFILE_CYCLES):
+        cycle(agent, env)
     torch.cuda.synchronize()
-    per_entry = {n: sum(a.elapsed_time(b) for a, b in ev) for n, ev in net.events.items()}
-    per_entry["arl_preprocess_push"] = sum(a.elapsed_time(b) for a, b in k1_events)
-    dominant = max(per_entry, key=per_entry.get)
+    launch_ms = {n: [a.elapsed_time(b) for a, b in ev] for n, ev in net.events.items()}
+    launch_ms["arl_preprocess_push"] = [a.elapsed_time(b) for a, b in k1_events]
+    per_entry = {n: sum(v) / PROFILE_CYCLES for n, v in launch_ms.items()}
+    traffic_all = load_traffic()
+
+    def units_of(entry):
+        if entry == "arl_clip_rmsprop":
+            return n_params
+        return B * T if entry.endswith("_backward") or entry == "arl_returns_lossgrad" else B
+
+    def roof(entry, avg_ms):
+        kname, flop_per, bytes_per, impl_per = work[entry]
+        units = units_of(entry)
+        t_hbm = bytes_per * units / (peaks["hbm"] * 1e9)
+        t_tensor = flop_per * units / (peaks["tensor"] * 1e12)
+        gbs = bytes_per * units / (avg_ms * 1e-3) / 1e9
+        tfs = flop_per * units / (avg_ms * 1e-3) / 1e12
+        # the bound is whichever roof gives the LONGER ideal time for the entry's algorithmic work
+        hbm = t_hbm >= t_tensor
+        return {"kernel": kname, "bound": "hbm" if hbm else "tensor",
+                "achieved": gbs if hbm else tfs, "peak": peaks["hbm"] if hbm else peaks["tensor"],
+                "unit": "GB/s" if hbm else "TFLOP/s",
+                "frac": (gbs / peaks["hbm"]) if hbm else (tfs / peaks["tensor"]),
+                "frac_impl_bytes": impl_per * units / (avg_ms * 1e-3) / 1e9 / peaks["hbm"],
+                "avg_launch_ms": avg_ms, "units_per_launch": units,
+                "algorithmic_bytes_per_unit": bytes_per, "impl_bytes_per_unit": impl_per,
+                "algorithmic_flop_per_unit": flop_per, "hbm_gbs": gbs, "tensor_tflops": tfs,
+                "traffic": (traffic_all.get(entry) or {}).get("dram_bytes_per_launch")}
+
+    entries = {}
+    for n, v in sorted(launch_ms.items(), key=lambda x: -per_entry[x[0]]):
+        if n in work and v:
+            e = roof(n, sum(v) / len(v))
+            e["launches_per_step"] = len(v) // PROFILE_CYCLES
+            e["ms_per_step"] = per_entry[n]
+            entries[n] = e
+    # fused floors of the chains: only what enters / must be kept leaves a count
+    fwd = ["arl_conv1_forward", "arl_conv2_forward", "arl_fc_forward", "arl_heads_forward"]
+    bwd = ["arl_heads_backward", "arl_fc_backward", "arl_conv2_backward", "arl_conv1_backward"]
+    fwd_bytes = 28224 + 25600 + 10368 + 1024 + 4 * (2 * A + 1)      # stack in; a1, a2, h, heads kept
+    bwd_bytes = 1024 + 4 * (A + 1) + 10368 + 25600 + 28224          # h, d heads, a2, a1, stack in
+    chains = {}
+    if all(k in per_entry for k in fwd + bwd):
+        f_ms, b_ms = sum(per_entry[k] for k in fwd), sum(per_entry[k] for k in bwd)
+        k1_ms, k5_ms = per_entry["arl_preprocess_push"], per_entry.get("arl_clip_rmsprop", 0.0)
+        chains["forward_chain"] = {"ms_per_step": f_ms, "bytes_per_sample": fwd_bytes,
+                                   "frac": fwd_bytes * B * (T + 1) / (f_ms * 1e-3) / 1e9 / peaks["hbm"]}
+        chains["backward_chain"] = {"ms_per_step": b_ms, "bytes_per_sample": bwd_bytes,
+                                    "frac": bwd_bytes * B * T / (b_ms * 1e-3) / 1e9 / peaks["hbm"]}
+        cyc_bytes = 87696 * B * T + fwd_bytes * B * (T + 1) + bwd_bytes * B * T + 20 * n_params
+        chains["cycle"] = {"bytes_per_step": cyc_bytes, "sum_of_entries_ms": sum(per_entry.values())}
+    dominant = max(entries, key=lambda k: entries[k]["ms_per_step"])
     if args.profile_all and rank == 0:
         print("per-entry ms per step:", json.dumps({k: round(v, 4) for k, v in
                                                     sorted(per_entry.items(), key=lambda x: -x[1])}),
               file=sys.stderr)
-    # timed region: events only around the dominant entry
+    # (b) timed region: events only around the dominant entry
     net.timed, net.events, k1_events[:] = {dominant}, {}, []
     if dominant != "arl_preprocess_push":
         agent.history.timer = None
@@ -312,33 +389,30 @@ def main():
     dom_ms = [a.elapsed_time(b) for a, b in ev]
     value = world * B * T * K / (ms_total * 1e-3)
     net.timed, agent.history.timer = None, None
+    if "cycle" in chains:
+        chains["cycle"]["ms_per_step"] = ms_total / K
+        chains["cycle"]["frac"] = chains["cycle"]["bytes_per_step"] / (ms_total / K * 1e-3) / 1e9 / peaks["hbm"]
 
-    kname, flop_per, bytes_per = ENTRY_WORK[dominant]
-    samples_per_launch = B * T if dominant.endswith("_backward") else B
-    avg_ms = sum(dom_ms) / len(dom_ms) if dom_ms else None
-    # the bound is whichever roof gives the LONGER ideal time for the entry's algorithmic work
-    t_hbm = bytes_per * samples_per_launch / (peaks["hbm"] * 1e9)
-    t_tensor = flop_per * samples_per_launch / (peaks["tensor"] * 1e12)
-    gbs = bytes_per * samples_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else None
-    tfs = flop_per * samples_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms else None
-    if t_hbm >= t_tensor:
-        bound, unit, peak, achieved = "hbm", "GB/s", peaks["hbm"], gbs
-    else:
-        bound, unit, peak, achieved = "tensor", "TFLOP/s", peaks["tensor"], tfs
-    traffic = (load_traffic().get(dominant) or {}).get("dram_bytes_per_launch")
-    roofline = {"kernel": kname, "entry": dominant, "bound": bound, "achieved": achieved,
-                "peak": peak, "unit": unit, "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(dom_ms),
-                "units_per_launch": samples_per_launch,
-                "algorithmic_bytes_per_unit": bytes_per, "algorithmic_flop_per_unit": flop_per,
-                "hbm_gbs": gbs, "tensor_tflops": tfs,
-                "share_of_step": (per_entry[dominant] / sum(per_entry.values())),
-                "peak_source": peaks["source"],
-                "entries_ms_per_step": {k: round(v, 4) for k, v in
-                                        sorted(per_entry.items(), key=lambda x: -x[1])},
-                "note": "entry = one C-ABI call, timed live with CUDA events on the launching "
-                        "stream; flop = one exact pass (the kernels run 2-3 bf16 passes per "
-                        "product for fp32-grade accuracy)"}
+    roofline = roof(dominant, sum(dom_ms) / len(dom_ms)) if dom_ms else dict(entries[dominant])
+    roofline.update({"entry": dominant, "launches_timed": len(dom_ms),
+                     "share_of_step": per_entry[dominant] / sum(per_entry.values()),
+                     "peak_source": peaks["source"], "entries": entries, "chains": chains,
+                     "entries_ms_per_step": {k: round(v, 4) for k, v in
+                                             sorted(per_entry.items(), key=lambda x: -x[1])},
+                     "note": "top level = the dominant entry timed live with CUDA events inside the "
+                             "timed region; entries = every C-ABI entry of the cycle timed the same "
+                             "way over %d cycles just before it.  frac = ALGORITHMIC bytes (each "
+                             "tensor once, natural size) / time / peak; frac_impl_bytes = the bytes "
+                             "the kernels move as built; traffic = ncu DRAM bytes per launch "
+                             "(profiles/r02_traffic.json); flop = one exact pass" % PROFILE_CYCLES})
+    params_checksum = float(net.params.double().sum().item())
+    replica_spread = 0.0
+    if world > 1:
+        # every rank holds a replica: max - min over ranks of every parameter must be exactly 0
+        lo, hi = net.params.clone(), net.params.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replica_spread = float((hi - lo).abs().max().item())
     del agent, env, net
     torch.cuda.empty_cache()
 
@@ -365,6 +439,7 @@ def main():
                           "(relative error ~1e-5 vs the fp64 oracle: activations between layers are kept as bf16 hi+lo pairs)",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline,
+            "parity": {"replica_max_minus_min": replica_spread, "params_checksum": params_checksum},
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base

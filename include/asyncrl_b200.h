@@ -118,11 +118,17 @@ ARL_API int arl_preprocess_push_pil(const uint8_t* frames, uint8_t* ring, int nu
                             int slot, int replicate, void* stream);
 
 /* Host -> device upload of exactly the frame rows K1 reads (environment.py:53 -> cv2.resize
- * 210x160 -> 84x84 never touches source rows == 2 mod 5): two strided async copies of
- * num_envs*42 x 960 B each = 80 640 of the 100 800 B of a frame.  host_frames should be pinned;
- * dev_frames keeps the full [num_envs,210,160,3] layout (the skipped rows are left as they are). */
+ * 210x160 -> 84x84 never touches source rows == 2 mod 5): 80 640 of the 100 800 B of a frame, as
+ * ONE strided async copy of 1920-B runs (4 rows) at a 2400-B pitch over the whole batch plus the
+ * two 960-B ends.  host_frames should be pinned; dev_frames keeps the full [num_envs,210,160,3]
+ * layout (the skipped rows are left as they are: NOT valid input for arl_preprocess_push_pil). */
 ARL_API int arl_upload_frames(const uint8_t* host_frames, uint8_t* dev_frames, int num_envs,
                       void* stream);
+
+/* The whole frames (one plain async copy of num_envs * 100 800 B): the upload to use with the
+ * scipy/PIL resize branch (arl_preprocess_push_pil reads every source row). */
+ARL_API int arl_upload_frames_full(const uint8_t* host_frames, uint8_t* dev_frames, int num_envs,
+                           void* stream);
 
 /* History.get()/copy() (src/history.py:20-27): materialise the NHWC stack
  * f32 [num_envs,84,84,4] (or u8 when out_is_u8) whose oldest plane is `first_slot`. */
@@ -242,7 +248,30 @@ ARL_API int arl_backward(const float* params, const float* prepared, int action_
                  const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                  const float* a1, const float* a2,
                  const float* h, const float* dlogits, const float* dvalue, float* d_h,
-                 float* d_a2, float* d_a1, float* grads, void* workspace, void* stream);
+                 float* d_a2, float* d_a1, float* grads, void* workspace, int allreduce,
+                 void* stream);
+
+/* ---- the exchange step: gradient all-reduce across the GPUs of a box ---------------------
+ * Replaces the reference's parameter-server push (main.py:60-62 places the variables on the ps,
+ * agent.py:321 applies every worker's gradients there): one process per GPU, replicas of the
+ * parameters, and ONE all-reduce(sum) of the flat gradient buffer per t_max cycle (NCCL over
+ * NVLink, bound at run time from libnccl.so.2).  Rank 0 makes an id (arl_comm_unique_id,
+ * ARL_COMM_ID_BYTES bytes), the host distributes it by any means, every rank calls
+ * arl_comm_init on its own device; one communicator per process.
+ *   arl_allreduce_grads   in-place sum over ranks of grads[0, count) on `stream`.
+ *   arl_allreduce_begin / arl_allreduce_end   the same for a slice, on the library's side stream,
+ *     ordered after what is already queued on `stream`; `end` makes `stream` wait for all slices
+ *     begun.  arl_backward(allreduce = 1) uses them: the l4_w..q_b slice (98 % of the bytes) is
+ *     final after the fc256 weight gradient and travels while the conv backward kernels run. */
+#define ARL_COMM_ID_BYTES 128
+ARL_API int arl_comm_unique_id(uint8_t* id_out);
+ARL_API int arl_comm_init(const uint8_t* id_bytes, int rank, int nranks);
+ARL_API int arl_comm_size(void);                 /* ranks of the communicator, 0 = none */
+ARL_API int arl_comm_nccl_version(void);         /* e.g. 22809; 0 = NCCL not loadable */
+ARL_API int arl_comm_destroy(void);
+ARL_API int arl_allreduce_grads(float* grads, int64_t count, void* stream);
+ARL_API int arl_allreduce_begin(float* grads, int64_t offset, int64_t count, void* stream);
+ARL_API int arl_allreduce_end(void* stream);
 
 /* ---- K5: per-tensor clip + shared RMSProp -------------------------------------------
  * agent.py:316-319 clip_by_norm(g, clip) per tensor, then TF ApplyRMSProp as configured at

@@ -246,7 +246,7 @@ def test_backward_single_sample_and_zero_samples(pkg, cuda):
     P = pkg._cabi.ptr
     assert lib.arl_backward(P(net.params), P(net.fc_w), A, P(hist.ring), 0, hist.ring_slots, 0, 1, P(net.l1),
                             P(net.l2), P(net.l4), P(net.d_logits), P(net.d_value), P(net.d_l4),
-                            P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), st) == 0
+                            P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), 0, st) == 0
     torch.cuda.synchronize()
     assert float(net.grads.abs().max()) == 0.0
 

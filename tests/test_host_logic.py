@@ -70,13 +70,64 @@ def test_gym_vector_adapter_host_logic(pkg):
     assert np.array_equal(f0[0].numpy(), envs[0].frames[0])
     f2, r2, t2, _ = ad.step(torch.tensor([0, 0, 0], dtype=torch.int32))
     assert t2.tolist() == [False, False, True]                    # env 2: episode_len 2, its only life
-    assert envs[2].resets == 2 and ad.ale.lives().tolist() == [2, 2, 1]   # ... so it was reset in place
+    # the terminal step hands out the TERMINAL frame (the reference pushes it into the history,
+    # agent.py:62-64, before it restarts the env); the emulator is not reset yet
+    assert envs[2].resets == 1 and ad.ale.lives().tolist() == [2, 2, 0]
     assert np.array_equal(f2[2].numpy(), envs[2].frames[-1])
+    # auto_reset: a finished emulator is reset in place on its NEXT step (reward 0, not terminal)
+    f2b, r2b, t2b, _ = ad.step(torch.tensor([1, 1, 1], dtype=torch.int32))
+    assert envs[2].resets == 2 and ad.ale.lives().tolist()[2] == 1
+    assert r2b.tolist() == [1.0, 1.0, 0.0] and t2b.tolist() == [True, True, False]   # envs 0, 1: third step of a 3-step life
+    assert np.array_equal(f2b[2].numpy(), envs[2].frames[-1])
     # masked reset: only env 0 restarts, the others keep their last frame
     f3 = ad.reset(torch.tensor([True, False, False]))
     assert envs[0].resets == 2 and envs[1].resets == 1
-    assert np.array_equal(f3[1].numpy(), f2[1].numpy()) and np.array_equal(f3[0].numpy(), envs[0].frames[-1])
+    assert np.array_equal(f3[1].numpy(), f2b[1].numpy()) and np.array_equal(f3[0].numpy(), envs[0].frames[-1])
     assert len(ad.action_space.sample()) == 3
+
+
+def test_gym_vector_adapter_per_env_restart(pkg):
+    """agent.py:66-67 restarts the env that died, environment.py:28-40: reset only when the game
+    is over (lives == 0), one no-op step, then that env's OWN number of random-start no-op steps.
+    The other envs are not touched."""
+    import numpy as np
+    import torch
+    from util import StubGymEnv
+    envs = [StubGymEnv(10 + b, episode_len=3, lives=2) for b in range(4)]
+    ad = pkg.environment.GymVectorAdapter(envs, device='cpu', auto_reset=False)
+    ad.restart([True] * 4, [0, 1, 2, 3])                          # first call: every env resets
+    assert [e.resets for e in envs] == [1, 1, 1, 1]
+    assert [len(e.frames) for e in envs] == [2, 3, 4, 5]          # reset + (1 + k_b) no-op steps
+    n_before = [len(e.frames) for e in envs]
+    f, r, t = ad.restart([False, True, False, True], [9, 2, 9, 0])
+    assert [len(e.frames) - n for e, n in zip(envs, n_before)] == [0, 3, 0, 1]
+    assert np.array_equal(f[1].numpy(), envs[1].frames[-1]) and np.array_equal(f[0].numpy(), envs[0].frames[-1])
+    # env 3 (5 steps so far with episode_len 3) lost a life on the way but its game is not over:
+    # no reset for it (environment.py:29-30)
+    assert envs[3].resets == 1 and envs[3]._lives == 1
+    # a game-over emulator without auto_reset idles on its last frame until it is restarted
+    while envs[3]._lives > 0:
+        f, r, t, _ = ad.step(torch.zeros(4, dtype=torch.int32))
+    n3 = len(envs[3].frames)
+    f2, r2, t2, _ = ad.step(torch.zeros(4, dtype=torch.int32))
+    assert len(envs[3].frames) == n3 and t2.tolist()[3] is True and r2.tolist()[3] == 0.0
+    ad.restart([False, False, False, True], [0, 0, 0, 1])
+    assert envs[3].resets == 2 and len(envs[3].frames) == n3 + 3   # reset frame + 2 no-op steps
+
+
+def test_adapter_without_ale_resets_on_terminal(pkg):
+    """an emulator without .ale has no lives -- every terminal is a game over."""
+    import torch
+    from util import StubGymEnv
+    e = StubGymEnv(3, episode_len=2, lives=5)
+    del e.ale
+    ad = pkg.environment.GymVectorAdapter([e], device='cpu')
+    ad.reset()
+    ad.step(torch.zeros(1, dtype=torch.int32))
+    _, _, t, _ = ad.step(torch.zeros(1, dtype=torch.int32))
+    assert t.tolist() == [True] and e.resets == 1
+    _, r, t, _ = ad.step(torch.zeros(1, dtype=torch.int32))      # reset in place on the next step
+    assert e.resets == 2 and t.tolist() == [False]
 
 
 def test_split_block_encode_decode_round_trip(pkg):

@@ -1,8 +1,8 @@
-"""profiles/r01_traffic.json from an `ncu --set full` capture: per C-ABI entry, DRAM bytes
+"""profiles/r02_traffic.json from an `ncu --set full` capture: per C-ABI entry, DRAM bytes
 (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of each kernel behind the entry.
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv
-    python tools/ncu_traffic.py raw.csv profiles/r01_traffic.json
+    python tools/ncu_traffic.py raw.csv profiles/r02_traffic.json
 """
 import csv
 import json
