@@ -48,6 +48,10 @@ SIGNATURES = {
     "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_backward": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "arl_sample_actions_dev": [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_u64, c_vp],
+    "arl_step_advance": [c_vp, c_i64, c_vp],
+    "arl_clip_rmsprop_sched": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, ctypes.c_double, c_i64, c_f32, c_f32,
+                               c_f32, c_vp, c_vp, c_vp],
     "arl_comm_unique_id": [c_vp],
     "arl_comm_init": [c_vp, c_int, c_int],
     "arl_comm_destroy": [],

@@ -45,6 +45,8 @@ class AgentConfig(object):
     clip_norm = 40.0                     # agent.py:319
     resize = 'cv2'                       # environment.py:5-12 executed branch
     loss_mode = 'a3c'                    # 'a3c' (network.py heads/loss) | 'async_q' (agent.py as run)
+    cuda_graphs = True                   # capture predict / observe(+update) as CUDA graphs (a3c mode)
+    max_graphs = 1024                    # cap of the graph cache; beyond it the loop runs eagerly
     collective = 'library'               # gradient all-reduce: 'library' (arl_comm_*, NCCL in the .so) | 'torch'
 
 

@@ -101,11 +101,14 @@ __device__ __forceinline__ void philox_two(uint32_t c0, uint32_t c1, uint32_t c2
   x0 = c0; x1 = c1;
 }
 
+// step_dev (optional): the step counter lives in device memory (a captured CUDA graph cannot carry
+// a host value that changes on every launch); the Philox step is then *step_dev + step
 __global__ void sample_actions_kernel(const float* __restrict__ probs, int32_t* __restrict__ actions,
                                       int num_envs, int A, uint64_t env_id_base, uint64_t step,
-                                      uint64_t seed) {
+                                      uint64_t seed, const int64_t* __restrict__ step_dev) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= num_envs) return;
+  if (step_dev != nullptr) step += (uint64_t)*step_dev;
   const uint32_t env = (uint32_t)(env_id_base + (uint64_t)b);
   const uint32_t x = philox_first(env, (uint32_t)step, (uint32_t)(step >> 32), 0u, (uint32_t)seed,
                                   (uint32_t)(seed >> 32));
@@ -425,8 +428,33 @@ extern "C" int arl_sample_actions(const float* probs, int32_t* actions, int num_
   ARL_REQUIRE(num_envs >= 0 && env_id_base >= 0 && step >= 0, "arl_sample_actions: negative argument");
   if (num_envs == 0) return ARL_OK;
   sample_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      probs, actions, num_envs, action_size, (uint64_t)env_id_base, (uint64_t)step, seed);
+      probs, actions, num_envs, action_size, (uint64_t)env_id_base, (uint64_t)step, seed, nullptr);
   ARL_LAUNCH_CHECK("sample_actions_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_sample_actions_dev(const float* probs, int32_t* actions, int num_envs,
+                                      int action_size, int64_t env_id_base, const int64_t* step_dev,
+                                      uint64_t seed, void* stream) {
+  ARL_REQUIRE(probs && actions && step_dev, "arl_sample_actions_dev: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_sample_actions_dev: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(num_envs >= 0 && env_id_base >= 0, "arl_sample_actions_dev: negative argument");
+  if (num_envs == 0) return ARL_OK;
+  sample_actions_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      probs, actions, num_envs, action_size, (uint64_t)env_id_base, 0ull, seed, step_dev);
+  ARL_LAUNCH_CHECK("sample_actions_kernel");
+  return ARL_OK;
+}
+
+namespace arl {
+__global__ void step_advance_kernel(int64_t* counter, int64_t inc) { *counter += inc; }
+}  // namespace arl
+
+extern "C" int arl_step_advance(int64_t* counter, int64_t inc, void* stream) {
+  ARL_REQUIRE(counter, "arl_step_advance: null pointer");
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  ARL_LAUNCH_CHECK("step_advance_kernel");
   return ARL_OK;
 }
 

@@ -50,8 +50,13 @@ sumsq_kernel(const float* __restrict__ grads, float* __restrict__ partial, Updat
 __global__ void __launch_bounds__(kUpThreads)
 rmsprop_kernel(float* __restrict__ params, float* __restrict__ rms, const float* __restrict__ grads,
                const float* __restrict__ partial, float* __restrict__ norms_out, UpdatePlan plan,
-               float lr, float decay, float eps, float clip) {
+               float lr, float decay, float eps, float clip, const int64_t* __restrict__ step_dev,
+               long long step_offset, double base_lr, long long max_step) {
   __shared__ float s_scale;
+  // agent.py:393-395 on the device (the step counter lives in device memory under a CUDA graph):
+  // the same double expression the host evaluates, rounded to float once
+  if (step_dev != nullptr)
+    lr = (float)((double)(max_step - (*step_dev + step_offset) + 1) / (double)max_step * base_lr);
   const int t = find_tensor(plan, blockIdx.x);
   if (threadIdx.x == 0) {
     float ss = 0.f;
@@ -78,9 +83,10 @@ rmsprop_kernel(float* __restrict__ params, float* __restrict__ rms, const float*
 
 using namespace arl;
 
-extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size,
-                                float lr, float decay, float eps, float clip_norm, float* norms_out,
-                                void* workspace, void* stream) {
+static int clip_rmsprop(float* params, float* rms, const float* grads, int action_size, float lr,
+                        float decay, float eps, float clip_norm, float* norms_out, void* workspace,
+                        const int64_t* step_dev, int64_t step_offset, double base_lr, int64_t max_step,
+                        void* stream) {
   ARL_REQUIRE(params && rms && grads && workspace, "arl_clip_rmsprop: null pointer");
   ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
               "arl_clip_rmsprop: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
@@ -100,7 +106,24 @@ extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, i
   sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
   ARL_LAUNCH_CHECK("sumsq_kernel");
   rmsprop_kernel<<<chunks, kUpThreads, 0, st>>>(params, rms, grads, partial, norms_out, plan, lr,
-                                               decay, eps, clip_norm);
+                                               decay, eps, clip_norm, step_dev, (long long)step_offset,
+                                               base_lr, (long long)max_step);
   ARL_LAUNCH_CHECK("rmsprop_kernel");
   return ARL_OK;
+}
+
+extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size,
+                                float lr, float decay, float eps, float clip_norm, float* norms_out,
+                                void* workspace, void* stream) {
+  return clip_rmsprop(params, rms, grads, action_size, lr, decay, eps, clip_norm, norms_out, workspace,
+                      nullptr, 0, 0.0, 1, stream);
+}
+
+extern "C" int arl_clip_rmsprop_sched(float* params, float* rms, const float* grads, int action_size,
+                                      const int64_t* step_dev, int64_t step_offset, double base_lr,
+                                      int64_t max_step, float decay, float eps, float clip_norm,
+                                      float* norms_out, void* workspace, void* stream) {
+  ARL_REQUIRE(step_dev && max_step > 0, "arl_clip_rmsprop_sched: null step counter or max_step <= 0");
+  return clip_rmsprop(params, rms, grads, action_size, 0.f, decay, eps, clip_norm, norms_out, workspace,
+                      step_dev, step_offset, base_lr, max_step, stream);
 }

@@ -73,6 +73,20 @@ class Agent(BaseModel):
         if self.loss_mode == 'async_q':
             self.network.make_target()
             self._last_target_sync = 0
+        # CUDA graphs of the loop: the device work of ``predict`` and of ``observe``
+        # (+ the learner step at the end of a rollout) is captured once per distinct set of launch
+        # arguments -- rollout slot, ring position, frame / reward buffers -- and replayed from then
+        # on.  The two host values that change on every step, the Philox step and the step the
+        # learning rate is annealed on, are read from ``step_dev`` (device memory) instead.
+        self.cuda_graphs = bool(getattr(config, 'cuda_graphs', True)) and self.loss_mode == 'a3c'
+        self.max_graphs = int(getattr(config, 'max_graphs', 1024))
+        self.graph_warmup_updates = 2                            # eager cycles first (lazy init, autotune)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._step_dev_host = None                               # value step_dev holds, if known
+        self._graphs = {}
+        self._graph_pool = None
+        self.graph_replays = 0
+        self.graph_kernels_replayed = 0                          # library kernels launched by replays
 
     # -- agent.py:33-50 ---------------------------------------------------------------------
     def before_train(self, is_chief=True):
@@ -212,15 +226,58 @@ class Agent(BaseModel):
                 self.network.update_target()
         return True
 
+    # -- CUDA-graph plumbing ----------------------------------------------------------------
+    def _graphs_on(self):
+        return (self.cuda_graphs and self.network.timed is None
+                and self.update_count >= self.graph_warmup_updates
+                and (self.world_size == 1 or self.collective == 'library'))
+
+    def _sync_step_dev(self):
+        """``step_dev`` mirrors the host's ``self.step``; callers that move ``self.step`` by hand
+        (tests drive the loop manually) are followed with one fill."""
+        if self._step_dev_host != self.step:
+            self.step_dev.fill_(int(self.step))
+            self._step_dev_host = self.step
+
+    def _run(self, key, launches):
+        """Run ``launches`` (device work only, no host state) -- replaying its captured graph when
+        one exists for ``key``, capturing it on first sight."""
+        if not self._graphs_on():
+            launches()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.max_graphs:
+                launches()
+                return
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _cabi.launch_count()
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                launches()
+            g = self._graphs[key] = (graph, _cabi.launch_count() - n0)   # + its kernel-node count
+        g[0].replay()
+        self.graph_replays += 1
+        self.graph_kernels_replayed += g[1]
+
     # -- agent.py:141-151 -------------------------------------------------------------------
     def predict(self, s_t=None, test_ep=None):
         """Forward of the current stack (already in the ring; ``s_t`` is accepted for signature
         compatibility and ignored) and one sampled action per env."""
-        self.network.forward(self.history, self.t)
+        net, t = self.network, self.t
         if self.loss_mode == 'async_q':                          # agent.py:142-149
+            net.forward(self.history, t)
             ep = self.ep if test_ep is None else test_ep
-            return self.network.egreedy(self.t, self.step, self.seed, ep, self.env_id_base)
-        return self.network.sample(self.t, self.step, self.seed, self.env_id_base)
+            return net.egreedy(t, self.step, self.seed, ep, self.env_id_base)
+        self._sync_step_dev()
+        refresh = net._fc_w_stale()
+
+        def launches():
+            net.forward(self.history, t, refresh=refresh)
+            net.sample_dev(t, self.step_dev, self.seed, self.env_id_base)
+        self._run(('predict', t, self.history.head, refresh), launches)
+        return net.sampled_action[net._rows(t)]
 
     # -- agent.py:351-391 -------------------------------------------------------------------
     def play(self, sv=None, is_chief=True, n_step=10000, n_episode=100, test_ep=None, render=False):
@@ -263,24 +320,71 @@ class Agent(BaseModel):
 
     # -- agent.py:153-167 -------------------------------------------------------------------
     def observe(self, screen, reward, action, terminal, is_chief=False):
-        self.history.add(screen)                                 # agent.py:156 (K1 when raw frames)
-        if reward.dtype == torch.float32 and terminal.dtype in (torch.bool, torch.uint8) \
-                and reward.is_contiguous() and terminal.is_contiguous():
-            # one kernel for both appends; the clip happens in K4 (agent.py:154)
-            _cabi.call("arl_observe_store", _cabi.ptr(reward), _cabi.ptr(terminal),
-                       _cabi.ptr(self.batch_reward[self.t]), _cabi.ptr(self.batch_terminal[self.t]),
-                       self.num_envs, _cabi.stream_ptr())
+        fast = (reward.dtype == torch.float32 and terminal.dtype in (torch.bool, torch.uint8)
+                and reward.is_contiguous() and terminal.is_contiguous())
+        t, hist = self.t, self.history
+        will_update = t + 1 == self.t_max                        # agent.py:162-163
+        if self.loss_mode == 'async_q' or not fast:
+            hist.add(screen)                                     # agent.py:156 (K1 when raw frames)
+            if fast:
+                _cabi.call("arl_observe_store", _cabi.ptr(reward), _cabi.ptr(terminal),
+                           _cabi.ptr(self.batch_reward[t]), _cabi.ptr(self.batch_terminal[t]),
+                           self.num_envs, _cabi.stream_ptr())
+            else:
+                self.batch_reward[t].copy_(reward)
+                self.batch_terminal[t].copy_(terminal)
+            self.t += 1
+            if will_update:
+                self.batch_update(is_chief)
         else:
-            self.batch_reward[self.t].copy_(reward)
-            self.batch_terminal[self.t].copy_(terminal)
-        self.t += 1
-        if self.t == self.t_max:                                 # agent.py:162-163
-            self.batch_update(is_chief)
+            self._sync_step_dev()
+            new_head = (hist.head + 1) % hist.ring_slots
+            hist.head = new_head                                 # host state first: the launches read it
+            refresh = self.network._fc_w_stale() if will_update else False
+
+            k1_eager = hist.timer is not None                    # bench.py: event pair around K1
+            if k1_eager:
+                hist.push_into(screen, new_head)
+
+            def launches():
+                if not k1_eager:
+                    hist.push_into(screen, new_head)             # agent.py:156: K1, fused screen + add
+                # one kernel for both appends; the clip happens in K4 (agent.py:154)
+                _cabi.call("arl_observe_store", _cabi.ptr(reward), _cabi.ptr(terminal),
+                           _cabi.ptr(self.batch_reward[t]), _cabi.ptr(self.batch_terminal[t]),
+                           self.num_envs, _cabi.stream_ptr())
+                _cabi.call("arl_step_advance", _cabi.ptr(self.step_dev), 1, _cabi.stream_ptr())
+                if will_update:
+                    self._update_launches(refresh)
+            self._run(('observe', t, new_head, screen.data_ptr(), reward.data_ptr(),
+                       terminal.data_ptr(), tuple(screen.shape), will_update, refresh, k1_eager),
+                      launches)
+            self._step_dev_host = self.step + 1
+            self.t += 1
+            if will_update:
+                self.network._param_writes += 1                  # the update wrote the parameters
+                self.update_count += 1
+                self.t = 0
         self.T += self.global_envs                               # agent.py:165 counts every worker
         if self.loss_mode == 'async_q' and \
                 self.T - self._last_target_sync >= self.target_q_update_step:
             self.update_target_q_network()                       # agent.py:166-167
             self._last_target_sync = self.T
+
+    def _update_launches(self, refresh):
+        """Device work of ``batch_update`` in a3c mode with the learning rate taken from the device
+        step counter (already advanced past the last frame of the rollout: offset -t_max gives
+        the step of the rollout's first frame)."""
+        net = self.network
+        in_lib = self.world_size > 1 and self.collective == 'library'
+        v_boot = net.bootstrap_value(self.history, refresh=refresh)
+        scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
+        net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
+                              grad_scale=scale, allreduce=in_lib, refresh=False)
+        if self.world_size > 1 and not in_lib:
+            dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)
+        net.apply_gradients_sched(self.step_dev, -self.t_max, self.learning_rate, self.max_step,
+                                  count_write=False)
 
     # -- agent.py:169-207 -------------------------------------------------------------------
     def batch_update(self, is_chief=False):

@@ -35,6 +35,19 @@ def from_blocked(planes):
     return x.permute(*range(n), n, n + 2, n + 1, n + 3).reshape(lead + (SCREEN, SCREEN))
 
 
+def default_ring_slots(t_max):
+    """Slots of the ring: at least t_max + 4 (the T+1 overlapping stacks of a rollout need T+4
+    planes).  The head advances by t_max per cycle, so the slot pattern of a cycle repeats every
+    R / gcd(t_max, R) cycles; a slightly larger R with a short period (<= 3 cycles) keeps the
+    number of distinct CUDA graphs of the loop small (t_max 5: 10 slots, period 2, instead of 9
+    slots with period 9; t_max 20: 30 slots, period 3, instead of 24 with period 6)."""
+    import math
+    for r in range(t_max + 4, 2 * t_max + 9):
+        if r // math.gcd(t_max, r) <= 3:
+            return r
+    return t_max + 4
+
+
 class History(object):
     def __init__(self, config, num_envs=None, ring_slots=None, device=None):
         self.cnn_format = getattr(config, 'cnn_format', 'NHWC')
@@ -43,7 +56,7 @@ class History(object):
         assert (config.screen_height, config.screen_width) == (SCREEN, SCREEN)
         self.num_envs = int(num_envs if num_envs is not None else getattr(config, 'num_envs', 1))
         t_max = int(getattr(config, 't_max', 5))
-        self.ring_slots = int(ring_slots if ring_slots is not None else t_max + 4)
+        self.ring_slots = int(ring_slots if ring_slots is not None else default_ring_slots(t_max))
         if self.ring_slots < 4:
             raise ValueError("ring_slots must be >= 4")
         self.device = torch.device(device if device is not None else 'cuda')
@@ -62,22 +75,27 @@ class History(object):
         """history.py:13-15.  ``screen`` is either raw frames u8 [B,210,160,3] (fused
         Environment.screen + add: one kernel, K1) or ready 84x84 screens u8 [B,84,84]."""
         new_head = (self.head + 1) % self.ring_slots
+        self.push_into(screen, new_head, replicate)
+        self.head = (new_head + replicate - 1) % self.ring_slots
+
+    def push_into(self, screen, slot, replicate=1):
+        """The device work of ``add`` for an explicit ring slot; no host state changes (the form a
+        captured CUDA graph can hold)."""
         if tuple(screen.shape[1:]) == FRAME_SHAPE:
             if screen.dtype != torch.uint8:
                 raise TypeError("frames must be uint8")
             args = (self._push, _cabi.ptr(screen), _cabi.ptr(self.ring),
-                    self.num_envs, self.ring_slots, new_head, int(replicate), _cabi.stream_ptr())
+                    self.num_envs, self.ring_slots, slot, int(replicate), _cabi.stream_ptr())
             if self.timer is not None:
                 self.timer(*args)                    # bench.py: event pair around K1
             else:
                 _cabi.call(*args)
         elif tuple(screen.shape[1:]) == (SCREEN, SCREEN):
             for r in range(replicate):
-                self.ring[:, (new_head + r) % self.ring_slots].copy_(to_blocked(screen))
+                self.ring[:, (slot + r) % self.ring_slots].copy_(to_blocked(screen))
         else:
             raise ValueError("expected [B,210,160,3] frames or [B,84,84] screens, got %s"
                              % (tuple(screen.shape),))
-        self.head = (new_head + replicate - 1) % self.ring_slots
 
     def reset(self):
         """history.py:17-18."""

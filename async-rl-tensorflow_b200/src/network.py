@@ -196,10 +196,12 @@ class Network(object):
         self._fc_w_key = key
         return stale
 
-    def _forward_into(self, history, l1, l2, l4, logits, probs, value):
+    def _forward_into(self, history, l1, l2, l4, logits, probs, value, refresh=None):
+        """``refresh``: rebuild the prepared weight images first; None = decide here from the
+        parameter version (host state).  A captured region passes the decision in."""
         P, st = _cabi.ptr, _cabi.stream_ptr()
         B, A = self.num_envs, self.action_size
-        refresh = 1 if self._fc_w_stale() else 0
+        refresh = (1 if self._fc_w_stale() else 0) if refresh is None else int(bool(refresh))
         if self.timed is None:
             _cabi.call("arl_forward", P(self.params), P(self.fc_w), refresh, A, P(history.ring), B,
                        history.ring_slots, history.first_slot(0), 1, P(l1), P(l2), P(l4),
@@ -214,11 +216,11 @@ class Network(object):
         self._timed_call("arl_heads_forward", P(self.params), A, P(l4), P(logits), P(probs),
                          P(value), B, st)
 
-    def forward(self, history, t):
+    def forward(self, history, t, refresh=None):
         """Forward of the current stack into rollout slot ``t``; returns (logits, policy, value)."""
         r = self._rows(t)
         self._forward_into(history, self.l1[r], self.l2[r], self.l4[r], self.policy_logits[r],
-                           self.policy[r], self.value[r])
+                           self.policy[r], self.value[r], refresh)
         return self.policy_logits[r], self.policy[r], self.value[r]
 
     def a1(self):
@@ -251,11 +253,21 @@ class Network(object):
                          int(env_id_base), int(step), int(seed), _cabi.stream_ptr())
         return self.sampled_action[r]
 
-    def bootstrap_value(self, history):
+    def bootstrap_value(self, history, refresh=None):
         """V(s_T) under the same theta (Algorithm 3: R = V(s_t, theta'_v))."""
         b = self._b
-        self._forward_into(history, b['l1'], b['l2'], b['l4'], b['logits'], b['probs'], b['value'])
+        self._forward_into(history, b['l1'], b['l2'], b['l4'], b['logits'], b['probs'], b['value'],
+                           refresh)
         return b['value']
+
+    def sample_dev(self, t, step_dev, seed, env_id_base=0):
+        """``sample`` with the Philox step read from the int64 device counter ``step_dev`` (the
+        form a captured CUDA graph can replay)."""
+        r = self._rows(t)
+        _cabi.call("arl_sample_actions_dev", _cabi.ptr(self.policy[r]),
+                   _cabi.ptr(self.sampled_action[r]), self.num_envs, self.action_size,
+                   int(env_id_base), _cabi.ptr(step_dev), int(seed), _cabi.stream_ptr())
+        return self.sampled_action[r]
 
     def evaluate(self, history, step, seed, ep=None, env_id_base=0):
         """Forward of ``history``'s current stack into the scratch buffers (no rollout slot is
@@ -291,7 +303,7 @@ class Network(object):
 
     # -- backward ---------------------------------------------------------------------------
     def compute_gradients(self, history, rewards, terminals, v_boot, actions=None,
-                          grad_scale=1.0, allreduce=False):
+                          grad_scale=1.0, allreduce=False, refresh=None):
         """Returns + loss grads (K4) then the full backward (agent.py:317) over the T*B samples
         of the rollout.  ``history`` must have had exactly t_max pushes since s_0."""
         T, B, A = self.t_max, self.num_envs, self.action_size
@@ -304,7 +316,7 @@ class Network(object):
                          _cabi.ptr(self.d_value), _cabi.ptr(self.loss_sums), T, B, A, self.gamma,
                          self.beta, self.min_reward, self.max_reward, float(grad_scale), st)
         P = _cabi.ptr
-        if self._fc_w_stale():                                 # (a forward normally did this already)
+        if self._fc_w_stale() if refresh is None else refresh:   # (a forward normally did this already)
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
         if self.timed is None:
             _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
@@ -387,6 +399,16 @@ class Network(object):
                          self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
                          _cabi.stream_ptr())
         self._param_writes += 1                                # the kernel wrote params: fc_w is stale
+
+    def apply_gradients_sched(self, step_dev, step_offset, base_lr, max_step, count_write=True):
+        """``apply_gradients`` with the learning rate of agent.py:393-395 evaluated on the device
+        from the int64 step counter ``step_dev`` (+ ``step_offset``): replayable by a CUDA graph."""
+        _cabi.call("arl_clip_rmsprop_sched", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                   _cabi.ptr(self.grads), self.action_size, _cabi.ptr(step_dev), int(step_offset),
+                   float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
+                   _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
+        if count_write:
+            self._param_writes += 1
 
     # -- checkpoints (network.py:109-127), reference variable names + the rms slot ----------
     def save_model(self, saver=None, checkpoint_dir='checkpoints', step=None):

@@ -251,6 +251,23 @@ ARL_API int arl_backward(const float* params, const float* prepared, int action_
                  float* d_a2, float* d_a1, float* grads, void* workspace, int allreduce,
                  void* stream);
 
+/* ---- device-resident step counter (CUDA-graph capture of the loop) -------------
+ * A captured graph replays fixed kernel arguments, so the two host values that change on every
+ * launch -- the Philox step of the sampler and the step the learning rate is annealed on
+ * (agent.py:393-395) -- can also be read from an int64 counter in device memory:
+ *   arl_sample_actions_dev   like arl_sample_actions with step = *step_dev
+ *   arl_step_advance         *counter += inc (one thread)
+ *   arl_clip_rmsprop_sched   like arl_clip_rmsprop with
+ *                            lr = (max_step - (*step_dev + step_offset) + 1) / max_step * base_lr
+ *                            evaluated in double on the device and rounded to float once. */
+ARL_API int arl_sample_actions_dev(const float* probs, int32_t* actions, int num_envs, int action_size,
+                           int64_t env_id_base, const int64_t* step_dev, uint64_t seed, void* stream);
+ARL_API int arl_step_advance(int64_t* counter, int64_t inc, void* stream);
+ARL_API int arl_clip_rmsprop_sched(float* params, float* rms, const float* grads, int action_size,
+                           const int64_t* step_dev, int64_t step_offset, double base_lr,
+                           int64_t max_step, float decay, float eps, float clip_norm,
+                           float* norms_out, void* workspace, void* stream);
+
 /* ---- the exchange step: gradient all-reduce across the GPUs of a box ---------------------
  * Replaces the reference's parameter-server push (main.py:60-62 places the variables on the ps,
  * agent.py:321 applies every worker's gradients there): one process per GPU, replicas of the

@@ -17,7 +17,7 @@ def header_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = header_symbols()
-    assert len(syms) == 41, syms
+    assert len(syms) == 44, syms
     for must in ("arl_preprocess_push", "arl_forward", "arl_backward", "arl_sample_actions",
                  "arl_returns_lossgrad", "arl_clip_rmsprop", "arl_param_layout", "arl_last_error",
                  "arl_comm_init", "arl_allreduce_grads"):      # SURVEY §8b minimum export set
@@ -72,7 +72,7 @@ def test_ctypes_prototypes_match_the_header(pkg):
     decls = dict((m.group(1), m.group(2)) for m in
                  re.finditer(r"ARL_API\s+int\s+(arl_\w+)\s*\(([^;]*?)\)\s*;", src, re.S))
     kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64",
-            ctypes.c_uint64: "u64", ctypes.c_float: "f32"}
+            ctypes.c_uint64: "u64", ctypes.c_float: "f32", ctypes.c_double: "f64"}
 
     def ckind(param):
         p = " ".join(param.split())
@@ -80,6 +80,8 @@ def test_ctypes_prototypes_match_the_header(pkg):
             return "ptr"
         if p.startswith("float"):
             return "f32"
+        if p.startswith("double"):
+            return "f64"
         if p.startswith("int64_t"):
             return "i64"
         if p.startswith("uint64_t"):
