@@ -52,6 +52,12 @@ SIGNATURES = {
     "arl_step_advance": [c_vp, c_i64, c_vp],
     "arl_clip_rmsprop_sched": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, ctypes.c_double, c_i64, c_f32, c_f32,
                                c_f32, c_vp, c_vp, c_vp],
+    "arl_nature_param_layout": [c_int, ctypes.POINTER(c_i64)],
+    "arl_nature_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "arl_nature_backward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                            c_vp, c_vp, c_i64, c_vp],
+    "arl_clip_rmsprop_layout": [c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_int, c_f32, c_vp, c_i64,
+                                ctypes.c_double, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
     "arl_comm_unique_id": [c_vp],
     "arl_comm_init": [c_vp, c_int, c_int],
     "arl_comm_destroy": [],
@@ -66,6 +72,7 @@ OTHER = {
     "arl_backward_workspace_bytes": ([c_int], c_i64),
     "arl_prepared_floats": ([], c_i64),
     "arl_launch_count": ([c_int], c_i64),
+    "arl_nature_workspace_bytes": ([c_int], c_i64),
     "arl_comm_size": ([], c_int),
     "arl_comm_nccl_version": ([], c_int),
 }
@@ -140,6 +147,13 @@ def param_layout(action_size):
     """(names, offsets[11]) of the flat parameter buffer."""
     off = (c_i64 * 11)()
     check(load().arl_param_layout(int(action_size), off), "arl_param_layout")
+    return list(off)
+
+
+def nature_param_layout(action_size):
+    """Offsets (13) of the 'nature' flat parameter buffer."""
+    off = (c_i64 * 13)()
+    check(load().arl_nature_param_layout(int(action_size), off), "arl_nature_param_layout")
     return list(off)
 
 

@@ -47,6 +47,7 @@ class AgentConfig(object):
     loss_mode = 'a3c'                    # 'a3c' (network.py heads/loss) | 'async_q' (agent.py as run)
     cuda_graphs = True                   # capture predict / observe(+update) as CUDA graphs (a3c mode)
     max_graphs = 1024                    # cap of the graph cache; beyond it the loop runs eagerly
+    DQN_type = 'nips'                    # network.py:30-55 trunk: 'nips' (agent.py:226-252) | 'nature'
     collective = 'library'               # gradient all-reduce: 'library' (arl_comm_*, NCCL in the .so) | 'torch'
 
 

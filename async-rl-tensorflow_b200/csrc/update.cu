@@ -13,15 +13,17 @@ namespace arl {
 constexpr int kChunk = 4096;
 constexpr int kUpThreads = 256;
 
+constexpr int kMaxTensors = 16;           // nips: 10 tensors, nature: 12
 struct UpdatePlan {
-  int64_t off[ARL_NUM_TENSORS + 1];
-  int chunk_begin[ARL_NUM_TENSORS + 1];   // first chunk index of each tensor
+  int n;                                  // tensors
+  int64_t off[kMaxTensors + 1];
+  int chunk_begin[kMaxTensors + 1];       // first chunk index of each tensor
 };
 
 __device__ __forceinline__ int find_tensor(const UpdatePlan& p, int chunk) {
   int t = 0;
 #pragma unroll
-  for (int i = 1; i < ARL_NUM_TENSORS; ++i) t += (chunk >= p.chunk_begin[i]) ? 1 : 0;
+  for (int i = 1; i < kMaxTensors; ++i) t += (i < p.n && chunk >= p.chunk_begin[i]) ? 1 : 0;
   return t;
 }
 
@@ -83,24 +85,27 @@ rmsprop_kernel(float* __restrict__ params, float* __restrict__ rms, const float*
 
 using namespace arl;
 
-static int clip_rmsprop(float* params, float* rms, const float* grads, int action_size, float lr,
-                        float decay, float eps, float clip_norm, float* norms_out, void* workspace,
-                        const int64_t* step_dev, int64_t step_offset, double base_lr, int64_t max_step,
-                        void* stream) {
-  ARL_REQUIRE(params && rms && grads && workspace, "arl_clip_rmsprop: null pointer");
-  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
-              "arl_clip_rmsprop: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+static int clip_rmsprop_offsets(float* params, float* rms, const float* grads, const int64_t* offsets,
+                                int num_tensors, float lr, float decay, float eps, float clip_norm,
+                                float* norms_out, void* workspace, const int64_t* step_dev,
+                                int64_t step_offset, double base_lr, int64_t max_step, void* stream) {
+  ARL_REQUIRE(params && rms && grads && workspace && offsets, "arl_clip_rmsprop: null pointer");
+  ARL_REQUIRE(num_tensors >= 1 && num_tensors <= kMaxTensors, "arl_clip_rmsprop: %d tensors outside [1,%d]",
+              num_tensors, kMaxTensors);
   ARL_REQUIRE(clip_norm > 0.f && eps >= 0.f, "arl_clip_rmsprop: clip_norm must be > 0, eps >= 0");
-  const ParamLayout L = param_layout(action_size);
   UpdatePlan plan;
+  plan.n = num_tensors;
   int chunks = 0;
-  for (int t = 0; t < ARL_NUM_TENSORS; ++t) {
-    plan.off[t] = L.off[t];
+  for (int t = 0; t < num_tensors; ++t) {
+    ARL_REQUIRE(offsets[t + 1] >= offsets[t], "arl_clip_rmsprop: offsets must not decrease");
+    plan.off[t] = offsets[t];
     plan.chunk_begin[t] = chunks;
-    chunks += (int)((L.off[t + 1] - L.off[t] + kChunk - 1) / kChunk);
+    chunks += (int)((offsets[t + 1] - offsets[t] + kChunk - 1) / kChunk);
   }
-  plan.off[ARL_NUM_TENSORS] = L.off[ARL_NUM_TENSORS];
-  plan.chunk_begin[ARL_NUM_TENSORS] = chunks;
+  for (int t = num_tensors; t <= kMaxTensors; ++t) {
+    plan.off[t] = offsets[num_tensors];
+    plan.chunk_begin[t] = chunks;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
@@ -110,6 +115,27 @@ static int clip_rmsprop(float* params, float* rms, const float* grads, int actio
                                                base_lr, (long long)max_step);
   ARL_LAUNCH_CHECK("rmsprop_kernel");
   return ARL_OK;
+}
+
+static int clip_rmsprop(float* params, float* rms, const float* grads, int action_size, float lr,
+                        float decay, float eps, float clip_norm, float* norms_out, void* workspace,
+                        const int64_t* step_dev, int64_t step_offset, double base_lr, int64_t max_step,
+                        void* stream) {
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_clip_rmsprop: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  const ParamLayout L = param_layout(action_size);
+  return clip_rmsprop_offsets(params, rms, grads, L.off, ARL_NUM_TENSORS, lr, decay, eps, clip_norm, norms_out,
+                              workspace, step_dev, step_offset, base_lr, max_step, stream);
+}
+
+extern "C" int arl_clip_rmsprop_layout(float* params, float* rms, const float* grads, const int64_t* offsets,
+                                       int num_tensors, float lr, const int64_t* step_dev,
+                                       int64_t step_offset, double base_lr, int64_t max_step, float decay,
+                                       float eps, float clip_norm, float* norms_out, void* workspace,
+                                       void* stream) {
+  ARL_REQUIRE(step_dev == nullptr || max_step > 0, "arl_clip_rmsprop_layout: max_step <= 0");
+  return clip_rmsprop_offsets(params, rms, grads, offsets, num_tensors, lr, decay, eps, clip_norm, norms_out,
+                              workspace, step_dev, step_offset, base_lr, step_dev ? max_step : 1, stream);
 }
 
 extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size,

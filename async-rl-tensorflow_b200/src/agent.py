@@ -23,7 +23,7 @@ import torch.distributed as dist
 from .. import _cabi
 from .base import BaseModel
 from .history import History
-from .network import Network
+from .network import make_network
 
 
 class Agent(BaseModel):
@@ -40,8 +40,9 @@ class Agent(BaseModel):
         self.global_envs = self.world_size * self.num_envs
 
         self.step_op = 0                                         # agent.py:25 global step (host int)
-        self.network = Network(
-            action_size=self.env.action_size, data_format=self.cnn_format,
+        # network.py:30-55: 'nips' (what agent.py:226-252 wires, the default) or 'nature'
+        self.network = make_network(
+            DQN_type=getattr(config, 'DQN_type', 'nips'), action_size=self.env.action_size, data_format=self.cnn_format,
             history_length=self.history_length, screen_height=self.screen_height,
             screen_width=self.screen_width, gamma=self.discount, beta=self.beta,
             num_envs=self.num_envs, t_max=self.t_max, device=self.device, seed=self.seed,

@@ -91,8 +91,9 @@ class Network(object):
                  num_envs=256, t_max=5, device='cuda', seed=123, decay=0.99, epsilon=0.1,
                  clip_norm=40.0, min_reward=-1.0, max_reward=1.0):
         if DQN_type.lower() != 'nips':
-            raise NotImplementedError("only the 'nips' trunk (conv16-conv32-fc256) is built; "
-                                      "network.py:30-42 'nature' is out of scope (SURVEY §8f)")
+            raise ValueError("Network is the 'nips' trunk (network.py:43-52); DQN_type='nature' "
+                             "(network.py:30-42) is network_nature.NatureNetwork -- use "
+                             "make_network(DQN_type=...); got %r" % (DQN_type,))
         if data_format != 'NHWC':
             raise ValueError("main.py:45 forces NHWC; NCHW is not built")
         if (history_length, screen_height, screen_width) != (4, 84, 84):
@@ -432,3 +433,15 @@ class Network(object):
         self.rms.copy_(torch.as_tensor(z["rms"]))
         self.loaded_step = int(z["step"])
         return True
+
+
+def make_network(DQN_type='nips', **kw):
+    """network.py:30-55: the trunk is chosen by ``DQN_type`` ('nature' | 'nips'); anything else is
+    the reference's ValueError('Wrong DQN type')."""
+    kind = str(DQN_type).lower()
+    if kind == 'nips':
+        return Network(DQN_type='nips', **kw)
+    if kind == 'nature':
+        from .network_nature import NatureNetwork
+        return NatureNetwork(DQN_type='nature', **kw)
+    raise ValueError('Wrong DQN type: %s' % DQN_type)

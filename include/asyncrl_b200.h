@@ -69,6 +69,8 @@ extern "C" {
 #define ARL_FC 256               /* agent.py:251 / network.py:51                 */
 #define ARL_NUM_TENSORS 10       /* l1_w l1_b l2_w l2_b l4_w l4_b p_w p_b q_w q_b */
 #define ARL_MAX_ACTIONS 32
+#define ARL_NATURE_TENSORS 12    /* l1_w l1_b l2_w l2_b l3_w l3_b l4_w l4_b p_w p_b q_w q_b (network.py:34-42,62,79) */
+#define ARL_NATURE_FC 512        /* network.py:41-42                              */
 
 #if defined(__GNUC__)
 #define ARL_API __attribute__((visibility("default")))
@@ -250,6 +252,32 @@ ARL_API int arl_backward(const float* params, const float* prepared, int action_
                  const float* h, const float* dlogits, const float* dvalue, float* d_h,
                  float* d_a2, float* d_a1, float* grads, void* workspace, int allreduce,
                  void* stream);
+
+/* ---- the 'nature' trunk (network.py:30-42): conv32 8x8 s4 -> conv64 4x4 s2 -> conv64 3x3 s1 ->
+ * fc512 -> heads.  A second shape set with plain float32 NHWC tensors on both sides:
+ *   x  f32 [N,84,84,4]  the stacks (History.get(), values 0..255; the /255 of network.py:33 is folded in)
+ *   a1 [N,20,20,32]  a2 [N,9,9,64]  a3 [N,7,7,64] (flatten (h*7+w)*64+c)  h [N,512]
+ * Parameters / gradients: flat f32 in the order l1_w [8,8,4,32] l1_b l2_w [4,4,32,64] l2_b
+ * l3_w [3,3,64,64] l3_b l4_w [3136,512] l4_b p_w [512,A] p_b q_w [512,1] q_b (TF layouts;
+ * arl_nature_param_layout: ARL_NATURE_TENSORS+1 offsets).  Every contraction is one generic
+ * tcgen05 kernel whose producers gather the operands (im2col, its transpose, the transposed
+ * convolution per stride-parity class) -- csrc/nature.cu.  d_* are the gradients w.r.t. the
+ * layer outputs before their relu, kept for inspection.  Update: arl_clip_rmsprop_layout. */
+ARL_API int arl_nature_param_layout(int action_size, int64_t* offsets);
+ARL_API int64_t arl_nature_workspace_bytes(int action_size);
+ARL_API int arl_nature_forward(const float* params, int action_size, const float* x, float* a1, float* a2,
+                       float* a3, float* h, float* logits, float* probs, float* value,
+                       int64_t num_samples, void* stream);
+ARL_API int arl_nature_backward(const float* params, int action_size, const float* x, const float* a1,
+                        const float* a2, const float* a3, const float* h, const float* dlogits,
+                        const float* dvalue, float* d_h, float* d_a3, float* d_a2, float* d_a1,
+                        float* grads, void* workspace, int64_t num_samples, void* stream);
+/* arl_clip_rmsprop for any flat layout: num_tensors segments given by offsets[num_tensors+1]
+ * (host array).  step_dev == NULL: use lr; else the schedule of arl_clip_rmsprop_sched. */
+ARL_API int arl_clip_rmsprop_layout(float* params, float* rms, const float* grads, const int64_t* offsets,
+                            int num_tensors, float lr, const int64_t* step_dev, int64_t step_offset,
+                            double base_lr, int64_t max_step, float decay, float eps, float clip_norm,
+                            float* norms_out, void* workspace, void* stream);
 
 /* ---- device-resident step counter (CUDA-graph capture of the loop) -------------
  * A captured graph replays fixed kernel arguments, so the two host values that change on every

@@ -21,9 +21,21 @@ import torch
 import torch.nn.functional as F
 
 PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l4_w", "l4_b", "p_w", "p_b", "q_w", "q_b")
+# the 'nature' trunk of network.py:30-42: conv32 8x8 s4, conv64 4x4 s2, conv64 3x3 s1, fc512
+NATURE_PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l3_w", "l3_b", "l4_w", "l4_b", "p_w", "p_b",
+                      "q_w", "q_b")
 
 
-def param_shapes(action_size):
+def param_shapes(action_size, trunk="nips"):
+    if trunk == "nature":
+        return OrderedDict([
+            ("l1_w", (8, 8, 4, 32)), ("l1_b", (32,)),               # network.py:34-35
+            ("l2_w", (4, 4, 32, 64)), ("l2_b", (64,)),              # network.py:36-37
+            ("l3_w", (3, 3, 64, 64)), ("l3_b", (64,)),              # network.py:38-39
+            ("l4_w", (3136, 512)), ("l4_b", (512,)),                # network.py:40-42 (flatten repaired)
+            ("p_w", (512, action_size)), ("p_b", (action_size,)),
+            ("q_w", (512, 1)), ("q_b", (1,)),
+        ])
     return OrderedDict([
         ("l1_w", (8, 8, 4, 16)), ("l1_b", (16,)),
         ("l2_w", (4, 4, 16, 32)), ("l2_b", (32,)),
@@ -33,20 +45,20 @@ def param_shapes(action_size):
     ])
 
 
-def param_count(action_size):
-    return sum(int(np.prod(s)) for s in param_shapes(action_size).values())
+def param_count(action_size, trunk="nips"):
+    return sum(int(np.prod(s)) for s in param_shapes(action_size, trunk).values())
 
 
-def init_params(action_size, seed=123, dtype=np.float32):
+def init_params(action_size, seed=123, dtype=np.float32, trunk="nips"):
     """agent.py:214 / network.py:10 truncated_normal(0, .02) for the convs (values beyond
     2 sigma are re-drawn), ops.py:36-39 random_normal(stddev=.02) for ``linear`` matrices,
     biases 0 (ops.py:24, 38-39).  RNG is numpy's, not TF's: only the distribution matches."""
     rng = np.random.default_rng(seed)
     out = OrderedDict()
-    for name, shape in param_shapes(action_size).items():
+    for name, shape in param_shapes(action_size, trunk).items():
         if name.endswith("_b"):
             out[name] = np.zeros(shape, dtype)
-        elif name in ("l1_w", "l2_w"):
+        elif len(shape) == 4:                                     # conv weights: truncated normal
             w = rng.normal(0.0, 0.02, shape)
             bad = np.abs(w) > 0.04
             while bad.any():
@@ -58,13 +70,18 @@ def init_params(action_size, seed=123, dtype=np.float32):
     return out
 
 
+def names_of(params):
+    """The flat-buffer tensor order of a parameter dict (nips or nature trunk)."""
+    return NATURE_PARAM_NAMES if "l3_w" in params else PARAM_NAMES
+
+
 def flatten_params(params):
-    return np.concatenate([np.asarray(params[n]).reshape(-1) for n in PARAM_NAMES])
+    return np.concatenate([np.asarray(params[n]).reshape(-1) for n in names_of(params)])
 
 
-def unflatten_params(flat, action_size):
+def unflatten_params(flat, action_size, trunk="nips"):
     out, o = OrderedDict(), 0
-    for name, shape in param_shapes(action_size).items():
+    for name, shape in param_shapes(action_size, trunk).items():
         n = int(np.prod(shape))
         out[name] = np.asarray(flat[o:o + n]).reshape(shape)
         o += n
@@ -102,6 +119,21 @@ def forward(p, s_nhwc, keep=False, masks=None):
     m = masks or {}
     m1 = None if "a1" not in m else torch.as_tensor(m["a1"]).permute(0, 3, 1, 2)
     a1 = _relu(F.conv2d(x, p["l1_w"].permute(3, 2, 0, 1), p["l1_b"], stride=4), m1)
+    if "l3_w" in p:
+        # network.py:30-42 'nature': conv2d(64,[4,4],[2,2]) relu, conv2d(64,[3,3],[1,1]) relu,
+        # linear(512, relu) -- on the NHWC flatten (the reference hands linear the 4-D tensor,
+        # which cannot run: same repair as agent.py:231-232)
+        m2 = None if "a2" not in m else torch.as_tensor(m["a2"]).permute(0, 3, 1, 2)
+        a2 = _relu(F.conv2d(a1, p["l2_w"].permute(3, 2, 0, 1), p["l2_b"], stride=2), m2)
+        a3 = F.conv2d(a2, p["l3_w"].permute(3, 2, 0, 1), p["l3_b"], stride=1)
+        flat = _relu(a3.permute(0, 2, 3, 1).reshape(a3.shape[0], -1), m.get("a3"))
+        h = _relu(flat @ p["l4_w"] + p["l4_b"], m.get("h"))
+        logits = h @ p["p_w"] + p["p_b"]
+        value = (h @ p["q_w"] + p["q_b"]).reshape(-1)
+        if keep:
+            return logits, value, dict(a1=a1.permute(0, 2, 3, 1), a2=a2.permute(0, 2, 3, 1), a3=flat, h=h,
+                                       _a1=a1, _a2=a2)
+        return logits, value
     a2 = F.conv2d(a1, p["l2_w"].permute(3, 2, 0, 1), p["l2_b"], stride=2)
     flat = _relu(a2.permute(0, 2, 3, 1).reshape(a2.shape[0], -1), m.get("a2"))
     h = _relu(flat @ p["l4_w"] + p["l4_b"], m.get("h"))
@@ -178,7 +210,8 @@ def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=tor
     ``num_envs`` = B of the mean (global env count); None -> pure sum."""
     p = to_torch(params_np, dtype, requires_grad=True)
     logits, value, keep = forward(p, stacks, masks=masks, keep=True)
-    for k in ("_a1", "a2", "h"):
+    nature = "l3_w" in p
+    for k in (("_a1", "_a2", "a3", "h") if nature else ("_a1", "a2", "h")):
         keep[k].retain_grad()
     Rt = torch.as_tensor(np.asarray(R), dtype=dtype)
     at = torch.as_tensor(np.asarray(actions))
@@ -192,10 +225,18 @@ def gradients(params_np, stacks, actions, R, beta=0.01, num_envs=None, dtype=tor
                value_loss=vl.detach().numpy())
     # gradients w.r.t. the PRE-relu layer outputs (what the backward kernels hand from layer to
     # layer): d loss / d post-relu activation, times the activation pattern
-    for name, k in (("d_a1", "_a1"), ("d_a2", "a2"), ("d_h", "h")):
+    pairs = ((("d_a1", "_a1"), ("d_a2", "_a2"), ("d_a3", "a3"), ("d_h", "h")) if nature else
+             (("d_a1", "_a1"), ("d_a2", "a2"), ("d_h", "h")))
+    for name, k in pairs:
         act, g = keep[k].detach(), keep[k].grad
-        d = (g * (act > 0).to(g.dtype)).numpy()
-        aux[name] = d.transpose(0, 2, 3, 1) if name == "d_a1" else d
+        on = (act > 0)
+        if masks is not None and k.lstrip("_") in masks:
+            # a forced activation pattern IS the relu derivative (act = pre * mask can be a tiny
+            # negative number where the device saw a tiny positive one)
+            fm = torch.as_tensor(masks[k.lstrip("_")])
+            on = (fm.permute(0, 3, 1, 2) if k.startswith("_") else fm) > 0
+        d = (g * on.to(g.dtype)).numpy()
+        aux[name] = d.transpose(0, 2, 3, 1) if k.startswith("_") else d
     return grads, aux
 
 
@@ -224,7 +265,7 @@ def learning_rate(step, max_step=80000000, base=0.0007):
 def update(params, rms, grads, lr, clip=40.0, decay=0.99, eps=0.1):
     """Per-tensor clip (agent.py:316-319) then RMSProp (agent.py:321)."""
     new_p, new_r = OrderedDict(), OrderedDict()
-    for k in PARAM_NAMES:
+    for k in names_of(params):
         g = clip_by_norm(np.asarray(grads[k], np.float64), clip)
         w, m = rmsprop_apply(np.asarray(params[k], np.float64), np.asarray(rms[k], np.float64),
                              g, lr, decay, eps)

@@ -115,3 +115,43 @@ def test_hyperparameters_are_the_ones_the_reference_passes(net_golden, pkg):
         float(g["rms_decay"]), float(g["rms_epsilon"]), float(g["rms_momentum"]), float(g["clip_norm"]))
     assert (cfg.max_step, cfg.learning_rate, cfg.discount, cfg.beta) == (
         int(g["max_step"]), float(g["base_lr"]), float(g["discount"]), float(g["cfg_beta"]))
+
+
+# ---- the 'nature' trunk (network.py:30-42), fixture made by oracle/make_golden_nature.py ---------
+def test_nature_forward_matches_executed_reference_lines():
+    """The reference's own statements network.py:31-40 (three conv2d calls under 'Nature_DQN') +
+    linear(512) on the NHWC flatten + the heads, executed over the TF stub, against the oracle's
+    nature branch."""
+    from oracle.make_golden_nature import golden_weights as nature_weights
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nature_golden.npz"))
+    A = int(g["action_size"])
+    w = nature_weights(A)
+    assert {k: v.shape for k, v in w.items()} == dict(a3c.param_shapes(A, "nature"))
+    assert list(w) == list(a3c.NATURE_PARAM_NAMES) == list(a3c.names_of(w))
+    sums = np.array([float(np.abs(w[k].astype(np.float64)).sum()) for k in sorted(w)])
+    assert np.allclose(sums, g["weights_sum"], rtol=1e-12, atol=0)
+    logits, value, keep = a3c.forward(a3c.to_torch(w, dtype=torch.float64), golden_stacks(), keep=True)
+    assert rel_err(keep["a1"].numpy(), g["a1"]) < 1e-6 and rel_err(keep["a2"].numpy(), g["a2"]) < 1e-6   # stored as float32
+    assert rel_err(keep["a3"].numpy(), g["a3"]) < 1e-12 and rel_err(keep["h"].numpy(), g["h"]) < 1e-12
+    assert rel_err(logits.numpy(), g["logits"]) < 1e-12 and rel_err(value.numpy(), g["value"].reshape(-1)) < 1e-12
+    req = dict(r.rsplit(" (", 1) for r in g["requested"].tolist())
+    assert req["Nature_DQN/l3_conv/w"].startswith("3, 3, 64, 64") and req["Nature_DQN/l4_linear/Matrix"].startswith("3136, 512")
+
+
+def test_nature_oracle_gradients_are_consistent():
+    """Closed-form head gradients == autograd for the nature branch too, and every tensor gets one."""
+    rng = np.random.default_rng(3)
+    A, N = 5, 3
+    p = a3c.init_params(A, seed=2, trunk="nature")
+    stacks = rng.integers(0, 256, (N, 84, 84, 4), dtype=np.uint8)
+    acts, R = rng.integers(0, A, N), rng.normal(0, 1, N)
+    grads, aux = a3c.gradients(p, stacks, acts, R, 0.01, N)
+    assert set(grads) == set(a3c.NATURE_PARAM_NAMES)
+    assert aux["d_a1"].shape == (N, 20, 20, 32) and aux["d_a2"].shape == (N, 9, 9, 64)
+    assert aux["d_a3"].shape == (N, 3136) and aux["d_h"].shape == (N, 512)
+    dl, dv = a3c.analytic_head_grads(torch.as_tensor(aux["logits"]), torch.as_tensor(aux["value"]),
+                                     torch.as_tensor(acts), torch.as_tensor(R), 0.01, 1.0 / N)
+    h = a3c.forward(a3c.to_torch(p), stacks, keep=True)[2]["h"].numpy()
+    assert rel_err(h.T @ dl.numpy(), grads["p_w"]) < 1e-10 and rel_err(dv.numpy().sum().reshape(1), grads["q_b"]) < 1e-10
+    new_p, new_r = a3c.update(p, {k: np.ones_like(v) for k, v in p.items()}, grads, 0.0007)
+    assert set(new_p) == set(a3c.NATURE_PARAM_NAMES)
