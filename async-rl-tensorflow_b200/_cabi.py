@@ -32,6 +32,10 @@ SIGNATURES = {
     "arl_heads_forward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "arl_forward": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                     c_vp, c_vp, c_vp, c_vp],
+    "arl_fc_heads_forward": [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_u64,
+                             c_i64, c_vp],
+    "arl_forward_sample": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                           c_vp, c_vp, c_i64, c_i64, c_vp, c_u64, c_vp],
     "arl_debug_gemm": [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "arl_sample_actions": [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_u64, c_vp],
     "arl_greedy_actions": [c_vp, c_vp, c_int, c_int, c_vp],
@@ -50,6 +54,7 @@ SIGNATURES = {
                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     "arl_sample_actions_dev": [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_u64, c_vp],
     "arl_step_advance": [c_vp, c_i64, c_vp],
+    "arl_observe_store_advance": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp],
     "arl_clip_rmsprop_sched": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, ctypes.c_double, c_i64, c_f32, c_f32,
                                c_f32, c_vp, c_vp, c_vp],
     "arl_nature_param_layout": [c_int, ctypes.POINTER(c_i64)],

@@ -99,9 +99,26 @@ extern "C" int arl_forward(const float* params, float* prepared, int refresh_pre
   if (rc) return rc;
   rc = arl_conv2_forward(prepared, a1, a2, N, stream);
   if (rc) return rc;
-  rc = arl_fc_forward(params, prepared, a2, h, N, stream);
+  // fc256 + heads: one launch when the step fits the clustered kernel
+  return arl_fc_heads_forward(params, prepared, action_size, a2, h, logits, probs, value, nullptr, 0, 0,
+                              nullptr, 0, N, stream);
+}
+
+extern "C" int arl_forward_sample(const float* params, float* prepared, int refresh_prepared, int action_size,
+                                  const uint8_t* ring, int num_envs, int ring_slots, int first_slot,
+                                  float* a1, float* a2, float* h, float* logits, float* probs, float* value,
+                                  int32_t* actions, int64_t env_id_base, int64_t step,
+                                  const int64_t* step_dev, uint64_t seed, void* stream) {
+  ARL_REQUIRE(actions, "arl_forward_sample: null pointer");
+  int rc = ARL_OK;
+  if (refresh_prepared) rc = arl_prepare_weights(params, prepared, stream);
   if (rc) return rc;
-  return arl_heads_forward(params, action_size, h, logits, probs, value, N, stream);
+  rc = arl_conv1_forward(prepared, ring, a1, num_envs, ring_slots, first_slot, 1, stream);
+  if (rc) return rc;
+  rc = arl_conv2_forward(prepared, a1, a2, num_envs, stream);
+  if (rc) return rc;
+  return arl_fc_heads_forward(params, prepared, action_size, a2, h, logits, probs, value, actions,
+                              env_id_base, step, step_dev, seed, num_envs, stream);
 }
 
 extern "C" int arl_backward(const float* params, const float* prepared, int action_size,

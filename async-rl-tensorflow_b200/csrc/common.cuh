@@ -152,6 +152,33 @@ __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Philox4x32-10, first output word (oracle/philox.py; Random123 known answers in the tests)
+__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+// inverse CDF over the float32 running sum in index order, fallback A-1 (the sampler contract of
+// DESIGN.md §4): u = float(x >> 8) * 2^-24
+__device__ __forceinline__ int sample_index(const float* p, int A, uint32_t x) {
+  const float u = (float)(x >> 8) * 5.9604644775390625e-08f;
+  float c = 0.f;
+  int a = A - 1;
+  for (int j = 0; j < A; ++j) {
+    c = __fadd_rn(c, p[j]);
+    if (u < c) { a = j; break; }
+  }
+  return a;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

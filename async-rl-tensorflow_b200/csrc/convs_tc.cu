@@ -19,6 +19,8 @@
 //                same row-major images serve as MN-major operands (k = row index); tap b is a
 //                second copy of the image shifted by one row, tap a a descriptor row offset.
 //                Work is split over row ranges; partials are summed in a fixed order.
+#include <stdlib.h>
+
 #include "gemm_tc.cuh"
 
 namespace arl {
@@ -408,6 +410,7 @@ struct Conv2FwdArgs {
   uint8_t* a2s;          // split-bf16 chunked output, one block of num_samples rows (gemm_tc.cuh SplitMat)
   int64_t rows;          // 100 * num_samples
   int num_samples;
+  int reverse;           // walk the row tiles from the last to the first (see serpentine())
 };
 struct Conv2Fwd : tc::PolicyBase {
   using Args = Conv2FwdArgs;
@@ -422,7 +425,9 @@ struct Conv2Fwd : tc::PolicyBase {
   static constexpr bool CUSTOM_EPI = true;
   static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return (int)((g.rows + 127) / 128); }
-  static __device__ __forceinline__ TileCoord coord(const Args&, int item) { return row_tile(item); }
+  static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
+    return row_tile(g.reverse ? num_items(g) - 1 - item : item);
+  }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord&) { return 1; }
   static __device__ __forceinline__ void load_resident(const Args& g, uint8_t* res, int ptid, int nthr) {
     copy_image<RES_BYTES>(res, g.w_img, ptid, nthr);
@@ -635,10 +640,11 @@ struct Conv2Dgrad : tc::PolicyBase {
 };
 
 // =================================== weight gradients =========================================
-__device__ __forceinline__ TileCoord range_tile(int item, int64_t rows, int k_chunk) {
+// work item `item` (= its partial slice `ks`) covers the row range number `range`
+__device__ __forceinline__ TileCoord range_tile(int item, int64_t rows, int k_chunk, int range) {
   TileCoord t;
   t.mt = item; t.nt = 0; t.ks = item;
-  const int64_t b = (int64_t)item * k_chunk;
+  const int64_t b = (int64_t)range * k_chunk;
   t.k_begin = (int)b;
   t.k_end = (int)(b + k_chunk < rows ? b + k_chunk : rows);
   return t;
@@ -662,6 +668,7 @@ struct Conv2WgradArgs {
   float* bias_partials;  // [items * PROD_WARPS][32]  column sums of dy2 (= db2), per producer warp
   int64_t rows;          // 100 * num_samples
   int num_samples, k_chunk, items;
+  int reverse;           // item i takes row range items-1-i (see serpentine())
 };
 struct Conv2Wgrad : tc::PolicyBase {
   using Args = Conv2WgradArgs;
@@ -680,7 +687,7 @@ struct Conv2Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ int acc_col(int c) { return (c >> 5) * 64 + (c & 31); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
-    return range_tile(item, g.rows, g.k_chunk);
+    return range_tile(item, g.rows, g.k_chunk, g.reverse ? g.items - 1 - item : item);
   }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
     return (t.k_end - t.k_begin + 127) / 128;
@@ -745,6 +752,7 @@ struct Conv1WgradArgs {
   float* partials;       // [items][4096]
   int64_t rows;          // 441 * num_samples
   int num_samples, k_chunk, items;
+  int reverse;           // item i takes row range items-1-i (see serpentine())
 };
 struct Conv1Wgrad : tc::PolicyBase {
   using Args = Conv1WgradArgs;
@@ -763,7 +771,7 @@ struct Conv1Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ int acc_col(int c) { return (c >> 4) * 32 + (c & 15); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
-    return range_tile(item, g.rows, g.k_chunk);
+    return range_tile(item, g.rows, g.k_chunk, g.reverse ? g.items - 1 - item : item);
   }
   static __device__ __forceinline__ int num_stages(const Args&, const TileCoord& t) {
     return (t.k_end - t.k_begin + 127) / 128;
@@ -849,6 +857,15 @@ __global__ void __launch_bounds__(256) build_images_kernel(const float* __restri
 static_assert(Conv1Fwd::RES_BYTES <= kPrepW1Bytes && Conv2Fwd::RES_BYTES <= kPrepW2FBytes &&
                   Conv2Dgrad::RES_BYTES <= kPrepW2DBytes, "prepared-weight layout");
 
+// Serpentine sweep: consecutive kernels of a chain walk the samples in OPPOSITE directions, so a
+// kernel starts with the rows its predecessor touched last -- the ones still in the 126 MB L2 --
+// instead of the ones evicted longest ago.  forward: conv1 up, conv2 DOWN; backward: fc dgrad up,
+// conv2 wgrad DOWN, conv2 dgrad up, conv1 wgrad DOWN.  ARL_SERPENTINE=0 turns it off (A/B runs).
+bool serpentine() {
+  static const bool on = [] { const char* e = getenv("ARL_SERPENTINE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int split_rows(int64_t rows, int want, int* k_chunk) {
   int64_t per = (rows + want - 1) / want;
   per = (per + 127) / 128 * 128;
@@ -897,7 +914,7 @@ extern "C" int arl_conv2_forward(const float* prepared, const float* a1, float* 
               "arl_conv2_forward: pointers must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
   Conv2FwdArgs g{reinterpret_cast<const uint8_t*>(prepared) + kPrepW2F, reinterpret_cast<const uint8_t*>(a1),
-                 reinterpret_cast<uint8_t*>(a2), num_samples * 100, (int)num_samples};
+                 reinterpret_cast<uint8_t*>(a2), num_samples * 100, (int)num_samples, serpentine() ? 1 : 0};
   return tc::launch<Conv2Fwd>(g, (int)((g.rows + 127) / 128), (cudaStream_t)stream);
 }
 
@@ -925,6 +942,7 @@ extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float*
   g.rows = N * 441;
   g.num_samples = (int)N;
   g.items = split_rows(g.rows, num_sms(), &g.k_chunk);
+  g.reverse = serpentine() ? 1 : 0;
   int rc = tc::launch<Conv1Wgrad>(g, g.items, st);
   if (rc) return rc;
   return reduce_partials(g.partials, grads, g.items, 4096, st);                  // l1_w
@@ -953,6 +971,7 @@ extern "C" int arl_conv2_backward(const float* prepared, const float* a1, const 
   w.rows = num_samples * 100;
   w.num_samples = (int)num_samples;
   w.items = split_rows(w.rows, num_sms(), &w.k_chunk);
+  w.reverse = serpentine() ? 1 : 0;
   w.bias_partials = (float*)workspace + (size_t)w.items * 2 * 8192;
   int rc = tc::launch<Conv2Wgrad>(w, w.items, st);
   if (rc) return rc;

@@ -16,6 +16,9 @@ namespace arl {
 
 int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream);
+int heads_forward_sample(const float* params, int action_size, const float* h, float* logits, float* probs,
+                         float* value, int32_t* actions, int64_t env_id_base, int64_t step,
+                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st);
 
 // X fp32 [rows][8*chunks] (row stride ld) -> one split block [part][chunk][row][8 bf16].
 // Thread = (row, chunk): reads 32 contiguous bytes, writes one hi and one lo vector.
@@ -147,6 +150,13 @@ struct FcFwdCluster : tc::BulkGemm<256, 32, false, false, tc::EPI_PLAIN, 4, fals
       part[(2 * c8 + 1) * tc::kTileM + row] = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
+  // (Measured and rejected, round 2: multiplying the reduced hidden rows with [p_w | q_w] right here
+  // and finishing softmax + Philox draw in a second cluster phase -- heads and sampling fused into
+  // this kernel, parity-green -- made the launch 24.8 -> 39.5 us (ncu) and the cycle 2.164 -> 2.230 ms:
+  // only the 128 epilogue threads of each CTA have the rows, one warp per scheduler, so every
+  // shared-memory weight read and FMA chain runs at full latency while the other 160 threads and,
+  // in the second phase, three of the four CTAs wait at the cluster barrier.  The heads stay a
+  // separate warp-per-sample kernel, which now also draws the action: heads.cu.)
   static __device__ __forceinline__ void cluster_reduce(const Args& g, uint8_t* smem, int warp, int lane) {
     const uint32_t rank = tc::cluster_ctarank();
     const int row = warp * 32 + lane, m = (int)(blockIdx.x / CLUSTER) * tc::kTileM + row;
@@ -227,7 +237,7 @@ extern "C" int arl_debug_gemm(int variant, const float* A, const float* B, float
   ARL_CUDA(cudaMalloc(&bs, (size_t)(variant >= 3 ? k8 : br) * bc * 4));
   if (variant == 2) ARL_CUDA(cudaMalloc(&ms, (size_t)M * N * 4));
   int rc = split_rows(A, ac, ar, ac / 8, as, st);
-  tc::BulkGemmArgs g;
+  tc::BulkGemmArgs g = {};
   g.A = mat(as, ar, ar, ac / 8);
   if (variant >= 3) {          // the wgrad's B is K-major over the samples: the transposed split of B [K][N]
     if (!rc) rc = split_cols(B, N, N, K, bs, st);
@@ -269,16 +279,11 @@ extern "C" int arl_prepare_weights(const float* params, float* prepared, void* s
   return conv_prepare(params, prepared, (cudaStream_t)stream);
 }
 
-extern "C" int arl_fc_forward(const float* params, const float* prepared, const float* a2, float* h,
-                              int64_t num_samples, void* stream) {
-  ARL_REQUIRE(params && prepared && a2 && h, "arl_fc_forward: null pointer");
-  ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_forward: bad num_samples");
-  ARL_REQUIRE(aligned16(params) && aligned16(prepared) && aligned16(a2) && aligned16(h),
-              "arl_fc_forward: pointers must be 16-byte aligned");
-  if (num_samples == 0) return ARL_OK;
+static int fc_forward_impl(const float* params, const float* prepared, const float* a2, float* h,
+                           int64_t num_samples, cudaStream_t st) {
   const ParamLayout L = param_layout(1);
   const int M = (int)num_samples;
-  tc::BulkGemmArgs g;
+  tc::BulkGemmArgs g = {};
   g.A = mat(a2, M, M, ARL_A2_ELEMS / 8);
   g.B = mat(prepared, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
   g.mask = mat(nullptr, 0, 1, 0);
@@ -287,9 +292,39 @@ extern "C" int arl_fc_forward(const float* params, const float* prepared, const 
   // one env step of up to 37 row tiles: 4-CTA clusters, one split-K slice per CTA
   if ((M + tc::kTileM - 1) / tc::kTileM * FcFwdCluster::CLUSTER <= num_sms()) {
     g.B = mat(reinterpret_cast<const uint8_t*>(prepared) + kPrepFcWT, ARL_FC, ARL_FC, ARL_A2_ELEMS / 8);
-    return run_gemm<FcFwdCluster>(g, FcFwdCluster::CLUSTER, (cudaStream_t)stream);
+    return run_gemm<FcFwdCluster>(g, FcFwdCluster::CLUSTER, st);
   }
-  return run_gemm<FcFwd>(g, 1, (cudaStream_t)stream);
+  return run_gemm<FcFwd>(g, 1, st);
+}
+
+extern "C" int arl_fc_forward(const float* params, const float* prepared, const float* a2, float* h,
+                              int64_t num_samples, void* stream) {
+  ARL_REQUIRE(params && prepared && a2 && h, "arl_fc_forward: null pointer");
+  ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_forward: bad num_samples");
+  ARL_REQUIRE(aligned16(params) && aligned16(prepared) && aligned16(a2) && aligned16(h),
+              "arl_fc_forward: pointers must be 16-byte aligned");
+  if (num_samples == 0) return ARL_OK;
+  return fc_forward_impl(params, prepared, a2, h, num_samples, (cudaStream_t)stream);
+}
+
+extern "C" int arl_fc_heads_forward(const float* params, const float* prepared, int action_size,
+                                    const float* a2, float* h, float* logits, float* probs, float* value,
+                                    int32_t* actions, int64_t env_id_base, int64_t step,
+                                    const int64_t* step_dev, uint64_t seed, int64_t num_samples,
+                                    void* stream) {
+  ARL_REQUIRE(params && prepared && a2 && h && logits && probs && value, "arl_fc_heads_forward: null pointer");
+  ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
+              "arl_fc_heads_forward: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
+  ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_heads_forward: bad num_samples");
+  ARL_REQUIRE(env_id_base >= 0 && step >= 0, "arl_fc_heads_forward: negative argument");
+  ARL_REQUIRE(aligned16(params) && aligned16(prepared) && aligned16(a2) && aligned16(h),
+              "arl_fc_heads_forward: pointers must be 16-byte aligned");
+  if (num_samples == 0) return ARL_OK;
+  int rc = fc_forward_impl(params, prepared, a2, h, num_samples, (cudaStream_t)stream);
+  if (rc) return rc;
+  // heads + softmax + (optionally) the Philox draw: one warp-per-sample kernel
+  return heads_forward_sample(params, action_size, h, logits, probs, value, actions, env_id_base, step, step_dev,
+                              seed, num_samples, (cudaStream_t)stream);
 }
 
 extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,
@@ -318,21 +353,22 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   const tc::SplitMat dhsT = mat(reinterpret_cast<const uint8_t*>(d_h) + (size_t)M * ARL_FC * sizeof(float),
                                 ARL_FC, ARL_FC, (M + 7) / 8);
   const tc::SplitMat ws = mat(prepared, ARL_A2_ELEMS, ARL_A2_ELEMS, ARL_FC / 8);
-  // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
-  tc::BulkGemmArgs g;
-  g.A = dhs; g.B = ws; g.mask = a2s;
-  g.D = d_a2; g.bias = nullptr;
-  g.M = M; g.N = ARL_A2_ELEMS; g.K = ARL_FC; g.ldd = ARL_A2_ELEMS;
-  int rc = run_gemm<FcDgrad>(g, 1, st);
-  if (rc) return rc;
-  // wgrad: dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles = 147 items
+  // wgrad first (dW [2592,256] = a2^T . d_h, 7 split-K slices x 21 row tiles = 147 items), dgrad
+  // LAST: the next kernel of the chain (conv2 wgrad) starts with the d_a2 rows dgrad wrote last
   float* part = (float*)workspace;
+  tc::BulkGemmArgs g = {};
   g.A = a2s; g.B = dhsT; g.mask = mat(nullptr, 0, 1, 0);
-  g.D = part;
+  g.D = part; g.bias = nullptr;
   g.M = ARL_A2_ELEMS; g.N = ARL_FC; g.K = M; g.ldd = ARL_FC;
-  rc = run_gemm<FcWgrad>(g, 7, st);
+  int rc = run_gemm<FcWgrad>(g, 7, st);
   if (rc) return rc;
   rc = reduce_partials(part, gW, g.k_splits, ARL_A2_ELEMS * ARL_FC, st);
+  if (rc) return rc;
+  // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
+  g.A = dhs; g.B = ws; g.mask = a2s;
+  g.D = d_a2;
+  g.M = M; g.N = ARL_A2_ELEMS; g.K = ARL_FC; g.ldd = ARL_A2_ELEMS;
+  rc = run_gemm<FcDgrad>(g, 1, st);
   if (rc) return rc;
   // bias grad
   const int grid = (int)((num_samples + 63) / 64 < num_sms() ? (num_samples + 63) / 64 : num_sms());

@@ -206,6 +206,11 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t cta_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ float dsmem_ld1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -306,6 +311,11 @@ struct PolicyBase {
   static constexpr int CLUSTER = 1;
   template <class Args>
   static __device__ __forceinline__ void cluster_reduce(const Args&, uint8_t*, int, int) {}
+  // CLUSTER_PHASES == 2: after another cluster barrier cluster_reduce2 (epilogue warps) may read what
+  // the peers left in their shared memory during cluster_reduce
+  static constexpr int CLUSTER_PHASES = 1;
+  template <class Args>
+  static __device__ __forceinline__ void cluster_reduce2(const Args&, uint8_t*, int, int) {}
   struct EpiPre {};
   struct EpiState {};
   template <class Args, class Pre>
@@ -611,6 +621,10 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
     cluster_sync_all();                                  // every CTA's partial is in its shared memory
     if (warp < kEpiWarps) P::cluster_reduce(g, smem, warp, lane);
     cluster_sync_all();                                  // nobody reads a peer's shared memory after this
+    if constexpr (P::CLUSTER_PHASES > 1) {
+      if (warp < kEpiWarps) P::cluster_reduce2(g, smem, warp, lane);
+      cluster_sync_all();                                // ... (second phase)
+    }
   }
 
   tc_fence_before();

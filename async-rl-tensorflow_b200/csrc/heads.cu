@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(kHfThreads)
 heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                  const float* __restrict__ qw, const float* __restrict__ qb,
                  const float* __restrict__ h, float* __restrict__ logits,
-                 float* __restrict__ probs, float* __restrict__ value, int64_t num_samples, int A) {
+                 float* __restrict__ probs, float* __restrict__ value, int64_t num_samples, int A,
+                 int32_t* __restrict__ actions, uint64_t env_id_base, uint64_t step, uint64_t seed,
+                 const int64_t* __restrict__ step_dev) {
   extern __shared__ __align__(16) float sm[];   // [A+1][8][32]
+  if (actions != nullptr && step_dev != nullptr) step += (uint64_t)*step_dev;
   const int J = A + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 256 * J; i += kHfThreads) {
@@ -65,28 +68,34 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float ex = lane < A ? expf(z - mx) : 0.f;
     const float inv = 1.0f / warp_sum(ex);
+    const float pj = ex * inv;
     if (lane < A) {
       logits[n * A + lane] = z;
-      probs[n * A + lane] = ex * inv;
+      probs[n * A + lane] = pj;
     }
     if (lane == 0) value[n] = zv + qb0;
+    if (actions != nullptr) {
+      // network.py:72 in the same launch: the draw of sample_actions_kernel (Philox4x32-10 keyed by
+      // the global env id and the step; inverse CDF over the float32 running sum in index order)
+      const uint32_t x = philox_first((uint32_t)(env_id_base + (uint64_t)n), (uint32_t)step,
+                                      (uint32_t)(step >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const float u = (float)(x >> 8) * 5.9604644775390625e-08f;       // 2^-24
+      float c = 0.f;
+      int a = A - 1;
+      bool done = false;
+      for (int j = 0; j < A; ++j) {
+        const float p = __shfl_sync(0xffffffffu, pj, j);
+        if (!done) {
+          c = __fadd_rn(c, p);
+          if (u < c) { a = j; done = true; }
+        }
+      }
+      if (lane == 0) actions[n] = a;
+    }
   }
 }
 
 // ------------------------------- action selection -----------------------------------------
-__device__ __forceinline__ uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return c0;
-}
-
 // second output word of the same block (used by the epsilon-greedy draw)
 __device__ __forceinline__ void philox_two(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                            uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
@@ -380,8 +389,9 @@ __global__ void act_update_kernel(const float* __restrict__ step_reward,
 // Agent.observe's rollout append (agent.py:158-160): reward and terminal of this step -> slot t
 __global__ void observe_store_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ terminal,
                                      float* __restrict__ reward_slot, uint8_t* __restrict__ terminal_slot,
-                                     int n) {
+                                     int n, int64_t* step_counter, int64_t inc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && step_counter != nullptr) *step_counter += inc;      // agent.py:55: the loop's step
   if (b >= n) return;
   reward_slot[b] = reward[b];
   terminal_slot[b] = terminal[b] != 0 ? 1 : 0;
@@ -399,6 +409,23 @@ using namespace arl;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+namespace arl {
+int heads_forward_sample(const float* params, int action_size, const float* h, float* logits, float* probs,
+                         float* value, int32_t* actions, int64_t env_id_base, int64_t step,
+                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st) {
+  const ParamLayout L = param_layout(action_size);
+  const size_t smem = (size_t)(action_size + 1) * 256 * sizeof(float);
+  const int64_t ctas = (num_samples + kHfThreads / 32 - 1) / (kHfThreads / 32);   // one warp per sample
+  const int grid = (int)(ctas < 2LL * num_sms() ? ctas : 2LL * num_sms());
+  heads_fwd_kernel<<<grid, kHfThreads, smem, st>>>(
+      params + L.off[T_PW], params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h,
+      logits, probs, value, num_samples, action_size, actions, (uint64_t)env_id_base, (uint64_t)step, seed,
+      step_dev);
+  ARL_LAUNCH_CHECK("heads_fwd_kernel");
+  return ARL_OK;
+}
+}  // namespace arl
+
 extern "C" int arl_heads_forward(const float* params, int action_size, const float* h,
                                  float* logits, float* probs, float* value, int64_t num_samples,
                                  void* stream) {
@@ -408,15 +435,8 @@ extern "C" int arl_heads_forward(const float* params, int action_size, const flo
   ARL_REQUIRE(num_samples >= 0, "arl_heads_forward: negative size");
   ARL_REQUIRE(aligned16(h), "arl_heads_forward: h must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
-  const ParamLayout L = param_layout(action_size);
-  const size_t smem = (size_t)(action_size + 1) * 256 * sizeof(float);
-  const int64_t ctas = (num_samples + kHfThreads / 32 - 1) / (kHfThreads / 32);   // one warp per sample
-  const int grid = (int)(ctas < 2LL * num_sms() ? ctas : 2LL * num_sms());
-  heads_fwd_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(
-      params + L.off[T_PW], params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h,
-      logits, probs, value, num_samples, action_size);
-  ARL_LAUNCH_CHECK("heads_fwd_kernel");
-  return ARL_OK;
+  return heads_forward_sample(params, action_size, h, logits, probs, value, nullptr, 0, 0, nullptr, 0,
+                              num_samples, (cudaStream_t)stream);
 }
 
 extern "C" int arl_sample_actions(const float* probs, int32_t* actions, int num_envs,
@@ -540,7 +560,19 @@ extern "C" int arl_observe_store(const float* reward, const uint8_t* terminal, f
   ARL_REQUIRE(num_envs >= 0, "arl_observe_store: negative size");
   if (num_envs == 0) return ARL_OK;
   observe_store_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      reward, terminal, reward_slot, terminal_slot, num_envs);
+      reward, terminal, reward_slot, terminal_slot, num_envs, nullptr, 0);
+  ARL_LAUNCH_CHECK("observe_store_kernel");
+  return ARL_OK;
+}
+
+extern "C" int arl_observe_store_advance(const float* reward, const uint8_t* terminal, float* reward_slot,
+                                         uint8_t* terminal_slot, int num_envs, int64_t* step_counter,
+                                         int64_t inc, void* stream) {
+  ARL_REQUIRE(reward && terminal && reward_slot && terminal_slot && step_counter,
+              "arl_observe_store_advance: null pointer");
+  ARL_REQUIRE(num_envs >= 1, "arl_observe_store_advance: num_envs must be >= 1");
+  observe_store_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reward, terminal, reward_slot, terminal_slot, num_envs, step_counter, inc);
   ARL_LAUNCH_CHECK("observe_store_kernel");
   return ARL_OK;
 }

@@ -274,9 +274,9 @@ class Agent(BaseModel):
         self._sync_step_dev()
         refresh = net._fc_w_stale()
 
-        def launches():
-            net.forward(self.history, t, refresh=refresh)
-            net.sample_dev(t, self.step_dev, self.seed, self.env_id_base)
+        def launches():                                        # forward + heads + Philox draw
+            net.forward_sample(self.history, t, 0, self.seed, self.env_id_base, step_dev=self.step_dev,
+                               refresh=refresh)
         self._run(('predict', t, self.history.head, refresh), launches)
         return net.sampled_action[net._rows(t)]
 
@@ -351,10 +351,9 @@ class Agent(BaseModel):
                 if not k1_eager:
                     hist.push_into(screen, new_head)             # agent.py:156: K1, fused screen + add
                 # one kernel for both appends; the clip happens in K4 (agent.py:154)
-                _cabi.call("arl_observe_store", _cabi.ptr(reward), _cabi.ptr(terminal),
+                _cabi.call("arl_observe_store_advance", _cabi.ptr(reward), _cabi.ptr(terminal),
                            _cabi.ptr(self.batch_reward[t]), _cabi.ptr(self.batch_terminal[t]),
-                           self.num_envs, _cabi.stream_ptr())
-                _cabi.call("arl_step_advance", _cabi.ptr(self.step_dev), 1, _cabi.stream_ptr())
+                           self.num_envs, _cabi.ptr(self.step_dev), 1, _cabi.stream_ptr())
                 if will_update:
                     self._update_launches(refresh)
             self._run(('observe', t, new_head, screen.data_ptr(), reward.data_ptr(),

@@ -213,9 +213,9 @@ class Network(object):
         self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring), P(l1), B,
                          history.ring_slots, history.first_slot(0), 1, st)
         self._timed_call("arl_conv2_forward", P(self.fc_w), P(l1), P(l2), B, st)
-        self._timed_call("arl_fc_forward", P(self.params), P(self.fc_w), P(l2), P(l4), B, st)
-        self._timed_call("arl_heads_forward", P(self.params), A, P(l4), P(logits), P(probs),
-                         P(value), B, st)
+        # fc256 + heads as the one fused launch arl_forward makes (timed as arl_fc_forward)
+        self._timed_call("arl_fc_heads_forward", P(self.params), P(self.fc_w), A, P(l2), P(l4), P(logits),
+                         P(probs), P(value), None, 0, 0, None, 0, B, st)
 
     def forward(self, history, t, refresh=None):
         """Forward of the current stack into rollout slot ``t``; returns (logits, policy, value)."""
@@ -223,6 +223,31 @@ class Network(object):
         self._forward_into(history, self.l1[r], self.l2[r], self.l4[r], self.policy_logits[r],
                            self.policy[r], self.value[r], refresh)
         return self.policy_logits[r], self.policy[r], self.value[r]
+
+    def forward_sample(self, history, t, step, seed, env_id_base=0, step_dev=None, refresh=None):
+        """``forward`` into rollout slot t + ``sample`` (network.py:72) as one composed call: the
+        heads and the Philox draw run inside the fc256 kernel (arl_forward_sample).  The Philox step
+        is ``step`` (+ the int64 device counter ``step_dev`` when given)."""
+        r = self._rows(t)
+        P, st = _cabi.ptr, _cabi.stream_ptr()
+        B, A = self.num_envs, self.action_size
+        refresh = (1 if self._fc_w_stale() else 0) if refresh is None else int(bool(refresh))
+        sd = P(step_dev) if step_dev is not None else None
+        if self.timed is None:
+            _cabi.call("arl_forward_sample", P(self.params), P(self.fc_w), refresh, A, P(history.ring), B,
+                       history.ring_slots, history.first_slot(0), P(self.l1[r]), P(self.l2[r]),
+                       P(self.l4[r]), P(self.policy_logits[r]), P(self.policy[r]), P(self.value[r]),
+                       P(self.sampled_action[r]), int(env_id_base), int(step), sd, int(seed), st)
+            return self.sampled_action[r]
+        if refresh:
+            _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
+        self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring), P(self.l1[r]), B,
+                         history.ring_slots, history.first_slot(0), 1, st)
+        self._timed_call("arl_conv2_forward", P(self.fc_w), P(self.l1[r]), P(self.l2[r]), B, st)
+        self._timed_call("arl_fc_heads_forward", P(self.params), P(self.fc_w), A, P(self.l2[r]),
+                         P(self.l4[r]), P(self.policy_logits[r]), P(self.policy[r]), P(self.value[r]),
+                         P(self.sampled_action[r]), int(env_id_base), int(step), sd, int(seed), B, st)
+        return self.sampled_action[r]
 
     def a1(self):
         """conv1 activations of the rollout as float32 [N,20,20,16] (decoded from the device layout)."""

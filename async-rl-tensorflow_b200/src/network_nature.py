@@ -134,6 +134,12 @@ class NatureNetwork(Network):
                            self.policy_logits[r], self.policy[r], self.value[r])
         return self.policy_logits[r], self.policy[r], self.value[r]
 
+    def forward_sample(self, history, t, step, seed, env_id_base=0, step_dev=None, refresh=None):
+        self.forward(history, t)
+        if step_dev is not None:
+            return self.sample_dev(t, step_dev, seed, env_id_base)
+        return self.sample(t, step, seed, env_id_base)
+
     def bootstrap_value(self, history, refresh=None):
         b = self._b
         self._forward_into(history, b['x'], b['l1'], b['l2'], b['l3'], b['l4'], b['logits'], b['probs'],

@@ -49,8 +49,9 @@ def entry_work(A):
                               stack + a1, stack + a1),
         "arl_conv2_forward": ("tc_kernel<Conv2Fwd> (bulk-copied a1s, split-bf16 a2 blocks out)",
                               2.0 * 663552, a1 + a2, a1 + a2),
-        "arl_fc_forward": ("tc_kernel<FcFwdCluster> (bulk-copied split-bf16 operands)", 2.0 * 663552,
-                           a2 + h, a2 + h),
+        # fc256, then heads + softmax + Philox draw as one warp-per-sample launch
+        "arl_fc_heads_forward": ("tc_kernel<FcFwdCluster> (bulk-copied split-bf16 operands) + heads_fwd_kernel (heads + sampling)",
+                                 2.0 * 663552 + 2.0 * 256 * (A + 1), a2 + h + heads_out + 4, a2 + h + heads_out + 4),
         "arl_heads_forward": ("heads_fwd_kernel", 2.0 * 256 * (A + 1), h + heads_out, h + heads_out),
         "arl_sample_actions": ("sample_actions_kernel", 0.0, 4 * A + 4, 4 * A + 4),
         "arl_returns_lossgrad": ("returns_lossgrad_kernel", 0.0, 4 * (A + 1) + 9 + 4 + 4 * (A + 1),
@@ -371,7 +372,7 @@ def main():
             e["ms_per_step"] = per_entry[n]
             entries[n] = e
     # fused floors of the chains: only what enters / must be kept leaves a count
-    fwd = ["arl_conv1_forward", "arl_conv2_forward", "arl_fc_forward", "arl_heads_forward"]
+    fwd = ["arl_conv1_forward", "arl_conv2_forward", "arl_fc_heads_forward"]
     bwd = ["arl_heads_backward", "arl_fc_backward", "arl_conv2_backward", "arl_conv1_backward"]
     fwd_bytes = 28224 + 25600 + 10368 + 1024 + 4 * (2 * A + 1)      # stack in; a1, a2, h, heads kept
     bwd_bytes = 1024 + 4 * (A + 1) + 10368 + 25600 + 28224          # h, d heads, a2, a1, stack in

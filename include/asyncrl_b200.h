@@ -159,12 +159,29 @@ ARL_API int arl_fc_forward(const float* params, const float* prepared, const flo
                    int64_t num_samples, void* stream);
 ARL_API int arl_heads_forward(const float* params, int action_size, const float* h, float* logits,
                       float* probs, float* value, int64_t num_samples, void* stream);
+/* fc256, then heads + softmax and -- when `actions` is not NULL -- the action draw of
+ * arl_sample_actions in the SAME launch as the heads (Philox step = step + *step_dev when step_dev
+ * is not NULL): two launches for agent.py:251-254 / network.py:62-79 instead of three.  (Fusing the
+ * heads into the fc256 kernel's cluster reduction was built, measured slower and dropped: fc.cu.) */
+ARL_API int arl_fc_heads_forward(const float* params, const float* prepared, int action_size,
+                         const float* a2, float* h, float* logits, float* probs, float* value,
+                         int32_t* actions, int64_t env_id_base, int64_t step, const int64_t* step_dev,
+                         uint64_t seed, int64_t num_samples, void* stream);
+
 /* The four above back to back, after arl_prepare_weights when refresh_prepared != 0 (pass 1
  * unless `prepared` was made from these very parameters by an earlier call). */
 ARL_API int arl_forward(const float* params, float* prepared, int refresh_prepared, int action_size,
                 const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                 float* a1, float* a2, float* h, float* logits, float* probs, float* value,
                 void* stream);
+/* arl_forward for ONE env step (steps = 1) that also draws the actions (network.py:72):
+ * conv1, conv2, then arl_fc_heads_forward. */
+ARL_API int arl_forward_sample(const float* params, float* prepared, int refresh_prepared, int action_size,
+                       const uint8_t* ring, int num_envs, int ring_slots, int first_slot,
+                       float* a1, float* a2, float* h, float* logits, float* probs, float* value,
+                       int32_t* actions, int64_t env_id_base, int64_t step, const int64_t* step_dev,
+                       uint64_t seed, void* stream);
+
 
 /* Test hook for the tcgen05 GEMM behind arl_fc_forward/backward (fp32 inputs are split into
  * scratch blocks first; bf16x3 products, fp32 accumulation in TMEM), on caller-chosen shapes.
@@ -291,6 +308,11 @@ ARL_API int arl_clip_rmsprop_layout(float* params, float* rms, const float* grad
 ARL_API int arl_sample_actions_dev(const float* probs, int32_t* actions, int num_envs, int action_size,
                            int64_t env_id_base, const int64_t* step_dev, uint64_t seed, void* stream);
 ARL_API int arl_step_advance(int64_t* counter, int64_t inc, void* stream);
+/* arl_observe_store + arl_step_advance as one launch (the per-step rollout append of agent.py:158-160
+ * and the loop's step increment of agent.py:55). */
+ARL_API int arl_observe_store_advance(const float* reward, const uint8_t* terminal, float* reward_slot,
+                              uint8_t* terminal_slot, int num_envs, int64_t* step_counter, int64_t inc,
+                              void* stream);
 ARL_API int arl_clip_rmsprop_sched(float* params, float* rms, const float* grads, int action_size,
                            const int64_t* step_dev, int64_t step_offset, double base_lr,
                            int64_t max_step, float decay, float eps, float clip_norm,
