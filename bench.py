@@ -190,8 +190,8 @@ def workload_config(args, ref=False):
                         % (args.envs, args.actions, args.t_max),
             "envs_per_gpu": args.envs, "t_max": args.t_max, "action_size": args.actions,
             "frame": "210x160x3 uint8", "frames_per_step_per_gpu": args.envs * args.t_max,
-            "l2_policy": "inputs larger than L2: each env step reads %d MB of fresh frames"
-                         % (args.envs * 100800 // 2 ** 20),
+            "l2_policy": "inputs larger than L2: each env step reads %d MB of fresh frames (pool of %s steps)"
+                         % (args.envs * 100800 // 2 ** 20, getattr(args, "pool_used", "t_max")),
             "parallelism": "dp%d (env-sharded, one NCCL all-reduce of the 2.7 MB gradient per step)"
                            % args.gpus}
 
@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-cycles-per-step", type=int, default=40)
     ap.add_argument("--profile-all", action="store_true", help="print per-entry times to stderr")
+    ap.add_argument("--pool", type=int, default=0, help="steps of synthetic frames kept (0: t_max, capped to ~24 GB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -260,8 +261,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the frame pool rotates over `pool` env steps (> L2 in any case: one step of 1024 envs is 103 MB);
+    # default t_max, capped so that the pool stays under ~24 GB at the large sweep points
+    pool = args.pool if args.pool > 0 else max(2, min(T, int(24e9 // (B * 100800))))
+    args.pool_used = pool
+
     def make_agent(host):
-        env = pkg.GymEnvironment(cfg, env=pkg.SyntheticAtari(B, A, seed=123 + rank, pool=T,
+        env = pkg.GymEnvironment(cfg, env=pkg.SyntheticAtari(B, A, seed=123 + rank, pool=pool,
                                                              device=dev, host=host), device=dev)
         agent = pkg.Agent(cfg, env, device=dev)
         agent.before_train()
@@ -387,6 +393,11 @@ def main():
         cyc_bytes = 87696 * B * T + fwd_bytes * B * (T + 1) + bwd_bytes * B * T + 20 * n_params
         chains["cycle"] = {"bytes_per_step": cyc_bytes, "sum_of_entries_ms": sum(per_entry.values())}
     dominant = max(entries, key=lambda k: entries[k]["ms_per_step"])
+    if world > 1:
+        # every rank must take the same path below (the eager re-run contains collectives): rank 0 decides
+        box = [dominant]
+        dist.broadcast_object_list(box, src=0)
+        dominant = box[0]
     if args.profile_all and rank == 0:
         print("per-entry ms per step:", json.dumps({k: round(v, 4) for k, v in
                                                     sorted(per_entry.items(), key=lambda x: -x[1])}),
@@ -448,11 +459,40 @@ def main():
         d2h = {"actions": torch.empty(B, dtype=torch.int32, pin_memory=True),
                "loss": torch.empty(3, dtype=torch.float32, pin_memory=True)}
         ms_e2e, _, _ = timed(agent, env, d2h=d2h)
-        e2e = {"value": world * B * T * K / (ms_e2e * 1e-3), "unit": UNIT,
+        # what the host->device path of THIS box gives when nothing else runs: every
+        # rank copies its own pinned pool at the same time -- plain whole-frame cudaMemcpyAsync, and
+        # the rows-only strided copy the loop uses -- max time over ranks
+        syn = env.env
+        def upload_rate(fn, nbytes, reps=10):
+            for _ in range(2):
+                fn(0)
+            barrier()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for i in range(reps):
+                fn(i)
+            u1.record()
+            barrier()
+            t = torch.tensor([u0.elapsed_time(u1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return nbytes * reps / (float(t.item()) * 1e-3) / 1e9
+        plain = upload_rate(lambda i: syn._stage[i & 1].copy_(syn._frames[i % syn.pool], non_blocking=True),
+                            B * 100800)
+        rows = upload_rate(lambda i: cabi.call("arl_upload_frames", syn._frames[i % syn.pool].data_ptr(),
+                                               cabi.ptr(syn._stage[i & 1]), B, cabi.stream_ptr()), B * 80640)
+        e2e_value = world * B * T * K / (ms_e2e * 1e-3)
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": T * B * 80640, "d2h_bytes_per_step": T * B * 4 + 12,
                "ms_per_step": ms_e2e / K,
+               "upload": {"plain_memcpy_gbs_per_gpu": plain, "rows_only_copy_gbs_per_gpu": rows,
+                          "aggregate_rows_only_gbs": rows * world,
+                          "ceiling_frames_per_s": rows * world * 1e9 / 80640,
+                          "e2e_fraction_of_ceiling": e2e_value * 80640 / (rows * world * 1e9),
+                          "note": "all ranks copy at once from their own pinned pools, nothing else running; "
+                                  "the e2e arm needs 80 640 B per frame over this path"},
                "note": "frames in pinned host memory, double-buffered upload of the 168 of 210 rows "
-                       "the resize reads (arl_upload_frames); PCIe-bound"}
+                       "the resize reads (arl_upload_frames: one 2-D copy per step); PCIe-bound"}
         del agent, env
 
     if rank == 0:
