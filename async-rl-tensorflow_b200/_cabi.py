@@ -46,12 +46,12 @@ SIGNATURES = {
                        c_f32, c_f32, c_vp],
     "arl_returns_lossgrad": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,
                              c_int, c_int, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp],
-    "arl_heads_backward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_fc_backward": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_conv2_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
-    "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "arl_heads_backward": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp],
+    "arl_fc_backward": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp],
+    "arl_conv2_backward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp],
+    "arl_conv1_backward": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp],
     "arl_backward": [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
-                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_vp],
     "arl_sample_actions_dev": [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_u64, c_vp],
     "arl_step_advance": [c_vp, c_i64, c_vp],
     "arl_observe_store_advance": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp],

@@ -126,12 +126,14 @@ extern "C" int arl_backward(const float* params, const float* prepared, int acti
                             int steps, const float* a1,
                             const float* a2, const float* h, const float* dlogits,
                             const float* dvalue, float* d_h, float* d_a2, float* d_a1, float* grads,
-                            void* workspace, int allreduce, void* stream) {
+                            void* workspace, float tensor_scale, int allreduce, void* stream) {
+  ARL_REQUIRE(tensor_scale > 0.f, "arl_backward: tensor_scale must be > 0");
   const int64_t N = (int64_t)num_envs * steps;
+  const float unscale = 1.0f / tensor_scale;
   int rc = arl_heads_backward(params, action_size, h, dlogits, dvalue, d_h, grads, workspace, N,
-                              stream);
+                              tensor_scale, stream);
   if (rc) return rc;
-  rc = arl_fc_backward(prepared, a2, num_envs, d_h, d_a2, grads, workspace, N, stream);
+  rc = arl_fc_backward(prepared, a2, num_envs, d_h, d_a2, grads, workspace, N, unscale, stream);
   if (rc) return rc;
   // l4_w .. q_b are final now: 98 % of the gradient bytes travel while the conv kernels run
   const bool comm = allreduce && arl_comm_size() > 1;
@@ -144,9 +146,9 @@ extern "C" int arl_backward(const float* params, const float* prepared, int acti
   // the statically scheduled CTAs of the next kernel by their own run time: nothing is hidden.
   static const bool overlap = [] { const char* e = getenv("ARL_ALLREDUCE_OVERLAP"); return e && e[0] == '1'; }();
   if (comm && !overlap) {
-    rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, stream);
+    rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, unscale, stream);
     if (rc) return rc;
-    rc = arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps, stream);
+    rc = arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps, unscale, stream);
     if (rc) return rc;
     return arl_allreduce_grads(grads, L.off[ARL_NUM_TENSORS], stream);
   }
@@ -154,10 +156,10 @@ extern "C" int arl_backward(const float* params, const float* prepared, int acti
     rc = arl_allreduce_begin(grads, L.off[T_L4W], L.off[ARL_NUM_TENSORS] - L.off[T_L4W], stream);
     if (rc) return rc;
   }
-  rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, stream);
+  rc = arl_conv2_backward(prepared, a1, d_a2, d_a1, grads, workspace, N, unscale, stream);
   if (rc) return rc;
   rc = arl_conv1_backward(ring, d_a1, grads, workspace, num_envs, ring_slots, first_slot, steps,
-                          stream);
+                          unscale, stream);
   if (rc || !comm) return rc;
   rc = arl_allreduce_begin(grads, 0, L.off[T_L4W], stream);        // l1_w .. l2_b
   if (rc) return rc;

@@ -26,6 +26,8 @@
 namespace arl {
 
 int reduce_partials(const float* partials, float* out, int num_partials, int n, cudaStream_t stream);
+int reduce_partials_scaled(const float* partials, float* out, int num_partials, int n, float alpha,
+                           cudaStream_t stream);
 
 namespace {
 using tc::TileCoord;
@@ -71,11 +73,13 @@ struct PixelGrid {
 };
 
 // Streams the pixels of grid rows [z0, z0+ROWS) (rows >= z_end count as zero) into a hi/lo image
-// pair whose 16-B vector (row r, chunk kc) sits at kc*PL + r*16.  U float4 loads are in flight per
+// pair whose 16-B vector (row r, chunk kc) sits at kc*PL + r*16; FP16 chooses the element format of
+// the pair (fp16 hi + lo next to fp16 activations, bf16 hi + lo next to bf16 weights: the two
+// operands of one MMA must share a format).  U float4 loads are in flight per
 // lane before the first one is consumed (U * gsize >= the whole window => one latency per stage).
 // acc (optional) accumulates the column sums of what was stored: a lane owns floats
 // (glane % CF4)*4 .. +3 of every pixel it touches.
-template <class G, int CF4, int ROWS, int PL, int U, bool ACC>
+template <class G, int CF4, int ROWS, int PL, int U, bool ACC, bool FP16>
 __device__ __forceinline__ void stream_pixels(uint8_t* hi, uint8_t* lo, const float* __restrict__ src,
                                               int z0, int z_end, int num_samples, int glane,
                                               int gsize, float (&acc)[4]) {
@@ -105,7 +109,9 @@ __device__ __forceinline__ void stream_pixels(uint8_t* hi, uint8_t* lo, const fl
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (rr[u] < 0) continue;
-      tc::store_half_split(hi, lo, (q >> 1) * PL + rr[u] * 16 + (q & 1) * 8, x[u]);
+      const int off = (q >> 1) * PL + rr[u] * 16 + (q & 1) * 8;
+      if (FP16) tc::store_half_split_h(hi, lo, off, x[u]);
+      else tc::store_half_split(hi, lo, off, x[u]);
       if (ACC) { acc[0] += x[u].x; acc[1] += x[u].y; acc[2] += x[u].z; acc[3] += x[u].w; }
     }
   }
@@ -196,38 +202,39 @@ __device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr
   }
 }
 
-// ---- a1 in HBM: split bf16, blocked ("a1s") ----------------------------------------------------
+// ---- a1 in HBM: fp16, blocked ("a1s") -----------------------------------------------------------
 // conv1's output is only ever consumed as a tensor-core operand (conv2 forward / conv2 wgrad)
-// and as a relu mask (conv2 dgrad), so it is stored the way those kernels want it -- same 25 600
-// bytes per sample as fp32 [20,20,16], but as bf16 hi and lo planes in space-to-depth order:
-//   a1s[n][part (hi,lo)][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 channels]     (16-B vectors)
+// and as a relu mask (conv2 dgrad), so it is stored the way those kernels want it -- ONE fp16 per
+// value (12 800 bytes per sample, half of fp32 [20,20,16]) in space-to-depth order:
+//   a1s[n][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 channels]     (16-B vectors)
 // with pixel (y,x) = (2yp+i, 2xp+j) and channels chalf*8 .. chalf*8+7.  A run of X2 rows of one
-// (part, kc) is then contiguous: the conv2 kernels fetch their A images with cp.async.bulk and
-// convert nothing.  hi + lo reproduces the fp32 value to ~2^-17 relative.
-constexpr int kA1sSample = 25600, kA1sPart = 12800, kA1sPlane = 1600;    // bytes
-__device__ __forceinline__ int a1s_offset(int y, int x, int chalf) {       // bytes inside a part
+// plane kc is then contiguous: the conv2 kernels fetch their A images with cp.async.bulk and
+// convert nothing.  (Round 1 kept a bf16 hi + lo pair, the bytes of fp32; tests/precision_study.py
+// is the measurement behind the narrower format.)
+constexpr int kA1sSample = 12800, kA1sPlane = 1600;    // bytes
+__device__ __forceinline__ int a1s_offset(int y, int x, int chalf) {       // bytes inside a sample
   return (((y & 1) * 2 + (x & 1)) * 2 + chalf) * kA1sPlane + ((y >> 1) * 10 + (x >> 1)) * 16;
 }
 
-// Bulk copies of X2 grid rows [xr0, xr0 + ROWS) of planes (part, kc) into an image whose vector
-// (row r, kc) sits at part*IMG + kc*PL + r*16; SHIFT additionally fills planes 8..15 with the
-// image shifted by one row (tap b = 1 of the wgrad).  Called by the lanes that own one (part, kc)
-// each; returns the bytes this lane has put in flight (it must expect_tx them BEFORE calling).
-template <int ROWS, int PL, int IMG, bool SHIFT>
+// Bulk copies of X2 grid rows [xr0, xr0 + ROWS) of plane kc into an image whose vector (row r, kc)
+// sits at kc*PL + r*16; SHIFT additionally fills planes 8..15 with the image shifted by one row
+// (tap b = 1 of the wgrad).  Called by the lanes that own one plane each; returns the bytes this
+// lane has put in flight (it must expect_tx them BEFORE calling).
+template <int ROWS, bool SHIFT>
 __device__ __forceinline__ uint32_t a1s_bulk_bytes(int xr0, int num_samples) {
-  // bytes one (part, kc) owner moves: every existing row once (+ once more, minus the first, if SHIFT)
+  // bytes one plane owner moves: every existing row once (+ once more, minus the first, if SHIFT)
   const int rows_left = num_samples * 100 - xr0;
   const int n = rows_left < ROWS ? (rows_left > 0 ? rows_left : 0) : ROWS;
   return (uint32_t)(SHIFT ? (n > 0 ? 2 * n - 1 : 0) : n) * 16u;
 }
-template <int ROWS, int PL, int IMG, bool SHIFT>
+template <int ROWS, int PL, bool SHIFT>
 __device__ __forceinline__ void a1s_bulk_issue(uint8_t* st, const uint8_t* a1s, int xr0, int num_samples,
-                                               int part, int kc, uint64_t* full) {
+                                               int kc, uint64_t* full) {
   int r = 0, n = xr0 / 100, q = xr0 - n * 100;
   while (r < ROWS && n < num_samples) {
     const int cnt = min(100 - q, ROWS - r);
-    const uint8_t* src = a1s + (size_t)n * kA1sSample + part * kA1sPart + kc * kA1sPlane + q * 16;
-    uint8_t* dst = st + part * IMG + kc * PL + r * 16;
+    const uint8_t* src = a1s + (size_t)n * kA1sSample + kc * kA1sPlane + q * 16;
+    uint8_t* dst = st + kc * PL + r * 16;
     bulk_g2s(dst, src, (uint32_t)cnt * 16u, full);
     if (SHIFT) {
       if (r > 0) bulk_g2s(dst + 8 * PL - 16, src, (uint32_t)cnt * 16u, full);
@@ -237,15 +244,15 @@ __device__ __forceinline__ void a1s_bulk_issue(uint8_t* st, const uint8_t* a1s, 
   }
 }
 // rows of the window beyond the last sample (last tile only): zero, by all lanes of the group
-template <int ROWS, int PL, int IMG, int PLANES>
+template <int ROWS, int PL, int PLANES>
 __device__ __forceinline__ void a1s_zero_tail(uint8_t* st, int xr0, int num_samples, int glane, int gsize) {
   const int valid = num_samples * 100 - xr0;
   if (valid >= ROWS) return;
-  for (int c = glane; c < ROWS * PLANES * 2; c += gsize) {
-    const int r = c % ROWS, pk = c / ROWS, part = pk / PLANES, kc = pk - part * PLANES;
+  for (int c = glane; c < ROWS * PLANES; c += gsize) {
+    const int r = c % ROWS, kc = c / ROWS;
     // planes 8.. (if any) hold the image shifted by one row: their row r is source row r+1
     if (r >= valid - (kc >= 8 ? 1 : 0))
-      *reinterpret_cast<uint4*>(st + part * IMG + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(st + kc * PL + r * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -253,7 +260,7 @@ __device__ __forceinline__ void a1s_zero_tail(uint8_t* st, int xr0, int num_samp
 struct Conv1FwdArgs {
   const uint8_t* w_img;  // prepared: s8 limb image of l1_w | 3 limb scales | l1_b
   RingGeo geo;
-  uint8_t* a1s;          // split-bf16 blocked output (see a1s above), 25 600 B per sample
+  uint8_t* a1s;          // fp16 blocked output (see a1s above), 12 800 B per sample
   int64_t rows;          // 441 * num_samples (grid rows)
   int num_samples;
 };
@@ -369,8 +376,8 @@ struct Conv1Fwd : tc::PolicyBase {
       }
     }
   }
-  // epilogue: lane = output pixel; limbs -> fp32 -> /255 + bias, relu -> bf16 hi/lo -> four 16-B
-  // vectors straight into the a1s planes (no staging: 16 consecutive lanes write 256 contiguous B)
+  // epilogue: lane = output pixel; limbs -> fp32 -> /255 + bias, relu -> fp16 -> two 16-B vectors
+  // straight into the a1s planes (no staging: 16 consecutive lanes write 256 contiguous B)
   static __device__ __forceinline__ void custom_epilogue(const Args& g, const TileCoord& t,
                                                          const uint8_t* res, uint32_t taddr, int row,
                                                          EpiPre&, EpiState&) {
@@ -387,26 +394,24 @@ struct Conv1Fwd : tc::PolicyBase {
     const int q = xr - n * GROWS, y = q / GW, x = q - y * GW;
     if (n >= g.num_samples || y >= 20 || x >= 20) return;
     const float2* bias = reinterpret_cast<const float2*>(res + BIAS_OFF);
-    uint32_t hi[8], lo[8];
+    uint32_t h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float2 bb = bias[e];
       const float o0 = fmaxf(fmaf(v[2 * e], 1.0f / 255.0f, bb.x), 0.f);
       const float o1 = fmaxf(fmaf(v[2 * e + 1], 1.0f / 255.0f, bb.y), 0.f);
-      tc::split2(o0, o1, hi[e], lo[e]);
+      h[e] = tc::pack_h2(o0, o1);
     }
     uint8_t* d = g.a1s + (size_t)n * kA1sSample + a1s_offset(y, x, 0);
-    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(d + kA1sPlane) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    *reinterpret_cast<uint4*>(d + kA1sPart) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(d + kA1sPart + kA1sPlane) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(d + kA1sPlane) = make_uint4(h[4], h[5], h[6], h[7]);
   }
 };
 
 // =================================== conv2 forward ============================================
 struct Conv2FwdArgs {
-  const uint8_t* w_img;  // prepared: [hi | lo] image of l2_w | l2_b
-  const uint8_t* a1s;    // split-bf16 blocked conv1 output
+  const uint8_t* w_img;  // prepared: fp16 [hi | lo] image of l2_w | l2_b
+  const uint8_t* a1s;    // fp16 blocked conv1 output
   uint8_t* a2s;          // split-bf16 chunked output, one block of num_samples rows (gemm_tc.cuh SplitMat)
   int64_t rows;          // 100 * num_samples
   int num_samples;
@@ -417,8 +422,9 @@ struct Conv2Fwd : tc::PolicyBase {
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
   static constexpr int PL = (TROWS + 1) * 16, IMG = 8 * PL;
   // operands arrive by cp.async.bulk straight from the a1s planes: one producer warp per stage,
-  // lanes 0..15 own one (part, kc) plane each; two epilogue sets
-  static constexpr int EPI_SETS = 2, PROD_WARPS = 4, STAGES = 4, STAGE_BYTES = 2 * IMG;     // hi + lo
+  // lanes 0..7 own one plane each; two epilogue sets.  One fp16 image per stage (18 KB): six
+  // stages = six tiles' worth of copies in flight per SM.
+  static constexpr int EPI_SETS = 2, PROD_WARPS = 6, STAGES = 6, STAGE_BYTES = IMG;
   // resident W2 image: rows = [32 co hi | 32 co lo] (N = 64), 32 k-chunk planes
   static constexpr int PLB = 65 * 16, B_IMG = 32 * PLB, BIAS_OFF = B_IMG, RES_BYTES = B_IMG + 128;
   static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 32, SEG = 32;
@@ -442,35 +448,32 @@ struct Conv2Fwd : tc::PolicyBase {
       float x[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) x[e] = w2[((kh * 4 + kw) * 16 + chalf * 8 + e) * 32 + co];
-      tc::store_chunk_split(res, res + 32 * 16, kc * PLB + co * 16, x);
+      tc::store_chunk_split_h(res, res + 32 * 16, kc * PLB + co * 16, x);
     }
   }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int,
                                                     uint8_t* st, int glane, int gsize, Prod&) {
-    a1s_zero_tail<TROWS, PL, IMG, 8>(st, t.mt * 128, g.num_samples, glane, gsize);
+    a1s_zero_tail<TROWS, PL, 8>(st, t.mt * 128, g.num_samples, glane, gsize);
   }
   static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int, uint8_t* st,
                                                     int glane, int, uint64_t* full) {
-    if (glane >= 16) return false;
-    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PL, IMG, false>(t.mt * 128, g.num_samples));
-    a1s_bulk_issue<TROWS, PL, IMG, false>(st, g.a1s, t.mt * 128, g.num_samples, glane >> 3, glane & 7, full);
+    if (glane >= 8) return false;
+    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, false>(t.mt * 128, g.num_samples));
+    a1s_bulk_issue<TROWS, PL, false>(st, g.a1s, t.mt * 128, g.num_samples, glane, full);
     return true;
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
-    constexpr uint32_t idesc64 = tc::make_idesc(64), idesc32 = tc::make_idesc(32);
-#pragma unroll
+    constexpr uint32_t idesc64 = tc::make_idesc_h(64);
     const uint64_t da0 = tc::make_sdesc(st, PL), db0 = tc::make_sdesc(res, PLB);   // one derivation per stage
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
       const uint32_t aoff = ((tap >> 1) * GW + (tap & 1)) * 16;
 #pragma unroll
       for (int k16 = 0; k16 < 4; ++k16) {
-        const uint64_t da_hi = tc::sdesc_advance(da0, aoff + 2 * k16 * PL);
-        const uint64_t da_lo = tc::sdesc_advance(da0, aoff + IMG + 2 * k16 * PL);
+        const uint64_t da = tc::sdesc_advance(da0, aoff + 2 * k16 * PL);
         const uint64_t db = tc::sdesc_advance(db0, (tap * 8 + 2 * k16) * PLB);
-        tc::umma_f16(d, da_hi, db, idesc64, (tap | k16) != 0 ? 1u : 0u);   // x_hi . [w_hi | w_lo]
-        tc::umma_f16(d, da_lo, db, idesc32, 1u);                            // x_lo . w_hi
+        tc::umma_f16(d, da, db, idesc64, (tap | k16) != 0 ? 1u : 0u);      // x . [w_hi | w_lo]
       }
     }
   }
@@ -488,7 +491,7 @@ struct Conv2Fwd : tc::PolicyBase {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       float v[8];
-      tc::tmem_ld8_sum(taddr + c8 * 8, taddr + 32 + c8 * 8, v);          // x_hi.w_hi + x_lo.w_hi, x_hi.w_lo
+      tc::tmem_ld8_sum(taddr + c8 * 8, taddr + 32 + c8 * 8, v);          // x.w_hi + x.w_lo
       if (!ok) continue;
       const float4 b0 = bias[c8 * 2], b1 = bias[c8 * 2 + 1];
       uint4 h, l;
@@ -504,8 +507,8 @@ struct Conv2Fwd : tc::PolicyBase {
 
 // =================================== conv2 input gradient =====================================
 struct Conv2DgradArgs {
-  const uint8_t* w_img;  // prepared: transposed [hi | lo] image of l2_w
-  const uint8_t* a1s;    // relu mask of conv1: sign of the hi plane of the split-bf16 output
+  const uint8_t* w_img;  // prepared: transposed bf16 [hi | lo] image of l2_w
+  const uint8_t* a1s;    // relu mask of conv1: sign of its fp16 output
   const float* dy2;      // [N, 81, 32]
   uint8_t* dy1s;         // conv1 output gradient, split bf16 on the conv1 X grid ("dy1s", see below)
   float* bias_partials;  // [grid * 8 epilogue warps][16]: column sums of dy1 (= the conv1 bias gradient)
@@ -552,8 +555,8 @@ struct Conv2Dgrad : tc::PolicyBase {
                                                     uint8_t* st, int glane, int gsize, Prod&) {
     float unused[4];
     const int z0 = t.mt * 128;
-    stream_pixels<GridZ, 8, TROWS, PL, 7, false>(st, st + IMG, g.dy2, z0, z0 + TROWS, g.num_samples,
-                                                  glane, gsize, unused);
+    stream_pixels<GridZ, 8, TROWS, PL, 7, false, false>(st, st + IMG, g.dy2, z0, z0 + TROWS, g.num_samples,
+                                                         glane, gsize, unused);
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int, uint32_t st,
                                                uint32_t res, uint32_t d) {
@@ -589,7 +592,7 @@ struct Conv2Dgrad : tc::PolicyBase {
     const int pr = t.mt * 128 + row, n = pr / GROWS;
     const int q = pr - n * GROWS, yy = q / GW, xx = q - yy * GW;
     const bool ok = n < g.num_samples && yy < 10 && xx < 10;
-    const uint8_t* p = g.a1s + (int64_t)n * kA1sSample + (yy * 10 + xx) * 16;     // plane = cls*2 + chalf
+    const uint8_t* p = g.a1s + (int64_t)n * kA1sSample + (yy * 10 + xx) * 16;     // plane = cls*2 + chalf (fp16 a1)
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       pre.m[i] = ok ? __ldg(reinterpret_cast<const uint4*>(p + i * kA1sPlane)) : make_uint4(0u, 0u, 0u, 0u);
@@ -614,7 +617,7 @@ struct Conv2Dgrad : tc::PolicyBase {
           const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            if ((int16_t)(w[i] & 0xFFFFu) <= 0) v[2 * i] = 0.f;        // bf16 > 0 <=> its bits as int16 > 0
+            if ((int16_t)(w[i] & 0xFFFFu) <= 0) v[2 * i] = 0.f;        // fp16 > 0 <=> its bits as int16 > 0
             if ((int32_t)w[i] < 0x10000) v[2 * i + 1] = 0.f;
           }
 #pragma unroll
@@ -662,7 +665,7 @@ __device__ __forceinline__ void bias_partial_store(float* dst_row, float (&acc)[
 }
 
 struct Conv2WgradArgs {
-  const uint8_t* a1s;    // split-bf16 blocked conv1 output
+  const uint8_t* a1s;    // fp16 blocked conv1 output
   const float* dy2;
   float* partials;       // [items][8192]
   float* bias_partials;  // [items * PROD_WARPS][32]  column sums of dy2 (= db2), per producer warp
@@ -674,16 +677,19 @@ struct Conv2Wgrad : tc::PolicyBase {
   using Args = Conv2WgradArgs;
   struct Prod { float acc[4]; };    // running column sums of dy2 (bias gradient)
   // dW2[(a,b) tap][ch][co] = sum_P X2[P + a*10 + b][ch] * dy2[P][co] over the rows P of the X2 grid.
-  // The hi and lo images of X2 (a1s) are the two halves of M (rows part*64 + ch): every a1s byte is
-  // copied into shared memory ONCE, a tap is a row offset of the A descriptor, and the four taps
-  // accumulate into four N = 64 column blocks ([dy_hi | dy_lo]).  The two row halves (x_hi.dy and
-  // x_lo.dy) leave as two partial slices and are summed with the split-K partials.
+  // Both operands are fp16: X2 is bulk-copied from a1s as it is (one fp16 per value), dy2 is
+  // converted by the producers into an fp16 hi + lo pair concatenated along N (the gradient keeps
+  // its two terms: a single fp16 term left l1_b / l2_w at 1e-3 against the oracle).  Tap b is
+  // folded into M: a second bulk copy of the X2 image shifted by one row fills planes 8..15, so
+  // rows b*64 + ch of the accumulator are tap b; tap a is a row offset of the A descriptor and its
+  // own block of 64 accumulator columns.  One N = 64 MMA per tap a and 16 rows: 16 per stage
+  // (round 1: 32, with X2 as a hi/lo pair stacked along M).
   static constexpr int GW = 10, GROWS = 100, TROWS = 140;
-  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 8 * PLA;    // one part: 8 channel groups
-  static constexpr int PLB = 130 * 16, B_IMG = 4 * PLB;            // dy2z: 4 co groups
+  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 8 * PLA;    // one copy: 8 channel groups
+  static constexpr int PLB = 130 * 16, B_IMG = 4 * PLB;            // dy2: 4 co groups per part
   static constexpr int PROD_WARPS = 18, STAGES = 3, STAGE_BYTES = 2 * A_IMG + 2 * B_IMG, RES_BYTES = 0;
-  // accumulator columns: tap*64 + part*32 + co
-  static constexpr int ACC_COLS = 256, OUT_COLS = 128, LO_DELTA = 32, SEG = 32;
+  // accumulator columns: a*64 + part*32 + co
+  static constexpr int ACC_COLS = 128, OUT_COLS = 64, LO_DELTA = 32, SEG = 32;
   static __device__ __forceinline__ int acc_col(int c) { return (c >> 5) * 64 + (c & 31); }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
@@ -699,21 +705,21 @@ struct Conv2Wgrad : tc::PolicyBase {
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
                                                     uint8_t* st, int glane, int gsize, Prod& ps) {
     const int p0 = t.k_begin + s * 128;
-    uint8_t* b_hi = st + 2 * A_IMG, *b_lo = b_hi + B_IMG;
-    // A: X2 rows p0 .. p0+139 arrive by cp.async.bulk (bulk_stage); only the rows beyond the last
-    // sample need zeros here
-    a1s_zero_tail<TROWS, PLA, A_IMG, 8>(st, p0, g.num_samples, glane, gsize);
+    // A: X2 rows p0 .. p0+139 (and the copy shifted by one row) arrive by cp.async.bulk
+    // (bulk_stage); only the rows beyond the last sample need zeros here
+    a1s_zero_tail<TROWS, PLA, 16>(st, p0, g.num_samples, glane, gsize);
     // B: dy2 on the 10-wide grid, zero at y'=9 / x'=9 and outside [k_begin, k_end)
-    stream_pixels<GridDy2, 8, 128, PLB, 7, true>(b_hi, b_lo, g.dy2, p0, t.k_end, g.num_samples, glane,
-                                                 gsize, ps.acc);
+    uint8_t* b_hi = st + 2 * A_IMG;
+    stream_pixels<GridDy2, 8, 128, PLB, 7, true, true>(b_hi, b_hi + B_IMG, g.dy2, p0, t.k_end, g.num_samples,
+                                                       glane, gsize, ps.acc);
   }
-  // 16 lanes of the stage's 192 (every 12th) own one (part, kc) plane each
+  // 8 lanes of the stage's 192 (every 24th) own one plane each
   static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
                                                     int glane, int, uint64_t* full) {
-    if (glane % 12 != 0) return false;
-    const int p0 = t.k_begin + s * 128, owner = glane / 12;          // 0..15
-    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, PLA, A_IMG, false>(p0, g.num_samples));
-    a1s_bulk_issue<TROWS, PLA, A_IMG, false>(st, g.a1s, p0, g.num_samples, owner >> 3, owner & 7, full);
+    if (glane % 24 != 0) return false;
+    const int p0 = t.k_begin + s * 128, kc = glane / 24;             // 0..7
+    mbar_expect_tx(full, a1s_bulk_bytes<TROWS, true>(p0, g.num_samples));
+    a1s_bulk_issue<TROWS, PLA, true>(st, g.a1s, p0, g.num_samples, kc, full);
     return true;
   }
   static __device__ __forceinline__ void prod_end(const Args& g, const TileCoord& t, Prod& ps, int pw,
@@ -722,27 +728,26 @@ struct Conv2Wgrad : tc::PolicyBase {
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(64, true, true);       // [x_hi ; x_lo] . [dy_hi | dy_lo]
-    // a_img = st, b_hi = st + 2 * A_IMG (b_lo = b_hi + B_IMG); one descriptor derivation per stage
+    constexpr uint32_t idesc = tc::make_idesc_h(64, true, true);     // [x ; x shifted] . [dy_hi | dy_lo]
+    // one descriptor derivation per stage
     const uint64_t da0 = tc::make_sdesc(st, 128, PLA), db0 = tc::make_sdesc(st + 2 * A_IMG, 128, PLB);
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
+    for (int a = 0; a < 2; ++a) {
 #pragma unroll
       for (int k16 = 0; k16 < 8; ++k16) {
-        const uint64_t da = tc::sdesc_advance(da0, ((tap >> 1) * GW + (tap & 1) + k16 * 16) * 16);
+        const uint64_t da = tc::sdesc_advance(da0, (a * GW + k16 * 16) * 16);
         const uint64_t db = tc::sdesc_advance(db0, k16 * 256);
-        tc::umma_f16(d + tap * 64, da, db, idesc, (s | k16) != 0 ? 1u : 0u);
+        tc::umma_f16(d + a * 64, da, db, idesc, (s | k16) != 0 ? 1u : 0u);
       }
     }
   }
-  // row = part*64 + ch, ch = (i*2+j)*16 + cin ; segment tap (a,b) = 32 co of (kh = 2a+i, kw = 2b+j);
-  // part p of work item ks -> partial slice 2*ks + p
+  // row = b*64 + ch, ch = (i*2+j)*16 + cin ; segment a = 32 co of tap (kh = 2a+i, kw = 2b+j)
   static __device__ __forceinline__ float* row_ptr(const Args& g, const TileCoord& t, int row) {
-    const int part = row >> 6, ch = row & 63, ij = ch >> 4, cin = ch & 15;
-    return g.partials + ((size_t)t.ks * 2 + part) * 8192 + (((ij >> 1) * 4 + (ij & 1)) * 16 + cin) * 32;
+    const int b = row >> 6, ch = row & 63, ij = ch >> 4, cin = ch & 15;
+    return g.partials + (size_t)t.ks * 8192 + (((ij >> 1) * 4 + 2 * b + (ij & 1)) * 16 + cin) * 32;
   }
-  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int tap) {
-    return ((tap >> 1) * 8 + (tap & 1) * 2) * 16 * 32;
+  static __device__ __forceinline__ int64_t seg_offset(const Args&, const TileCoord&, int a) {
+    return a * 8 * 16 * 32;
   }
 };
 
@@ -920,7 +925,7 @@ extern "C" int arl_conv2_forward(const float* prepared, const float* a1, float* 
 
 extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads,
                                   void* workspace, int num_envs, int ring_slots, int first_slot,
-                                  int steps, void* stream) {
+                                  int steps, float grad_unscale, void* stream) {
   ARL_REQUIRE(ring && d_a1 && grads && workspace, "arl_conv1_backward: null pointer");
   ARL_REQUIRE(num_envs >= 0 && steps >= 0, "arl_conv1_backward: negative size");
   ARL_REQUIRE(ring_slots >= steps + 3 && first_slot >= 0 && first_slot < ring_slots,
@@ -945,12 +950,12 @@ extern "C" int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float*
   g.reverse = serpentine() ? 1 : 0;
   int rc = tc::launch<Conv1Wgrad>(g, g.items, st);
   if (rc) return rc;
-  return reduce_partials(g.partials, grads, g.items, 4096, st);                  // l1_w
+  return reduce_partials_scaled(g.partials, grads, g.items, 4096, grad_unscale, st);   // l1_w
 }
 
 extern "C" int arl_conv2_backward(const float* prepared, const float* a1, const float* d_a2,
                                   float* d_a1, float* grads, void* workspace, int64_t num_samples,
-                                  void* stream) {
+                                  float grad_unscale, void* stream) {
   const float* params = prepared;
   ARL_REQUIRE(params && a1 && d_a2 && d_a1 && grads && workspace,
               "arl_conv2_backward: null pointer");
@@ -972,20 +977,20 @@ extern "C" int arl_conv2_backward(const float* prepared, const float* a1, const 
   w.num_samples = (int)num_samples;
   w.items = split_rows(w.rows, num_sms(), &w.k_chunk);
   w.reverse = serpentine() ? 1 : 0;
-  w.bias_partials = (float*)workspace + (size_t)w.items * 2 * 8192;
+  w.bias_partials = (float*)workspace + (size_t)w.items * 8192;
   int rc = tc::launch<Conv2Wgrad>(w, w.items, st);
   if (rc) return rc;
-  rc = reduce_partials(w.partials, g2, 2 * w.items, 8192, st);       // two row halves (x_hi, x_lo) per item
+  rc = reduce_partials_scaled(w.partials, g2, w.items, 8192, grad_unscale, st);
   if (rc) return rc;
   // l2_b = column sums of d_a2, accumulated by the wgrad producers while they stream d_a2
-  rc = reduce_partials(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, st);
+  rc = reduce_partials_scaled(w.bias_partials, g2 + 8192, w.items * Conv2Wgrad::PROD_WARPS, 32, grad_unscale, st);
   if (rc) return rc;
   // dgrad; its epilogue also sums the columns of d_a1 = the conv1 bias gradient l1_b
-  float* db1 = (float*)workspace + (size_t)w.items * (2 * 8192 + Conv2Wgrad::PROD_WARPS * 32);
+  float* db1 = (float*)workspace + (size_t)w.items * (8192 + Conv2Wgrad::PROD_WARPS * 32);
   Conv2DgradArgs d{reinterpret_cast<const uint8_t*>(prepared) + kPrepW2D, reinterpret_cast<const uint8_t*>(a1),
                    d_a2, reinterpret_cast<uint8_t*>(d_a1), db1, num_samples * 121, (int)num_samples};
   const int items = (int)((d.rows + 127) / 128);
   rc = tc::launch<Conv2Dgrad>(d, items, st);
   if (rc) return rc;
-  return reduce_partials(db1, grads + 4096, (items < num_sms() ? items : num_sms()) * 8, 16, st);
+  return reduce_partials_scaled(db1, grads + 4096, (items < num_sms() ? items : num_sms()) * 8, 16, grad_unscale, st);
 }

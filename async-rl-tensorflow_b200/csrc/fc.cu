@@ -16,6 +16,8 @@ namespace arl {
 
 int reduce_partials(const float* partials, float* out, int num_partials, int n,
                     cudaStream_t stream);
+int reduce_partials_scaled(const float* partials, float* out, int num_partials, int n, float alpha,
+                           cudaStream_t stream);
 int heads_forward_sample(const float* params, int action_size, const float* h, float* logits, float* probs,
                          float* value, int32_t* actions, int64_t env_id_base, int64_t step,
                          const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st);
@@ -329,7 +331,7 @@ extern "C" int arl_fc_heads_forward(const float* params, const float* prepared, 
 
 extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,
                                const float* d_h, float* d_a2, float* grads, void* workspace,
-                               int64_t num_samples, void* stream) {
+                               int64_t num_samples, float grad_unscale, void* stream) {
   ARL_REQUIRE(prepared && a2 && d_h && d_a2 && grads && workspace, "arl_fc_backward: null pointer");
   ARL_REQUIRE(num_samples >= 0 && num_samples < (1LL << 31), "arl_fc_backward: bad num_samples");
   ARL_REQUIRE(aligned16(prepared) && aligned16(a2) && aligned16(d_h) && aligned16(d_a2) &&
@@ -362,7 +364,7 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   g.M = ARL_A2_ELEMS; g.N = ARL_FC; g.K = M; g.ldd = ARL_FC;
   int rc = run_gemm<FcWgrad>(g, 7, st);
   if (rc) return rc;
-  rc = reduce_partials(part, gW, g.k_splits, ARL_A2_ELEMS * ARL_FC, st);
+  rc = reduce_partials_scaled(part, gW, g.k_splits, ARL_A2_ELEMS * ARL_FC, grad_unscale, st);
   if (rc) return rc;
   // dgrad: d_a2 [M,2592] = d_h [M,256] . W^T, masked by a2 > 0
   g.A = dhs; g.B = ws; g.mask = a2s;
@@ -374,5 +376,5 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   const int grid = (int)((num_samples + 63) / 64 < num_sms() ? (num_samples + 63) / 64 : num_sms());
   colsum_split256_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_h, part, M);
   ARL_LAUNCH_CHECK("colsum_split256_kernel");
-  return reduce_partials(part, gb, grid, ARL_FC, st);
+  return reduce_partials_scaled(part, gb, grid, ARL_FC, grad_unscale, st);
 }

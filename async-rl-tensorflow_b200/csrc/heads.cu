@@ -280,7 +280,7 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
                  const float* __restrict__ h, const float* __restrict__ dlogits,
                  const float* __restrict__ dvalue, uint8_t* __restrict__ dhs,
                  uint8_t* __restrict__ dhsT, float* __restrict__ partials, int64_t num_samples,
-                 int64_t per, int A) {
+                 int64_t per, int A, float tensor_scale) {
   __shared__ float dzs[kHbChunk][JMAX];
   __shared__ float dt[kHbSub][257];
   const int J = A + 1;
@@ -324,7 +324,7 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
               acc[j] = fmaf(hv, g, acc[j]);
             }
           }
-          dt[s][k] = hv > 0.f ? d : 0.f;
+          dt[s][k] = hv > 0.f ? d * tensor_scale : 0.f;       // d_h leaves scaled (arl_backward)
         }
       }
       __syncthreads();
@@ -579,9 +579,11 @@ extern "C" int arl_observe_store_advance(const float* reward, const uint8_t* ter
 
 extern "C" int arl_heads_backward(const float* params, int action_size, const float* h,
                                   const float* dlogits, const float* dvalue, float* d_h,
-                                  float* grads, void* workspace, int64_t num_samples, void* stream) {
+                                  float* grads, void* workspace, int64_t num_samples,
+                                  float tensor_scale, void* stream) {
   ARL_REQUIRE(params && h && dlogits && dvalue && d_h && grads && workspace,
               "arl_heads_backward: null pointer");
+  ARL_REQUIRE(tensor_scale > 0.f, "arl_heads_backward: tensor_scale must be > 0");
   ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
               "arl_heads_backward: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
   ARL_REQUIRE(num_samples >= 0, "arl_heads_backward: negative size");
@@ -605,13 +607,13 @@ extern "C" int arl_heads_backward(const float* params, int action_size, const fl
   uint8_t* dhsT = dhs + (size_t)num_samples * 256 * sizeof(float);
   if (J <= 8)
     heads_bwd_kernel<8><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
-                                             dvalue, dhs, dhsT, part, num_samples, per, A);
+                                             dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
   else if (J <= 20)
     heads_bwd_kernel<20><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h,
-                                              dlogits, dvalue, dhs, dhsT, part, num_samples, per, A);
+                                              dlogits, dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
   else
     heads_bwd_kernel<ARL_MAX_ACTIONS + 1><<<grid, 256, 0, st>>>(
-        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, dhs, dhsT, part, num_samples, per, A);
+        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
   ARL_LAUNCH_CHECK("heads_bwd_kernel");
   return reduce_partials(part, g, grid, 256 * J + J, st);
 }

@@ -6,7 +6,7 @@ namespace arl {
 
 // many elements, few partials (fc wgrad: 663 552 x 7): one thread per element
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, float* __restrict__ out,
-                                       int num_partials, int n) {
+                                       int num_partials, int n, float alpha) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -18,7 +18,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, float
     a3 += partials[(size_t)(p + 3) * n + i];
   }
   for (; p < num_partials; ++p) a0 += partials[(size_t)p * n + i];
-  out[i] = (a0 + a1) + (a2 + a3);
+  out[i] = ((a0 + a1) + (a2 + a3)) * alpha;
 }
 
 // few elements, many partials (conv wgrads: 4096 / 8192 x 148; conv bias grads: 16 / 32 x 2368):
@@ -26,7 +26,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, float
 // p = s, s+32, ...) and combined by a fixed-order tree, so the result does not depend on timing
 __global__ void __launch_bounds__(1024)
 reduce_partials_wide_kernel(const float* __restrict__ partials, float* __restrict__ out,
-                            int num_partials, int n) {
+                            int num_partials, int n, float alpha) {
   __shared__ float red[32][33];
   const int e = threadIdx.x & 31, s = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
@@ -51,17 +51,24 @@ reduce_partials_wide_kernel(const float* __restrict__ partials, float* __restric
     if (s < h) red[s][e] += red[s + h][e];
     __syncthreads();
   }
-  if (s == 0 && i < n) out[i] = red[0][e];
+  if (s == 0 && i < n) out[i] = red[0][e] * alpha;
 }
 
-int reduce_partials(const float* partials, float* out, int num_partials, int n,
-                    cudaStream_t stream) {
+// out = alpha * sum of the partials (alpha = 1 / tensor_scale: the gradients handed from layer to
+// layer carry a power-of-two factor so that they sit in the middle of the fp16 range, see
+// arl_backward; a power of two scales exactly)
+int reduce_partials_scaled(const float* partials, float* out, int num_partials, int n, float alpha,
+                           cudaStream_t stream) {
   if (n >= 65536 || num_partials < 16)
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, num_partials, n);
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, num_partials, n, alpha);
   else
-    reduce_partials_wide_kernel<<<(n + 31) / 32, 1024, 0, stream>>>(partials, out, num_partials, n);
+    reduce_partials_wide_kernel<<<(n + 31) / 32, 1024, 0, stream>>>(partials, out, num_partials, n, alpha);
   ARL_LAUNCH_CHECK("reduce_partials_kernel");
   return ARL_OK;
+}
+int reduce_partials(const float* partials, float* out, int num_partials, int n,
+                    cudaStream_t stream) {
+  return reduce_partials_scaled(partials, out, num_partials, n, 1.0f, stream);
 }
 
 int conv_init() { return ARL_OK; }

@@ -18,18 +18,18 @@ from .. import _cabi
 
 PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l4_w", "l4_b", "p_w", "p_b", "q_w", "q_b")
 A1_ELEMS, A2_ELEMS, FC, DA1_ELEMS = 6400, 2592, 256, 7056
+A1_STORE = 3200                                               # float32 words of storage per sample of a1 (fp16)
 
 
-def decode_a1(raw):
-    """conv1's output lives in HBM as split bf16 in space-to-depth blocks (csrc/convs_tc.cu "a1s":
-    [n][hi|lo][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 ch], pixel (y,x) = (2yp+i, 2xp+j)) -- the
-    layout the conv2 tensor-core kernels consume without conversion.  ``raw`` is the float32
-    [N,20,20,16]-shaped storage the C-ABI fills; returns the float32 [N,20,20,16] activations
-    (network.py:47-48 l1)."""
-    n = raw.shape[0]
-    b = raw.reshape(n, 6400).view(torch.bfloat16).reshape(n, 2, 2, 2, 2, 10, 10, 8)
-    v = b[:, 0].float() + b[:, 1].float()                     # [n, i, j, chalf, yp, xp, 8]
-    return v.permute(0, 4, 1, 5, 2, 3, 6).reshape(n, 20, 20, 16)
+def decode_a1(raw, n=None):
+    """conv1's output lives in HBM as fp16 in space-to-depth blocks (csrc/convs_tc.cu "a1s":
+    [n][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 ch], pixel (y,x) = (2yp+i, 2xp+j), 12 800 bytes
+    per sample) -- the layout the conv2 tensor-core kernels consume without conversion.  ``raw`` is
+    the storage the C-ABI filled (any shape whose first dimension is the sample count, or pass
+    ``n``); returns the float32 [N,20,20,16] activations (network.py:47-48 l1)."""
+    n = raw.shape[0] if n is None else n
+    b = raw.reshape(-1)[:n * A1_STORE].view(torch.float16).reshape(n, 2, 2, 2, 10, 10, 8)
+    return b.float().permute(0, 4, 1, 5, 2, 3, 6).reshape(n, 20, 20, 16)   # [n, yp, i, xp, j, chalf, 8]
 
 
 def decode_split(raw, rows, cols):
@@ -130,7 +130,7 @@ class Network(object):
         N = B * T
         f32 = dict(device=dev, dtype=torch.float32)
         # rollout activations, t-major: sample n = t*B + b
-        self.l1 = torch.empty(N, 20, 20, 16, **f32)           # network.py:47-48, stored split-bf16 blocked: see a1()
+        self.l1 = torch.empty(N, A1_STORE, **f32)             # network.py:47-48, stored as blocked fp16: see a1()
         self.l2 = torch.empty(N, A2_ELEMS, **f32)             # network.py:49-50 (flattened NHWC), one split block per step: see a2()
         self.l4 = torch.empty(N, FC, **f32)                   # network.py:51-52
         self.policy_logits = torch.empty(N, A, **f32)         # network.py:62
@@ -139,7 +139,7 @@ class Network(object):
         self.sampled_action = torch.zeros(N, dtype=torch.int32, device=dev)   # network.py:72
         self.R = torch.empty(N, **f32)                        # network.py:82
         # bootstrap-state scratch (not kept for backward)
-        self._b = dict(l1=torch.empty(B, 20, 20, 16, **f32), l2=torch.empty(B, A2_ELEMS, **f32),
+        self._b = dict(l1=torch.empty(B, A1_STORE, **f32), l2=torch.empty(B, A2_ELEMS, **f32),
                        l4=torch.empty(B, FC, **f32), logits=torch.empty(B, A, **f32),
                        probs=torch.empty(B, A, **f32), value=torch.empty(B, **f32))
         # backward scratch
@@ -154,6 +154,7 @@ class Network(object):
         self.loss_sums = torch.zeros(3, **f32)                # sum policy / value loss, entropy
         self.grad_norms = torch.zeros(len(PARAM_NAMES), **f32)
         self.events = {}
+        self.tensor_scale = 1.0                               # set by compute_gradients
 
     # -- parameters -----------------------------------------------------------------------
     def set_weights(self, weights):
@@ -259,17 +260,34 @@ class Network(object):
         B = self.num_envs
         return torch.cat([decode_split(self.l2[self._rows(t)], B, A2_ELEMS) for t in range(self.t_max)])
 
+    @staticmethod
+    def pick_tensor_scale(grad_scale):
+        """The power of two the layer-to-layer gradients are stored multiplied by
+        (include/asyncrl_b200.h, arl_backward): 64 / grad_scale rounded to a power of two, i.e. the
+        loss gradient as if it were multiplied by ~64 instead of divided by the env count."""
+        import math
+        e = int(round(math.log2(64.0 / max(float(grad_scale), 1e-30))))
+        return float(2.0 ** max(-20, min(40, e)))
+
     def d_h(self):
         """Gradient w.r.t. the fc256 output of the last backward as float32 [N,256]."""
         N = self.num_envs * self.t_max
-        return decode_split(self.d_l4[:N], N, FC)
+        return decode_split(self.d_l4[:N], N, FC) / self.tensor_scale
+
+    def d_a2(self):
+        """Gradient w.r.t. the conv2 output (pre-relu) of the last backward, float32 [N,2592]."""
+        return self.d_l2 / self.tensor_scale
+
+    def d_a1(self):
+        """Gradient w.r.t. the conv1 output (pre-relu) of the last backward, float32 [N,20,20,16]."""
+        return decode_da1(self.d_l1, self.num_envs * self.t_max) / self.tensor_scale
 
     def d_h_transposed(self):
         """The same gradient decoded from its second, transposed copy (what fc wgrad reads)."""
         N = self.num_envs * self.t_max
         n8 = (N + 7) // 8 * 8
         b = self.d_l4[N:].reshape(-1).view(torch.bfloat16).reshape(2, n8 // 8, FC, 8)
-        return (b[0].float() + b[1].float()).permute(0, 2, 1).reshape(n8, FC)[:N]
+        return (b[0].float() + b[1].float()).permute(0, 2, 1).reshape(n8, FC)[:N] / self.tensor_scale
 
     def sample(self, t, step, seed, env_id_base=0):
         """network.py:72-73 sampled_action for rollout slot t."""
@@ -344,24 +362,25 @@ class Network(object):
         P = _cabi.ptr
         if self._fc_w_stale() if refresh is None else refresh:   # (a forward normally did this already)
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
+        S = self.tensor_scale = self.pick_tensor_scale(grad_scale)
         if self.timed is None:
             _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                        history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2),
                        P(self.l4), P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
-                       P(self.d_l1), P(self.grads), P(self.workspace), 1 if allreduce else 0, st)
+                       P(self.d_l1), P(self.grads), P(self.workspace), S, 1 if allreduce else 0, st)
             return self.grads
         N = T * B
         self._timed_call("arl_heads_backward", P(self.params), A, P(self.l4), P(self.d_logits),
-                         P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, st)
+                         P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, S, st)
         self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), B, P(self.d_l4), P(self.d_l2),
-                         P(self.grads), P(self.workspace), N, st)
+                         P(self.grads), P(self.workspace), N, 1.0 / S, st)
         if allreduce:                                          # same bucket order as arl_backward
             lo = self.offsets[4]
             _cabi.call("arl_allreduce_begin", P(self.grads), lo, self.offsets[-1] - lo, st)
         self._timed_call("arl_conv2_backward", P(self.fc_w), P(self.l1), P(self.d_l2),
-                         P(self.d_l1), P(self.grads), P(self.workspace), N, st)
+                         P(self.d_l1), P(self.grads), P(self.workspace), N, 1.0 / S, st)
         self._timed_call("arl_conv1_backward", P(history.ring), P(self.d_l1), P(self.grads),
-                         P(self.workspace), B, history.ring_slots, history.first_slot(T), T, st)
+                         P(self.workspace), B, history.ring_slots, history.first_slot(T), T, 1.0 / S, st)
         if allreduce:
             _cabi.call("arl_allreduce_begin", P(self.grads), 0, self.offsets[4], st)
             _cabi.call("arl_allreduce_end", st)
@@ -408,10 +427,11 @@ class Network(object):
         self.d_value.zero_()                                   # the value head is unused
         if self._fc_w_stale():
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
+        S = self.tensor_scale = self.pick_tensor_scale(grad_scale)
         _cabi.call("arl_backward", P(self.params), P(self.fc_w), A, P(history.ring), B,
                    history.ring_slots, history.first_slot(T), T, P(self.l1), P(self.l2), P(self.l4),
                    P(self.d_logits), P(self.d_value), P(self.d_l4), P(self.d_l2),
-                   P(self.d_l1), P(self.grads), P(self.workspace), 1 if allreduce else 0, st)
+                   P(self.d_l1), P(self.grads), P(self.workspace), S, 1 if allreduce else 0, st)
         return self.grads
 
     @property

@@ -251,24 +251,32 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
  * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);
  * prepared must hold arl_prepare_weights of the parameters the forward used. */
 ARL_API int64_t arl_backward_workspace_bytes(int action_size);
+/* tensor_scale / grad_unscale: the gradients handed from layer to layer (d_h, d_a2, d_a1) are
+ * stored multiplied by tensor_scale, a power of two chosen by the host so that they sit in the
+ * middle of the range of the 16-bit operand formats whatever the batch size is (the loss gradient
+ * is divided by the number of envs, agent.py's mean); arl_heads_backward applies it when it writes
+ * d_h, the three weight-gradient entries divide it out again (grad_unscale = 1 / tensor_scale:
+ * exact), so `grads` always holds the true gradient.  arl_backward takes tensor_scale. */
 ARL_API int arl_heads_backward(const float* params, int action_size, const float* h,
                        const float* dlogits, const float* dvalue, float* d_h, float* grads,
-                       void* workspace, int64_t num_samples, void* stream);
+                       void* workspace, int64_t num_samples, float tensor_scale, void* stream);
 ARL_API int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,
                     const float* d_h, float* d_a2, float* grads, void* workspace,
-                    int64_t num_samples, void* stream);
+                    int64_t num_samples, float grad_unscale, void* stream);
 /* l2_w, l2_b, d_a1 and l1_b (the column sums of d_a1). */
 ARL_API int arl_conv2_backward(const float* prepared, const float* a1, const float* d_a2, float* d_a1,
-                       float* grads, void* workspace, int64_t num_samples, void* stream);
+                       float* grads, void* workspace, int64_t num_samples, float grad_unscale,
+                       void* stream);
 /* l1_w only (l1_b comes from arl_conv2_backward). */
 ARL_API int arl_conv1_backward(const uint8_t* ring, const float* d_a1, float* grads, void* workspace,
-                       int num_envs, int ring_slots, int first_slot, int steps, void* stream);
+                       int num_envs, int ring_slots, int first_slot, int steps, float grad_unscale,
+                       void* stream);
 ARL_API int arl_backward(const float* params, const float* prepared, int action_size,
                  const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                  const float* a1, const float* a2,
                  const float* h, const float* dlogits, const float* dvalue, float* d_h,
-                 float* d_a2, float* d_a1, float* grads, void* workspace, int allreduce,
-                 void* stream);
+                 float* d_a2, float* d_a1, float* grads, void* workspace, float tensor_scale,
+                 int allreduce, void* stream);
 
 /* ---- the 'nature' trunk (network.py:30-42): conv32 8x8 s4 -> conv64 4x4 s2 -> conv64 3x3 s1 ->
  * fc512 -> heads.  A second shape set with plain float32 NHWC tensors on both sides:

@@ -200,20 +200,22 @@ def test_backward_gradients_vs_oracle(pkg, cuda, A, B, T):
     # the gradients handed from layer to layer, decoded from their device layouts
     N = T * B
     assert bool((net.d_h() == net.d_h_transposed()).all())     # the two device copies of d_h agree
-    ierrs = dict(d_h=rel_err(net.d_h().cpu(), aux["d_h"]), d_a2=rel_err(net.d_l2.cpu(), aux["d_a2"]),
-                 d_a1=rel_err(pkg.network.decode_da1(net.d_l1, N).cpu(), aux["d_a1"]))
+    ierrs = dict(d_h=rel_err(net.d_h().cpu(), aux["d_h"]), d_a2=rel_err(net.d_a2().cpu(), aux["d_a2"]),
+                 d_a1=rel_err(net.d_a1().cpu(), aux["d_a1"]))
     print("layer-gradient rel-err", ierrs)
     assert max(ierrs.values()) <= REL_TOL, ierrs
     raw = net.d_l1.reshape(-1)[:N * 7056].view(torch.bfloat16).reshape(2, 2, N, 21, 21, 8)
     assert float(raw[:, :, :, 20].abs().max()) == 0.0 and float(raw[:, :, :, :, 20].abs().max()) == 0.0
-    # (2) free oracle: a pre-activation within rounding distance (~1e-5 relative, bf16x3 operands)
-    # of 0 may flip one relu and with it one gradient column; with only T*B samples in the sums
-    # one flip is visible, so this comparison is reported in the 2-norm and gated at 1e-2
+    # (2) free oracle (REPORTED; loosely gated): a pre-activation within rounding distance of 0 --
+    # ~2e-4 relative now that a1 is stored as fp16 -- flips one relu and with it one gradient
+    # column; with only T*B samples in the sums a handful of flips is visible in the 2-norm
+    # (tests/precision_study.py: 250 flips in 11.8 M relus, 1.3e-2 on l2_w, against 4.4e-4 with the
+    # pattern forced).  The gated comparison is (1); the 100-update free trajectory is its own test.
     grads_free, _ = a3c.gradients(params, stacks[:T].reshape(T * B, 84, 84, 4), acts.reshape(-1),
                                   R.reshape(-1), 0.01, B)
     nerrs = {k: norm_err(net.g[k].cpu(), grads_free[k]) for k in a3c.PARAM_NAMES}
     print("grad 2-norm rel-err (free relu)", nerrs)
-    assert max(nerrs.values()) <= 1e-2, nerrs
+    assert max(nerrs.values()) <= 5e-2, nerrs
     assert rel_err(net.policy_logits.cpu(), aux["logits"]) <= REL_TOL
     assert rel_err(net.value.cpu(), aux["value"]) <= REL_TOL
 
@@ -246,7 +248,7 @@ def test_backward_single_sample_and_zero_samples(pkg, cuda):
     P = pkg._cabi.ptr
     assert lib.arl_backward(P(net.params), P(net.fc_w), A, P(hist.ring), 0, hist.ring_slots, 0, 1, P(net.l1),
                             P(net.l2), P(net.l4), P(net.d_logits), P(net.d_value), P(net.d_l4),
-                            P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), 0, st) == 0
+                            P(net.d_l2), P(net.d_l1), P(net.grads), P(net.workspace), 1.0, 0, st) == 0
     torch.cuda.synchronize()
     assert float(net.grads.abs().max()) == 0.0
 
@@ -381,7 +383,9 @@ def test_rmsprop_trajectory_100_updates_free_oracle(pkg, cuda):
     print("100-update FREE trajectory", {k: v for k, v in worst.items() if k != "per_tensor"})
     assert worst["flat_2norm"] <= REL_TOL, worst
     assert max(v[0] for v in worst["per_tensor"].values()) <= REL_TOL, worst
-    assert worst["flips"] <= 1e-5 * worst["relus"], worst         # a handful in ~1.2e9
+    # a1 is stored as fp16 (2^-12 per element): a pre-activation within ~2e-4 of 0 can land on the
+    # other side -- measured 3.2e-5 of the 1.2e9 relus (with the bf16 hi+lo storage of round 1: 5e-7)
+    assert worst["flips"] <= 1e-4 * worst["relus"], worst
     assert worst["disp_2norm"] <= 2e-2, worst
 
 
