@@ -160,44 +160,47 @@ struct RingGeo {
   const uint8_t* ring;
   int num_envs, ring_slots, first_slot;
 };
-template <int ROWS, int PL, int U, bool SHIFTED>
-__device__ __forceinline__ void stream_x1(uint8_t* img, const RingGeo& g, int xr0, int num_samples,
-                                          int glane, int gsize) {
+// split in two so that the loads of the NEXT stage can be in flight while the producer waits for
+// its shared-memory slot (PolicyBase::PREFETCH): U * gsize >= ROWS * 4, one round
+template <int ROWS, int U>
+__device__ __forceinline__ void x1_request(uint4 (&w)[U], const RingGeo& g, int xr0, int num_samples,
+                                           int glane, int gsize) {
   constexpr int GROWS = 441, TOTAL = ROWS * 4;
   const int n0 = xr0 / GROWS, q0 = xr0 - n0 * GROWS;
   const int tt0 = n0 / g.num_envs, b0 = n0 - tt0 * g.num_envs;
-  for (int u0 = glane; u0 < TOTAL; u0 += U * gsize) {
-    uint4 w[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int un = u0 + u * gsize;
-      const int c = un / ROWS, r = un - c * ROWS;
-      int q = q0 + r, n = n0, tt = tt0, b = b0;
-      if (q >= GROWS) {                                      // ROWS < GROWS: at most one wrap
-        q -= GROWS; ++n; ++b;
-        if (b == g.num_envs) { b = 0; ++tt; }
-      }
-      w[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (un < TOTAL && n < num_samples) {
-        int slot = g.first_slot + tt + c;
-        slot -= slot >= g.ring_slots ? g.ring_slots : 0;
-        slot -= slot >= g.ring_slots ? g.ring_slots : 0;
-        w[u] = __ldg(reinterpret_cast<const uint4*>(g.ring + ((size_t)b * g.ring_slots + slot) * kPlane) + q);
-      }
+  for (int u = 0; u < U; ++u) {
+    const int un = glane + u * gsize;
+    const int c = un / ROWS, r = un - c * ROWS;
+    int q = q0 + r, n = n0, tt = tt0, b = b0;
+    if (q >= GROWS) {                                      // ROWS < GROWS: at most one wrap
+      q -= GROWS; ++n; ++b;
+      if (b == g.num_envs) { b = 0; ++tt; }
     }
+    w[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (un < TOTAL && n < num_samples) {
+      int slot = g.first_slot + tt + c;
+      slot -= slot >= g.ring_slots ? g.ring_slots : 0;
+      slot -= slot >= g.ring_slots ? g.ring_slots : 0;
+      w[u] = __ldg(reinterpret_cast<const uint4*>(g.ring + ((size_t)b * g.ring_slots + slot) * kPlane) + q);
+    }
+  }
+}
+template <int ROWS, int PL, int U, bool SHIFTED>
+__device__ __forceinline__ void x1_store(uint8_t* img, const uint4 (&w)[U], int glane, int gsize) {
+  constexpr int TOTAL = ROWS * 4;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int un = u0 + u * gsize;
-      if (un >= TOTAL) break;
-      const int c = un / ROWS, r = un - c * ROWS;
-      const uint4 lo2 = tc::bytes8_to_bf16(w[u].x, w[u].y), hi2 = tc::bytes8_to_bf16(w[u].z, w[u].w);
-      uint8_t* d = img + (2 * c) * PL + r * 16;
-      *reinterpret_cast<uint4*>(d) = lo2;
-      *reinterpret_cast<uint4*>(d + PL) = hi2;
-      if (SHIFTED && r > 0) {
-        *reinterpret_cast<uint4*>(d + 8 * PL - 16) = lo2;
-        *reinterpret_cast<uint4*>(d + 9 * PL - 16) = hi2;
-      }
+  for (int u = 0; u < U; ++u) {
+    const int un = glane + u * gsize;
+    if (un >= TOTAL) break;
+    const int c = un / ROWS, r = un - c * ROWS;
+    const uint4 lo2 = tc::bytes8_to_bf16(w[u].x, w[u].y), hi2 = tc::bytes8_to_bf16(w[u].z, w[u].w);
+    uint8_t* d = img + (2 * c) * PL + r * 16;
+    *reinterpret_cast<uint4*>(d) = lo2;
+    *reinterpret_cast<uint4*>(d + PL) = hi2;
+    if (SHIFTED && r > 0) {
+      *reinterpret_cast<uint4*>(d + 8 * PL - 16) = lo2;
+      *reinterpret_cast<uint4*>(d + 9 * PL - 16) = hi2;
     }
   }
 }
@@ -782,11 +785,21 @@ struct Conv1Wgrad : tc::PolicyBase {
     return (t.k_end - t.k_begin + 127) / 128;
   }
   static __device__ __forceinline__ void load_resident(const Args&, uint8_t*, int, int) {}
+  // the u8 ring rows of the NEXT stage are requested (5 x 16 B per lane, held in registers) before
+  // the producer waits for its slot: the ncu capture of round 1 showed producers 24 % of their time
+  // waiting for a free stage and then another 13 % on the first use of these loads
+  static constexpr bool PREFETCH = true;
+  static constexpr int XU = 5;                                      // 16 warps / 4 stages = 128 lanes x 5 >= 129 x 4
+  struct Prod { uint4 w[XU]; };
+  static __device__ __forceinline__ void prefetch_stage(const Args& g, const TileCoord& t, int s, int glane,
+                                                        int gsize, Prod& ps) {
+    x1_request<TROWS, XU>(ps.w, g.geo, t.k_begin + s * 128, g.num_samples, glane, gsize);
+  }
   static __device__ __forceinline__ void load_stage(const Args& g, const TileCoord& t, int s,
-                                                    uint8_t* st, int glane, int gsize, Prod&) {
+                                                    uint8_t* st, int glane, int gsize, Prod& ps) {
     const int p0 = t.k_begin + s * 128;
     // A: X rows p0 .. p0+128 (exact in bf16: one image); planes 8..15 = shifted copy (tap b = 1)
-    stream_x1<TROWS, PLA, 5, true>(st, g.geo, p0, g.num_samples, glane, gsize);
+    x1_store<TROWS, PLA, XU, true>(st, ps.w, glane, gsize);
     // B: image row r of planes 0..3 = dy1 row p0 + r, of planes 4..7 = dy1 row p0 + r - 21; rows
     // with p0 + r >= k_end (the next work item's) and rows before the first sample are zero
     const int valid = t.k_end - p0, lead = p0 < GW ? GW - p0 : 0;

@@ -405,9 +405,16 @@ struct PolicyBase {
   static constexpr bool HAS_AUX = false;       // finish() needs an operand from HBM (bias, relu mask)
   static constexpr bool AUX_ROW_INVARIANT = true;   // ... that depends on the column only (bias)
   struct Prod {};
-  static __device__ __forceinline__ void prod_begin(Prod&) {}
-  template <class Args>
-  static __device__ __forceinline__ void prod_end(const Args&, const TileCoord&, Prod&, int, int) {}
+  template <class Pr>
+  static __device__ __forceinline__ void prod_begin(Pr&) {}
+  // PREFETCH: the producer requests the global data of its NEXT stage (into registers held in
+  // Prod) right after it has handed the current one over, i.e. BEFORE it waits for that stage's
+  // shared-memory slot to be free: the load latency runs behind the wait instead of after it
+  static constexpr bool PREFETCH = false;
+  template <class Args, class Pr>
+  static __device__ __forceinline__ void prefetch_stage(const Args&, const TileCoord&, int, int, int, Pr&) {}
+  template <class Args, class Pr>
+  static __device__ __forceinline__ void prod_end(const Args&, const TileCoord&, Pr&, int, int) {}
   template <class Args>
   static __device__ __forceinline__ bool seg_valid(const Args&, const TileCoord&, int) { return true; }
   template <class Args>
@@ -525,12 +532,16 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
       const int ns = P::num_stages(g, tc);
       typename P::Prod ps;
       P::prod_begin(ps);
+      bool first = true;
       for (int s = 0; s < ns; ++s, ++i) {
         if (i % STAGES != pg) continue;
+        if (P::PREFETCH && first) P::prefetch_stage(g, tc, s, glane, 32 * WPS, ps);
+        first = false;
         mbar_wait_backoff<128>(&empty[pg], ((i / STAGES) & 1) ^ 1);
         P::load_stage(g, tc, s, st, glane, 32 * WPS, ps);
         fence_proxy_async_smem();        // generic-proxy stores -> visible to the MMA (async proxy)
         if (!P::bulk_stage(g, tc, s, st, glane, 32 * WPS, &full[pg])) mbar_arrive(&full[pg]);
+        if (P::PREFETCH && s + STAGES < ns) P::prefetch_stage(g, tc, s + STAGES, glane, 32 * WPS, ps);
       }
       P::prod_end(g, tc, ps, pw, lane);
     }
