@@ -63,6 +63,9 @@ SIGNATURES = {
                             c_vp, c_vp, c_i64, c_vp],
     "arl_clip_rmsprop_layout": [c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_int, c_f32, c_vp, c_i64,
                                 ctypes.c_double, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
+    "arl_comm_enable_p2p": [c_i64],
+    "arl_exchange_clip_rmsprop": [c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_int, c_f32, c_vp, c_i64,
+                                  ctypes.c_double, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp],
     "arl_comm_unique_id": [c_vp],
     "arl_comm_init": [c_vp, c_int, c_int],
     "arl_comm_destroy": [],
@@ -79,6 +82,8 @@ OTHER = {
     "arl_launch_count": ([c_int], c_i64),
     "arl_nature_workspace_bytes": ([c_int], c_i64),
     "arl_comm_size": ([], c_int),
+    "arl_comm_p2p_enabled": ([], c_int),
+    "arl_comm_p2p_error": ([], c_int),
     "arl_comm_nccl_version": ([], c_int),
 }
 EXPORTS = tuple(SIGNATURES) + tuple(OTHER)

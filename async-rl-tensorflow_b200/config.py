@@ -48,7 +48,8 @@ class AgentConfig(object):
     cuda_graphs = True                   # capture predict / observe(+update) as CUDA graphs (a3c mode)
     max_graphs = 1024                    # cap of the graph cache; beyond it the loop runs eagerly
     DQN_type = 'nips'                    # network.py:30-55 trunk: 'nips' (agent.py:226-252) | 'nature'
-    collective = 'library'               # gradient all-reduce: 'library' (arl_comm_*, NCCL in the .so) | 'torch'
+    collective = 'p2p'                   # gradient exchange: 'p2p' (NVLink peer memory, fused into the update) |
+                                         # 'library' (arl_allreduce_grads: NCCL inside the .so) | 'torch'
 
 
 class EnvironmentConfig(object):

@@ -21,6 +21,8 @@ typedef int (*CommDestroyFn)(NcclComm);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
 typedef int (*GetVersionFn)(int*);
+typedef int (*AllGatherFn)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
+constexpr int kNcclInt8 = 0;
 constexpr int kNcclFloat32 = 7, kNcclSum = 0;
 
 struct Nccl {
@@ -31,6 +33,7 @@ struct Nccl {
   AllReduceFn all_reduce = nullptr;
   GetErrorStringFn error_string = nullptr;
   GetVersionFn get_version = nullptr;
+  AllGatherFn all_gather = nullptr;
 };
 Nccl g_nccl;
 
@@ -42,6 +45,15 @@ struct Comm {
   bool pending = false;
 };
 Comm g_comm;
+
+// peer-memory exchange (arl_comm_enable_p2p)
+struct P2P {
+  bool on = false;
+  void* local = nullptr;                 // this rank's cudaMalloc'd buffer
+  void* opened[kMaxRanks] = {nullptr};   // peers' buffers as mapped here (cudaIpcOpenMemHandle)
+  P2PView view;
+};
+P2P g_p2p;
 
 int load_nccl() {
   if (g_nccl.handle) return ARL_OK;
@@ -63,6 +75,7 @@ int load_nccl() {
   n.all_reduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
   n.error_string = (GetErrorStringFn)dlsym(h, "ncclGetErrorString");
   n.get_version = (GetVersionFn)dlsym(h, "ncclGetVersion");
+  n.all_gather = (AllGatherFn)dlsym(h, "ncclAllGather");
   if (!n.get_unique_id || !n.comm_init_rank || !n.comm_destroy || !n.all_reduce || !n.error_string) {
     set_error("arl_comm: libnccl.so.2 lacks an expected symbol");
     return ARL_ERR_UNSUPPORTED;
@@ -82,9 +95,88 @@ int nccl_fail(int rc, const char* what) {
   } while (0)
 
 }  // namespace
+
+const P2PView* p2p_view() { return g_p2p.on ? &g_p2p.view : nullptr; }
+
 }  // namespace arl
 
 using namespace arl;
+
+// One-shot all-reduce over NVLink peer memory, fused into the update (update.cu): every rank
+// publishes its gradient into one of two slots of its own IPC-shared buffer and raises a flag word
+// in every peer's memory; the norm pass of the update then READS all ranks' slots (plain loads over
+// NVLink), adds them in rank order -- bit-identical on every rank -- writes the summed gradient
+// locally and accumulates the per-tensor sums of squares in the same pass.  No NCCL kernel, no
+// extra launch, nothing for the persistent backward kernels to wait behind.  Two slots alternate so
+// that no second barrier is needed: a rank overwrites slot p two cycles later, after its own
+// reduction of the cycle in between has seen every peer's flag for that cycle.
+extern "C" int arl_comm_enable_p2p(int64_t count) {
+  ARL_REQUIRE(g_comm.comm, "arl_comm_enable_p2p: arl_comm_init has not been called");
+  ARL_REQUIRE(count > 0, "arl_comm_enable_p2p: count must be > 0");
+  ARL_REQUIRE(g_comm.nranks <= kMaxRanks, "arl_comm_enable_p2p: at most %d ranks", kMaxRanks);
+  ARL_REQUIRE(g_nccl.all_gather, "arl_comm_enable_p2p: libnccl lacks ncclAllGather");
+  if (g_p2p.on) {
+    ARL_REQUIRE(g_p2p.view.count == count, "arl_comm_enable_p2p: already enabled for %lld floats",
+                (long long)g_p2p.view.count);
+    return ARL_OK;
+  }
+  const int n = g_comm.nranks, me = g_comm.rank;
+  const size_t slot_bytes = ((size_t)count * sizeof(float) + 255) / 256 * 256;
+  const size_t ctl_off = 2 * slot_bytes, bytes = ctl_off + 4096;
+  ARL_CUDA(cudaMalloc(&g_p2p.local, bytes));
+  ARL_CUDA(cudaMemset(g_p2p.local, 0, bytes));
+  // exchange the IPC handles through the communicator that already exists
+  cudaIpcMemHandle_t mine;
+  ARL_CUDA(cudaIpcGetMemHandle(&mine, g_p2p.local));
+  void* stage = nullptr;
+  ARL_CUDA(cudaMalloc(&stage, (size_t)(n + 1) * sizeof(mine)));
+  char* all_dev = (char*)stage + sizeof(mine);
+  ARL_CUDA(cudaMemcpy(stage, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  ARL_NCCL(g_nccl.all_gather(stage, all_dev, sizeof(mine), kNcclInt8, g_comm.comm, g_comm.side));
+  ARL_CUDA(cudaStreamSynchronize(g_comm.side));
+  cudaIpcMemHandle_t all[kMaxRanks];
+  ARL_CUDA(cudaMemcpy(all, all_dev, (size_t)n * sizeof(mine), cudaMemcpyDeviceToHost));
+  ARL_CUDA(cudaFree(stage));
+  P2PView v = {};
+  for (int r = 0; r < n; ++r) {
+    void* base = g_p2p.local;
+    if (r != me) {
+      ARL_CUDA(cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess));
+      g_p2p.opened[r] = base;
+    }
+    v.slot[r] = (float*)base;
+    v.flags[r] = (unsigned long long*)((char*)base + ctl_off);
+  }
+  char* ctl = (char*)g_p2p.local + ctl_off;
+  v.cycle = (unsigned long long*)(ctl + 1024);
+  v.done = (unsigned int*)(ctl + 1024 + 64);
+  v.error = (int*)(ctl + 1024 + 128);
+  v.count = (long long)count;
+  v.stride = (long long)(slot_bytes / sizeof(float));
+  v.rank = me; v.nranks = n;
+  g_p2p.view = v;
+  g_p2p.on = true;
+  // nobody publishes before every rank has mapped every buffer: one tiny collective as a barrier
+  void* tok = nullptr;
+  ARL_CUDA(cudaMalloc(&tok, 256));
+  ARL_CUDA(cudaMemset(tok, 0, 256));
+  ARL_NCCL(g_nccl.all_reduce(tok, tok, 1, kNcclFloat32, kNcclSum, g_comm.comm, g_comm.side));
+  ARL_CUDA(cudaStreamSynchronize(g_comm.side));
+  ARL_CUDA(cudaFree(tok));
+  return ARL_OK;
+}
+
+/* 1 when the peer-memory exchange is active */
+extern "C" int arl_comm_p2p_enabled(void) { return g_p2p.on ? 1 : 0; }
+
+/* the error word of the peer-memory exchange: 0 = fine, 1 = a peer's flag did not arrive within
+ * the time limit of the reduction kernel (its result is then garbage; the caller should stop) */
+extern "C" int arl_comm_p2p_error(void) {
+  if (!g_p2p.on) return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, g_p2p.view.error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return e;
+}
 
 extern "C" int arl_comm_unique_id(uint8_t* id_out) {
   ARL_REQUIRE(id_out, "arl_comm_unique_id: null pointer");
@@ -127,6 +219,13 @@ extern "C" int arl_comm_nccl_version(void) {
 extern "C" int arl_comm_destroy(void) {
   if (!g_comm.comm) return ARL_OK;
   cudaStreamSynchronize(g_comm.side);
+  if (g_p2p.on) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (g_p2p.opened[r]) cudaIpcCloseMemHandle(g_p2p.opened[r]);
+    cudaFree(g_p2p.local);
+    g_p2p = P2P();
+  }
   g_nccl.comm_destroy(g_comm.comm);
   cudaEventDestroy(g_comm.ready);
   cudaEventDestroy(g_comm.done);

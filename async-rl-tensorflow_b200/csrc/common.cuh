@@ -65,6 +65,21 @@ constexpr int64_t kPrepW2DBytes = 33024;
 constexpr int64_t kPrepFcWT = kPrepW2D + kPrepW2DBytes;           // l4_w TRANSPOSED as a split block [256 rows][2592]
 constexpr int64_t kPrepBytes = kPrepFcWT + kPrepFcWBytes;
 
+// Peer-memory exchange state (comm.cu): every rank's gradient slots and flag words mapped into this
+// process (CUDA IPC over NVLink); see arl_comm_enable_p2p.
+constexpr int kMaxRanks = 16;
+struct P2PView {
+  float* slot[kMaxRanks];              // rank r's buffer base: [slot 0 | slot 1], `count` floats each
+  unsigned long long* flags[kMaxRanks];// rank r's flag words [kMaxRanks]: flags[r][q] = last cycle rank q published
+  unsigned long long* cycle;           // this rank's cycle counter
+  unsigned int* done;                  // this rank's "blocks finished" counter of the publish kernel
+  int* error;                          // this rank's error word (1 = a peer's flag did not arrive in time)
+  long long count;                     // floats of a gradient the buffer was sized for
+  long long stride;                    // floats from slot 0 to slot 1 (count rounded up to 256 B)
+  int rank, nranks;
+};
+const P2PView* p2p_view();             // nullptr unless arl_comm_enable_p2p succeeded
+
 // ---- small device helpers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

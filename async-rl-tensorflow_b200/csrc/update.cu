@@ -10,6 +10,7 @@
 
 namespace arl {
 
+int num_sms();
 constexpr int kChunk = 4096;
 constexpr int kUpThreads = 256;
 
@@ -46,6 +47,118 @@ sumsq_kernel(const float* __restrict__ grads, float* __restrict__ partial, Updat
 #pragma unroll
     for (int i = 0; i < kUpThreads / 32; ++i) v += red[i];
     partial[blockIdx.x] = v;
+  }
+}
+
+// ---- all-reduce over NVLink peer memory fused into the norm pass (comm.cu: arl_comm_enable_p2p) ----
+// publish: copy this rank's gradient into slot (cycle+1)&1 of its own shared buffer; the LAST block to
+// finish makes the copy visible system-wide, advances the cycle counter and writes the new cycle
+// number into word [rank] of every rank's flag array (remote stores over NVLink).
+__global__ void __launch_bounds__(256)
+p2p_publish_kernel(const float* __restrict__ grads, P2PView v, long long n) {
+  const unsigned long long next = *v.cycle + 1;                 // (only the last block changes it, below)
+  float* dst = v.slot[v.rank] + (next & 1) * v.stride;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(grads)[i];
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = grads[i];
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(v.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) {
+    *v.done = 0u;
+    *v.cycle = next;
+  }
+  __threadfence_system();
+  if (threadIdx.x < v.nranks)
+    *reinterpret_cast<volatile unsigned long long*>(v.flags[threadIdx.x] + v.rank) = next;
+}
+
+// the norm pass of the update with the exchange inside: wait until every rank's flag has reached
+// this cycle, then g[i] = sum over ranks (in rank order: the same bits on every rank) of their
+// published gradient, written locally, + the partial sum of squares of the chunk
+template <int NR>
+__global__ void __launch_bounds__(kUpThreads)
+p2p_reduce_sumsq_kernel(float* __restrict__ grads, float* __restrict__ partial, UpdatePlan plan, P2PView v) {
+  __shared__ float red[kUpThreads / 32];
+  const unsigned long long c = *v.cycle;
+  if (threadIdx.x < v.nranks) {
+    const volatile unsigned long long* f = v.flags[v.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < c) {
+      if (clock64() - t0 > 6000000000LL) {                      // ~3 s: a peer is gone; do not hang the GPU
+        *v.error = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  const int t = find_tensor(plan, blockIdx.x);
+  const int64_t beg = plan.off[t] + (int64_t)(blockIdx.x - plan.chunk_begin[t]) * kChunk;
+  const int64_t end = beg + kChunk < plan.off[t + 1] ? beg + kChunk : plan.off[t + 1];
+  const long long so = (long long)(c & 1) * v.stride;
+  float s = 0.f;
+  // A remote load takes a few microseconds: every thread requests ALL ranks' values of its
+  // elements (NR x U vectors in flight) before it adds the first one -- one latency per round, two
+  // rounds per 4096-element chunk -- instead of one dependent round per element.
+  constexpr int U = 2;
+  if (((beg | end) & 3) == 0) {
+    for (int64_t i0 = beg + 4 * threadIdx.x; i0 < end; i0 += 4 * kUpThreads * U) {
+      float4 x[NR][U];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = i0 + (int64_t)u * 4 * kUpThreads;
+          x[r][u] = i < end ? __ldcg(reinterpret_cast<const float4*>(v.slot[r] + so + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * 4 * kUpThreads;
+        if (i >= end) break;
+        float4 g = x[0][u];
+#pragma unroll
+        for (int r = 1; r < NR; ++r) { g.x += x[r][u].x; g.y += x[r][u].y; g.z += x[r][u].z; g.w += x[r][u].w; }
+        *reinterpret_cast<float4*>(grads + i) = g;
+        s = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, fmaf(g.w, g.w, s))));
+      }
+    }
+  } else {                                          // small tensors whose offsets are not multiples of 4
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kUpThreads * 4) {
+      float x[NR][4];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = i0 + (int64_t)u * kUpThreads;
+          x[r][u] = i < end ? __ldcg(v.slot[r] + so + i) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + (int64_t)u * kUpThreads;
+        if (i >= end) break;
+        float g = x[0][u];
+#pragma unroll
+        for (int r = 1; r < NR; ++r) g += x[r][u];
+        grads[i] = g;
+        s = fmaf(g, g, s);
+      }
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kUpThreads / 32; ++i) acc += red[i];
+    partial[blockIdx.x] = acc;
   }
 }
 
@@ -88,7 +201,8 @@ using namespace arl;
 static int clip_rmsprop_offsets(float* params, float* rms, const float* grads, const int64_t* offsets,
                                 int num_tensors, float lr, float decay, float eps, float clip_norm,
                                 float* norms_out, void* workspace, const int64_t* step_dev,
-                                int64_t step_offset, double base_lr, int64_t max_step, void* stream) {
+                                int64_t step_offset, double base_lr, int64_t max_step, void* stream,
+                                bool exchange = false) {
   ARL_REQUIRE(params && rms && grads && workspace && offsets, "arl_clip_rmsprop: null pointer");
   ARL_REQUIRE(num_tensors >= 1 && num_tensors <= kMaxTensors, "arl_clip_rmsprop: %d tensors outside [1,%d]",
               num_tensors, kMaxTensors);
@@ -108,8 +222,33 @@ static int clip_rmsprop_offsets(float* params, float* rms, const float* grads, c
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
-  sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
-  ARL_LAUNCH_CHECK("sumsq_kernel");
+  if (exchange) {
+    // `grads` holds this rank's gradient: publish it, then sum every rank's copy back into it
+    const P2PView* v = p2p_view();
+    ARL_REQUIRE(v != nullptr, "arl_clip_rmsprop: exchange requested but arl_comm_enable_p2p has not succeeded");
+    const int64_t n = offsets[num_tensors];
+    ARL_REQUIRE(n <= v->count, "arl_clip_rmsprop: %lld parameters but the exchange buffer holds %lld",
+                (long long)n, (long long)v->count);
+    ARL_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "arl_clip_rmsprop: grads must be 16-byte aligned");
+    int pgrid = (int)((n / 4 + 255) / 256);
+    if (pgrid > 2 * num_sms()) pgrid = 2 * num_sms();
+    if (pgrid < 1) pgrid = 1;
+    p2p_publish_kernel<<<pgrid, 256, 0, st>>>(grads, *v, (long long)n);
+    ARL_LAUNCH_CHECK("p2p_publish_kernel");
+    float* gw = const_cast<float*>(grads);
+    switch (v->nranks) {
+      case 2: p2p_reduce_sumsq_kernel<2><<<chunks, kUpThreads, 0, st>>>(gw, partial, plan, *v); break;
+      case 4: p2p_reduce_sumsq_kernel<4><<<chunks, kUpThreads, 0, st>>>(gw, partial, plan, *v); break;
+      case 8: p2p_reduce_sumsq_kernel<8><<<chunks, kUpThreads, 0, st>>>(gw, partial, plan, *v); break;
+      default:
+        set_error("arl_exchange_clip_rmsprop: the peer-memory exchange is built for 2, 4 or 8 ranks (got %d)", v->nranks);
+        return ARL_ERR_UNSUPPORTED;
+    }
+    ARL_LAUNCH_CHECK("p2p_reduce_sumsq_kernel");
+  } else {
+    sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
+    ARL_LAUNCH_CHECK("sumsq_kernel");
+  }
   rmsprop_kernel<<<chunks, kUpThreads, 0, st>>>(params, rms, grads, partial, norms_out, plan, lr,
                                                decay, eps, clip_norm, step_dev, (long long)step_offset,
                                                base_lr, (long long)max_step);
@@ -136,6 +275,16 @@ extern "C" int arl_clip_rmsprop_layout(float* params, float* rms, const float* g
   ARL_REQUIRE(step_dev == nullptr || max_step > 0, "arl_clip_rmsprop_layout: max_step <= 0");
   return clip_rmsprop_offsets(params, rms, grads, offsets, num_tensors, lr, decay, eps, clip_norm, norms_out,
                               workspace, step_dev, step_offset, base_lr, step_dev ? max_step : 1, stream);
+}
+
+extern "C" int arl_exchange_clip_rmsprop(float* params, float* rms, float* grads, const int64_t* offsets,
+                                         int num_tensors, float lr, const int64_t* step_dev,
+                                         int64_t step_offset, double base_lr, int64_t max_step, float decay,
+                                         float eps, float clip_norm, float* norms_out, void* workspace,
+                                         void* stream) {
+  ARL_REQUIRE(step_dev == nullptr || max_step > 0, "arl_exchange_clip_rmsprop: max_step <= 0");
+  return clip_rmsprop_offsets(params, rms, grads, offsets, num_tensors, lr, decay, eps, clip_norm, norms_out,
+                              workspace, step_dev, step_offset, base_lr, step_dev ? max_step : 1, stream, true);
 }
 
 extern "C" int arl_clip_rmsprop(float* params, float* rms, const float* grads, int action_size,

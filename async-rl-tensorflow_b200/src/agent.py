@@ -52,11 +52,16 @@ class Agent(BaseModel):
         # the per-cycle exchange runs inside the library (arl_comm_init / arl_backward(allreduce=1):
         # NCCL, bucketed so that the fc256 gradient travels while the conv backward kernels run);
         # collective='torch' keeps the all-reduce in torch.distributed (debugging / gloo)
-        self.collective = getattr(config, 'collective', 'library')
-        if self.collective not in ('library', 'torch'):
-            raise ValueError("collective must be 'library' or 'torch'")
-        if self.world_size > 1 and self.collective == 'library':
+        # 'p2p' (default): no collective kernel at all -- every rank reads the others' gradients over
+        # NVLink peer memory inside the norm pass of the update (arl_exchange_clip_rmsprop)
+        self.collective = getattr(config, 'collective', 'p2p')
+        if self.collective not in ('p2p', 'library', 'torch'):
+            raise ValueError("collective must be 'p2p', 'library' or 'torch'")
+        if self.world_size > 1 and self.collective in ('p2p', 'library'):
             _cabi.comm_init(self.device)
+            if self.collective == 'p2p':
+                with torch.cuda.device(self.device):
+                    _cabi.call("arl_comm_enable_p2p", int(self.network.params.numel()))
 
         T, B = self.t_max, self.num_envs
         self.batch_reward = torch.zeros(T, B, device=self.device)
@@ -231,7 +236,7 @@ class Agent(BaseModel):
     def _graphs_on(self):
         return (self.cuda_graphs and self.network.timed is None
                 and self.update_count >= self.graph_warmup_updates
-                and (self.world_size == 1 or self.collective == 'library'))
+                and (self.world_size == 1 or self.collective in ('p2p', 'library')))
 
     def _sync_step_dev(self):
         """``step_dev`` mirrors the host's ``self.step``; callers that move ``self.step`` by hand
@@ -381,10 +386,11 @@ class Agent(BaseModel):
         scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
         net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
                               grad_scale=scale, allreduce=in_lib, refresh=False)
-        if self.world_size > 1 and not in_lib:
+        if self.world_size > 1 and self.collective == 'torch':
             dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)
         net.apply_gradients_sched(self.step_dev, -self.t_max, self.learning_rate, self.max_step,
-                                  count_write=False)
+                                  count_write=False,
+                                  exchange=self.world_size > 1 and self.collective == 'p2p')
 
     # -- agent.py:169-207 -------------------------------------------------------------------
     def batch_update(self, is_chief=False):
@@ -400,9 +406,9 @@ class Agent(BaseModel):
             scale = 1.0 / self.global_envs if self.reduce_mean else 1.0
             net.compute_gradients(self.history, self.batch_reward, self.batch_terminal, v_boot,
                                   grad_scale=scale, allreduce=in_lib)   # the one exchange per cycle
-        if self.world_size > 1 and not in_lib:
+        if self.world_size > 1 and self.collective == 'torch':
             dist.all_reduce(net.grads, op=dist.ReduceOp.SUM)
-        net.apply_gradients(self.lr)
+        net.apply_gradients(self.lr, exchange=self.world_size > 1 and self.collective == 'p2p')
         self.update_count += 1
         self.t = 0
 

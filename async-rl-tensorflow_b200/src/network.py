@@ -438,21 +438,41 @@ class Network(object):
     def q(self):                                               # agent.py:252
         return self.policy_logits
 
-    def apply_gradients(self, lr):
-        """agent.py:316-321: per-tensor clip_by_norm(40) + shared RMSProp (K5)."""
-        self._timed_call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
-                         _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
-                         self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
-                         _cabi.stream_ptr())
+    def _exchange_update(self, lr, step_dev, step_offset, base_lr, max_step):
+        """K5 with the gradient exchange inside (arl_exchange_clip_rmsprop: every rank's gradient
+        is read over NVLink peer memory in the norm pass; no separate all-reduce)."""
+        import ctypes
+        if not hasattr(self, '_offsets_c'):
+            self._offsets_c = (ctypes.c_int64 * len(self.offsets))(*self.offsets)
+        self._timed_call("arl_exchange_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                         _cabi.ptr(self.grads), self._offsets_c, len(self.offsets) - 1, float(lr),
+                         _cabi.ptr(step_dev) if step_dev is not None else None, int(step_offset),
+                         float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
+                         _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
+
+    def apply_gradients(self, lr, exchange=False):
+        """agent.py:316-321: per-tensor clip_by_norm(40) + shared RMSProp (K5).  ``exchange``: sum
+        the gradient over the ranks first, inside the same kernels (NVLink peer memory)."""
+        if exchange:
+            self._exchange_update(lr, None, 0, 0.0, 1)
+        else:
+            self._timed_call("arl_clip_rmsprop", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                             _cabi.ptr(self.grads), self.action_size, float(lr), self.decay, self.epsilon,
+                             self.clip_norm, _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace),
+                             _cabi.stream_ptr())
         self._param_writes += 1                                # the kernel wrote params: fc_w is stale
 
-    def apply_gradients_sched(self, step_dev, step_offset, base_lr, max_step, count_write=True):
+    def apply_gradients_sched(self, step_dev, step_offset, base_lr, max_step, count_write=True,
+                              exchange=False):
         """``apply_gradients`` with the learning rate of agent.py:393-395 evaluated on the device
         from the int64 step counter ``step_dev`` (+ ``step_offset``): replayable by a CUDA graph."""
-        _cabi.call("arl_clip_rmsprop_sched", _cabi.ptr(self.params), _cabi.ptr(self.rms),
-                   _cabi.ptr(self.grads), self.action_size, _cabi.ptr(step_dev), int(step_offset),
-                   float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
-                   _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
+        if exchange:
+            self._exchange_update(0.0, step_dev, step_offset, base_lr, max_step)
+        else:
+            _cabi.call("arl_clip_rmsprop_sched", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                       _cabi.ptr(self.grads), self.action_size, _cabi.ptr(step_dev), int(step_offset),
+                       float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
+                       _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
         if count_write:
             self._param_writes += 1
 

@@ -192,19 +192,21 @@ class NatureNetwork(Network):
         raise NotImplementedError("loss_mode='async_q' runs the reference's agent.py net, which is the "
                                   "nips trunk (agent.py:226-252); the nature trunk is A3C-only")
 
-    def _update(self, lr, step_dev, step_offset, base_lr, max_step):
-        _cabi.call("arl_clip_rmsprop_layout", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+    def _update(self, lr, step_dev, step_offset, base_lr, max_step, exchange=False):
+        _cabi.call("arl_exchange_clip_rmsprop" if exchange else "arl_clip_rmsprop_layout",
+                   _cabi.ptr(self.params), _cabi.ptr(self.rms),
                    _cabi.ptr(self.grads), self._offsets_c, len(PARAM_NAMES), float(lr),
                    _cabi.ptr(step_dev) if step_dev is not None else None, int(step_offset),
                    float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
                    _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
 
-    def apply_gradients(self, lr):
-        self._update(lr, None, 0, 0.0, 1)
+    def apply_gradients(self, lr, exchange=False):
+        self._update(lr, None, 0, 0.0, 1, exchange)
         self._param_writes += 1
 
-    def apply_gradients_sched(self, step_dev, step_offset, base_lr, max_step, count_write=True):
-        self._update(0.0, step_dev, step_offset, base_lr, max_step)
+    def apply_gradients_sched(self, step_dev, step_offset, base_lr, max_step, count_write=True,
+                              exchange=False):
+        self._update(0.0, step_dev, step_offset, base_lr, max_step, exchange)
         if count_write:
             self._param_writes += 1
 

@@ -192,8 +192,11 @@ def workload_config(args, ref=False):
             "frame": "210x160x3 uint8", "frames_per_step_per_gpu": args.envs * args.t_max,
             "l2_policy": "inputs larger than L2: each env step reads %d MB of fresh frames (pool of %s steps)"
                          % (args.envs * 100800 // 2 ** 20, getattr(args, "pool_used", "t_max")),
-            "parallelism": "dp%d (env-sharded, one NCCL all-reduce of the 2.7 MB gradient per step)"
-                           % args.gpus}
+            "parallelism": "dp%d (env-sharded; the 2.7 MB gradient is summed over the ranks once per step: "
+                           "%s)" % (args.gpus, {"p2p": "read over NVLink peer memory inside the update kernel",
+                                                "library": "ncclAllReduce inside the library",
+                                                "torch": "torch.distributed all_reduce"}[
+                                                    getattr(args, "collective", None) or "p2p"])}
 
 
 def main():
@@ -209,6 +212,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-cycles-per-step", type=int, default=40)
     ap.add_argument("--profile-all", action="store_true", help="print per-entry times to stderr")
+    ap.add_argument("--collective", default=None, choices=[None, "p2p", "library", "torch"],
+                    help="gradient exchange at N>1 (default: config.collective = p2p)")
     ap.add_argument("--pool", type=int, default=0, help="steps of synthetic frames kept (0: t_max, capped to ~24 GB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -253,7 +258,10 @@ def main():
     cabi = pkg._cabi
     peaks = load_peaks()
     B, T, A, K, W = args.envs, args.t_max, args.actions, args.steps, args.warmup
-    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T})
+    over = {"model": "m1", "num_envs": B, "t_max": T}
+    if args.collective:
+        over["collective"] = args.collective
+    cfg = pkg.config.get_config(over)
 
     def barrier():
         torch.cuda.synchronize()

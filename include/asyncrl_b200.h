@@ -347,6 +347,22 @@ ARL_API int arl_comm_destroy(void);
 ARL_API int arl_allreduce_grads(float* grads, int64_t count, void* stream);
 ARL_API int arl_allreduce_begin(float* grads, int64_t offset, int64_t count, void* stream);
 ARL_API int arl_allreduce_end(void* stream);
+/* The same exchange WITHOUT a collective kernel, over NVLink peer memory (CUDA IPC), fused into the
+ * update: arl_comm_enable_p2p(count) gives every rank a buffer of two gradient slots + flag words
+ * mapped into every other rank.  arl_exchange_clip_rmsprop is arl_clip_rmsprop_layout whose norm
+ * pass first publishes this rank's `grads` (copy into a slot, flag word raised in every peer's
+ * memory), waits for every rank's flag and then READS all ranks' slots, adding them in rank order
+ * (bit-identical on every rank) into `grads` while it accumulates the per-tensor sums of squares:
+ * no NCCL kernel, no extra pass over the gradient.  Call it INSTEAD of arl_allreduce_grads +
+ * arl_clip_rmsprop*, on every rank, once per cycle.  arl_comm_p2p_error() != 0: a peer's flag did
+ * not arrive within ~3 s (the reduction gives up instead of hanging the GPU). */
+ARL_API int arl_comm_enable_p2p(int64_t count);
+ARL_API int arl_comm_p2p_enabled(void);
+ARL_API int arl_comm_p2p_error(void);
+ARL_API int arl_exchange_clip_rmsprop(float* params, float* rms, float* grads, const int64_t* offsets,
+                              int num_tensors, float lr, const int64_t* step_dev, int64_t step_offset,
+                              double base_lr, int64_t max_step, float decay, float eps,
+                              float clip_norm, float* norms_out, void* workspace, void* stream);
 
 /* ---- K5: per-tensor clip + shared RMSProp -------------------------------------------
  * agent.py:316-319 clip_by_norm(g, clip) per tensor, then TF ApplyRMSProp as configured at
