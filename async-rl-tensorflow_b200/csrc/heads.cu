@@ -205,7 +205,11 @@ __global__ void q_lossgrad_kernel(const float* __restrict__ rewards,
 }
 
 // ------------------------------- returns + loss gradients ---------------------------------
-// One thread per env walks t = T-1 .. 0.
+// One thread per SAMPLE (t, b): the return recurrence is the only serial part, and it is T - t
+// fused multiply-adds, so every thread just runs it from T-1 down to its own t (the same operations
+// in the same order as a walk over the whole rollout: identical bits) and then does the softmax /
+// gradient work of its one sample.  (One thread per env walking all T samples: 32 CTAs for 4096
+// envs, 14.4 us.)
 __global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
                                         const uint8_t* __restrict__ terminals,
                                         const int32_t* __restrict__ actions,
@@ -216,42 +220,43 @@ __global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
                                         float* __restrict__ loss_sums, int T, int B, int A,
                                         float gamma, float beta, float rmin, float rmax,
                                         float grad_scale) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;
-  if (b < B) {
+  if (n < (int64_t)T * B) {
+    const int t = (int)(n / B), b = (int)(n - (int64_t)t * B);
     float R = v_boot[b];
-    for (int t = T - 1; t >= 0; --t) {
-      const size_t n = (size_t)t * B + b;
-      const float r = fminf(fmaxf(rewards[n], rmin), rmax);               // agent.py:154
-      R = fmaf(gamma * (1.0f - (terminals[n] ? 1.0f : 0.0f)), R, r);      // agent.py:190
-      returns[n] = R;
-      const float* z = logits + n * A;
-      float zz[ARL_MAX_ACTIONS];
-      float mx = z[0];
-#pragma unroll 1
-      for (int j = 0; j < A; ++j) { zz[j] = z[j]; mx = fmaxf(mx, zz[j]); }
-      float den = 0.f;
-      for (int j = 0; j < A; ++j) den += expf(zz[j] - mx);
-      const float lse = mx + logf(den);
-      float ent = 0.f;
-      for (int j = 0; j < A; ++j) {
-        const float lp = zz[j] - lse;
-        ent -= expf(lp) * lp;                                             // network.py:69
-      }
-      const float v = value[n];
-      const float adv = R - v;
-      const int a = actions[n];
-      float* dz = dlogits + n * A;
-      for (int j = 0; j < A; ++j) {
-        const float lp = zz[j] - lse, p = expf(lp);
-        const float g = -adv * ((j == a ? 1.0f : 0.0f) - p) + beta * p * (lp + ent);
-        dz[j] = g * grad_scale;
-      }
-      dvalue[n] = -adv * grad_scale;                                      // d/dV (R-V)^2/2
-      s_pol += -(zz[a] - lse) * adv - beta * ent;                         // network.py:87-88
-      s_val += 0.5f * adv * adv;                                          // network.py:91
-      s_ent += ent;
+    for (int tt = T - 1; tt >= t; --tt) {
+      const size_t m = (size_t)tt * B + b;
+      const float r = fminf(fmaxf(rewards[m], rmin), rmax);               // agent.py:154
+      R = fmaf(gamma * (1.0f - (terminals[m] ? 1.0f : 0.0f)), R, r);      // agent.py:190
     }
+    returns[n] = R;
+    const float* z = logits + n * A;
+    float zz[ARL_MAX_ACTIONS];
+    float mx = z[0];
+#pragma unroll 1
+    for (int j = 0; j < A; ++j) { zz[j] = z[j]; mx = fmaxf(mx, zz[j]); }
+    float den = 0.f;
+    for (int j = 0; j < A; ++j) den += expf(zz[j] - mx);
+    const float lse = mx + logf(den);
+    float ent = 0.f;
+    for (int j = 0; j < A; ++j) {
+      const float lp = zz[j] - lse;
+      ent -= expf(lp) * lp;                                             // network.py:69
+    }
+    const float v = value[n];
+    const float adv = R - v;
+    const int a = actions[n];
+    float* dz = dlogits + n * A;
+    for (int j = 0; j < A; ++j) {
+      const float lp = zz[j] - lse, p = expf(lp);
+      const float g = -adv * ((j == a ? 1.0f : 0.0f) - p) + beta * p * (lp + ent);
+      dz[j] = g * grad_scale;
+    }
+    dvalue[n] = -adv * grad_scale;                                      // d/dV (R-V)^2/2
+    s_pol = -(zz[a] - lse) * adv - beta * ent;                          // network.py:87-88
+    s_val = 0.5f * adv * adv;                                           // network.py:91
+    s_ent = ent;
   }
   if (loss_sums) {
     s_pol = warp_sum(s_pol); s_val = warp_sum(s_val); s_ent = warp_sum(s_ent);
@@ -534,7 +539,8 @@ extern "C" int arl_returns_lossgrad(const float* rewards, const uint8_t* termina
   ARL_REQUIRE(action_size >= 1 && action_size <= ARL_MAX_ACTIONS,
               "arl_returns_lossgrad: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
   if (t_max == 0 || num_envs == 0) return ARL_OK;
-  returns_lossgrad_kernel<<<(num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  const int64_t total = (int64_t)t_max * num_envs;
+  returns_lossgrad_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       rewards, terminals, actions, logits, value, v_boot, returns, dlogits, dvalue, loss_sums,
       t_max, num_envs, action_size, gamma, beta, reward_min, reward_max, grad_scale);
   ARL_LAUNCH_CHECK("returns_lossgrad_kernel");

@@ -469,10 +469,10 @@ class Network(object):
         if exchange:
             self._exchange_update(0.0, step_dev, step_offset, base_lr, max_step)
         else:
-            _cabi.call("arl_clip_rmsprop_sched", _cabi.ptr(self.params), _cabi.ptr(self.rms),
-                       _cabi.ptr(self.grads), self.action_size, _cabi.ptr(step_dev), int(step_offset),
-                       float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
-                       _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
+            self._timed_call("arl_clip_rmsprop_sched", _cabi.ptr(self.params), _cabi.ptr(self.rms),
+                             _cabi.ptr(self.grads), self.action_size, _cabi.ptr(step_dev), int(step_offset),
+                             float(base_lr), int(max_step), self.decay, self.epsilon, self.clip_norm,
+                             _cabi.ptr(self.grad_norms), _cabi.ptr(self.workspace), _cabi.stream_ptr())
         if count_write:
             self._param_writes += 1
 

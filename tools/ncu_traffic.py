@@ -12,7 +12,12 @@ ENTRY_OF = [
     ("preprocess_kernel", "arl_preprocess_push"),
     ("Conv1Fwd", "arl_conv1_forward"),
     ("Conv2Fwd", "arl_conv2_forward"),
-    ("FcFwdCluster", "arl_fc_forward"),                  # (int)/(bool) casts are stripped below
+    ("FcFwdCluster", "arl_fc_heads_forward"),            # (int)/(bool) casts are stripped below
+    ("heads_fwd_kernel", "arl_fc_heads_forward"),
+    ("heads_bwd_kernel", "arl_heads_backward"),
+    ("returns_lossgrad_kernel", "arl_returns_lossgrad"),
+    ("sumsq_kernel", "arl_clip_rmsprop"),
+    ("rmsprop_kernel", "arl_clip_rmsprop"),
     ("BulkGemm<128, 32, 0, 0, 2", "arl_fc_backward"),    # fc dgrad
     ("BulkGemm<128, 64, 1, 1, 0", "arl_fc_backward"),    # fc wgrad (earlier form)
     ("BulkGemm<256, 32, 1, 0, 0", "arl_fc_backward"),    # fc wgrad
