@@ -48,8 +48,9 @@ class AgentConfig(object):
     cuda_graphs = True                   # capture predict / observe(+update) as CUDA graphs (a3c mode)
     max_graphs = 1024                    # cap of the graph cache; beyond it the loop runs eagerly
     DQN_type = 'nips'                    # network.py:30-55 trunk: 'nips' (agent.py:226-252) | 'nature'
-    collective = 'p2p'                   # gradient exchange: 'p2p' (NVLink peer memory, fused into the update) |
-                                         # 'library' (arl_allreduce_grads: NCCL inside the .so) | 'torch'
+    collective = 'auto'                  # gradient exchange: 'p2p' (NVLink peer memory, fused into the update) |
+                                         # 'library' (arl_allreduce_grads: NCCL inside the .so) | 'torch' |
+                                         # 'auto' = p2p on 2 GPUs, library beyond (measured: profiles/r02_exchange.txt)
 
 
 class EnvironmentConfig(object):

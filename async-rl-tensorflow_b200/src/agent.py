@@ -52,11 +52,16 @@ class Agent(BaseModel):
         # the per-cycle exchange runs inside the library (arl_comm_init / arl_backward(allreduce=1):
         # NCCL, bucketed so that the fc256 gradient travels while the conv backward kernels run);
         # collective='torch' keeps the all-reduce in torch.distributed (debugging / gloo)
-        # 'p2p' (default): no collective kernel at all -- every rank reads the others' gradients over
-        # NVLink peer memory inside the norm pass of the update (arl_exchange_clip_rmsprop)
-        self.collective = getattr(config, 'collective', 'p2p')
+        # 'p2p': no collective kernel at all -- every rank reads the others' gradients over NVLink
+        # peer memory inside the norm pass of the update (arl_exchange_clip_rmsprop)
+        # 'auto' (default): 'p2p' on 2 GPUs, 'library' beyond -- measured (profiles/r02_exchange.txt):
+        # the one-shot peer read wins by 8 us per cycle at N=2 and loses 33 us at N=8, where every
+        # rank pulls 7 x 2.7 MB while NCCL reduces inside the NVSwitch (NVLS)
+        self.collective = getattr(config, 'collective', 'auto')
+        if self.collective == 'auto':
+            self.collective = 'p2p' if self.world_size == 2 else 'library'
         if self.collective not in ('p2p', 'library', 'torch'):
-            raise ValueError("collective must be 'p2p', 'library' or 'torch'")
+            raise ValueError("collective must be 'auto', 'p2p', 'library' or 'torch'")
         if self.world_size > 1 and self.collective in ('p2p', 'library'):
             _cabi.comm_init(self.device)
             if self.collective == 'p2p':

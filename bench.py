@@ -197,7 +197,8 @@ def workload_config(args, ref=False):
                            "%s)" % (args.gpus, {"p2p": "read over NVLink peer memory inside the update kernel",
                                                 "library": "ncclAllReduce inside the library",
                                                 "torch": "torch.distributed all_reduce"}[
-                                                    getattr(args, "collective", None) or "p2p"])}
+                                                    (getattr(args, "collective", None) or "auto").replace(
+                                                        "auto", "p2p" if args.gpus == 2 else "library")])}
 
 
 def main():
@@ -213,8 +214,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-cycles-per-step", type=int, default=40)
     ap.add_argument("--profile-all", action="store_true", help="print per-entry times to stderr")
-    ap.add_argument("--collective", default=None, choices=[None, "p2p", "library", "torch"],
-                    help="gradient exchange at N>1 (default: config.collective = p2p)")
+    ap.add_argument("--collective", default=None, choices=[None, "auto", "p2p", "library", "torch"],
+                    help="gradient exchange at N>1 (default: config.collective = auto)")
     ap.add_argument("--pool", type=int, default=0, help="steps of synthetic frames kept (0: t_max, capped to ~24 GB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
