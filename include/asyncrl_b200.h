@@ -20,11 +20,12 @@
  *     bytes are stored in 4x4 blocks (space-to-depth): screen byte (y,x) sits at
  *     ((y/4)*21 + x/4)*16 + (y%4)*4 + x%4 -- arl_preprocess_push writes that order,
  *     arl_conv1_* read it, arl_history_get returns the reference's row-major stack.
- *   - conv1's output a1 (the f32 [N,20,20,16]-sized buffer) holds split bf16 in space-to-depth
- *     blocks: [n][hi|lo][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 channels] with pixel
- *     (y,x) = (2yp+i, 2xp+j); value = hi + lo.  Only arl_conv1_forward writes it and only
+ *   - conv1's output a1 (12 800 bytes per sample) holds ONE fp16 per value in space-to-depth
+ *     blocks: [n][kc = (i*2+j)*2 + chalf][q = yp*10 + xp][8 channels] with pixel
+ *     (y,x) = (2yp+i, 2xp+j).  Only arl_conv1_forward writes it and only
  *     arl_conv2_forward / arl_conv2_backward read it (as tensor-core operand and relu mask);
- *     src/network.py:decode_a1 turns it back into f32 NHWC.
+ *     src/network.py:decode_a1 turns it back into f32 NHWC.  (the measured
+ *     precision behind the 16-bit format; round 1 kept a bf16 hi + lo pair.)
  *   - the fc256 layer's tensors are kept as "split blocks": a logical f32 matrix [rows][8*chunks]
  *     stored as [part (hi, lo)][chunk][row][8 bf16] (16-byte vectors, value = hi + lo, same bytes
  *     as the f32 matrix), which the tcgen05 kernels fetch with cp.async.bulk and never convert:
