@@ -194,7 +194,7 @@ __device__ __forceinline__ void x1_store(uint8_t* img, const uint4 (&w)[U], int 
     const int un = glane + u * gsize;
     if (un >= TOTAL) break;
     const int c = un / ROWS, r = un - c * ROWS;
-    const uint4 lo2 = tc::bytes8_to_bf16(w[u].x, w[u].y), hi2 = tc::bytes8_to_bf16(w[u].z, w[u].w);
+    const uint4 lo2 = tc::bytes8_to_f16(w[u].x, w[u].y), hi2 = tc::bytes8_to_f16(w[u].z, w[u].w);   // exact
     uint8_t* d = img + (2 * c) * PL + r * 16;
     *reinterpret_cast<uint4*>(d) = lo2;
     *reinterpret_cast<uint4*>(d + PL) = hi2;
@@ -520,9 +520,12 @@ struct Conv2DgradArgs {
 };
 // dy1s: the gradient w.r.t. conv1's output is only ever the B operand of the conv1 weight-gradient
 // MMA (rows of the 21-wide X grid = the reduction index), so conv2 dgrad stores it the way that
-// kernel fetches it with cp.async.bulk:
-//   dy1s[part (hi, lo)][co group (2)][grid row n*441 + y*21 + x][8 channels]      (16-B vectors)
-// with the rows y = 20 / x = 20 (no conv1 output there) written as zeros: 28 224 B per sample.
+// kernel fetches it with cp.async.bulk -- ONE fp16 per value (x tensor_scale, saturating):
+//   dy1s[co group (2)][grid row n*441 + y*21 + x][8 channels]      (16-B vectors)
+// with the rows y = 20 / x = 20 (no conv1 output there) written as zeros: 14 112 B per sample.
+// One term is enough HERE (unlike dy2): its only consumer is l1_w (l1_b comes from the fp32 sums
+// of this kernel's epilogue), 2e-4 in tests/precision_study.py's "fp16 a1 + d_a1" row; round 1
+// kept a bf16 hi + lo pair (28 224 B).
 constexpr int kDy1sRows = 441;
 struct Conv2Dgrad : tc::PolicyBase {
   using Args = Conv2DgradArgs;
@@ -614,7 +617,7 @@ struct Conv2Dgrad : tc::PolicyBase {
         float v[8];
         tc::tmem_ld8_sum(taddr + cls * 16 + half * 8, taddr + 64 + cls * 16 + half * 8, v);
         if (!live || y > 20 || x > 20) continue;
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        uint4 hv = make_uint4(0u, 0u, 0u, 0u);
         if (y < 20 && x < 20) {
           const uint4 m = pre.m[cls * 2 + half];
           const uint32_t w[4] = {m.x, m.y, m.z, m.w};
@@ -625,14 +628,10 @@ struct Conv2Dgrad : tc::PolicyBase {
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) st.b[half * 8 + e] += v[e];
-          tc::split2(v[0], v[1], hi.x, lo.x);
-          tc::split2(v[2], v[3], hi.y, lo.y);
-          tc::split2(v[4], v[5], hi.z, lo.z);
-          tc::split2(v[6], v[7], hi.w, lo.w);
+          hv = make_uint4(tc::pack_h2(v[0], v[1]), tc::pack_h2(v[2], v[3]), tc::pack_h2(v[4], v[5]),
+                          tc::pack_h2(v[6], v[7]));
         }
-        uint8_t* d = g.dy1s + ((int64_t)half * R + (int64_t)n * kDy1sRows + y * 21 + x) * 16;
-        *reinterpret_cast<uint4*>(d) = hi;
-        *reinterpret_cast<uint4*>(d + 2 * R * 16) = lo;
+        *reinterpret_cast<uint4*>(g.dy1s + ((int64_t)half * R + (int64_t)n * kDy1sRows + y * 21 + x) * 16) = hv;
       }
     }
   }
@@ -756,7 +755,7 @@ struct Conv2Wgrad : tc::PolicyBase {
 
 struct Conv1WgradArgs {
   RingGeo geo;
-  const uint8_t* dy1s;   // split bf16 on the X grid, written by conv2 dgrad (see dy1s above)
+  const uint8_t* dy1s;   // fp16 on the X grid, written by conv2 dgrad (see dy1s above)
   float* partials;       // [items][4096]
   int64_t rows;          // 441 * num_samples
   int num_samples, k_chunk, items;
@@ -765,18 +764,19 @@ struct Conv1WgradArgs {
 struct Conv1Wgrad : tc::PolicyBase {
   using Args = Conv1WgradArgs;
   // dW1[(a,b) tap][ch][co] = sum_P X[P + a*21 + b][ch] * dy1[P][co] over the rows P of the X grid.
-  // Tap b is folded into M (a second copy of the X image shifted by one row), tap a into N (a
-  // second copy of the dy1 image shifted BACK by 21 rows: sum_Q X[Q + b][ch] * dy1[Q - 21][co]),
-  // so one N = 64 MMA per 16 rows covers all four taps and the wide X tile is read from shared
-  // memory once.  The dy1 images arrive by cp.async.bulk from dy1s (8 copies of 2 KB per stage).
+  // Both operands fp16: the u8 pixels are exact, dy1 is one fp16 per value.  Tap b is folded into M
+  // (a second copy of the X image shifted by one row), tap a into N (a second copy of the dy1 image
+  // shifted BACK by 21 rows: sum_Q X[Q + b][ch] * dy1[Q - 21][co]), so one N = 32 MMA per 16 rows
+  // covers all four taps and the wide X tile is read from shared memory once.  The dy1 images
+  // arrive by cp.async.bulk from dy1s (4 copies of 2 KB per stage).
   static constexpr int GW = 21, TROWS = 129;
-  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // exact bf16: hi only
+  static constexpr int PLA = (TROWS + 1) * 16, A_IMG = 16 * PLA;   // u8 -> fp16, exact
   static constexpr int PLB = 128 * 16, B_IMG = 2 * PLB;            // dy1: 2 co groups
-  // stage = [A | dy hi | dy lo | dy' hi | dy' lo]  (dy' = shifted copy = tap a = 1)
-  static constexpr int PROD_WARPS = 16, STAGES = 4, STAGE_BYTES = A_IMG + 4 * B_IMG, RES_BYTES = 0;
-  // accumulator columns: a*32 + part*16 + co
-  static constexpr int ACC_COLS = 64, OUT_COLS = 32, LO_DELTA = 16, SEG = 16;
-  static __device__ __forceinline__ int acc_col(int c) { return (c >> 4) * 32 + (c & 15); }
+  // stage = [A | dy | dy']  (dy' = shifted copy = tap a = 1); five stages of 41 KB
+  static constexpr int PROD_WARPS = 20, STAGES = 5, STAGE_BYTES = A_IMG + 2 * B_IMG, RES_BYTES = 0;
+  // accumulator columns: a*16 + co
+  static constexpr int ACC_COLS = 32, OUT_COLS = 32, LO_DELTA = 0, SEG = 16;
+  static __device__ __forceinline__ int acc_col(int c) { return c; }
   static __device__ __forceinline__ int num_items(const Args& g) { return g.items; }
   static __device__ __forceinline__ TileCoord coord(const Args& g, int item) {
     return range_tile(item, g.rows, g.k_chunk, g.reverse ? g.items - 1 - item : item);
@@ -789,7 +789,7 @@ struct Conv1Wgrad : tc::PolicyBase {
   // the producer waits for its slot: the ncu capture of round 1 showed producers 24 % of their time
   // waiting for a free stage and then another 13 % on the first use of these loads
   static constexpr bool PREFETCH = true;
-  static constexpr int XU = 5;                                      // 16 warps / 4 stages = 128 lanes x 5 >= 129 x 4
+  static constexpr int XU = 5;                                      // 20 warps / 5 stages = 128 lanes x 5 >= 129 x 4
   struct Prod { uint4 w[XU]; };
   static __device__ __forceinline__ void prefetch_stage(const Args& g, const TileCoord& t, int s, int glane,
                                                         int gsize, Prod& ps) {
@@ -804,32 +804,32 @@ struct Conv1Wgrad : tc::PolicyBase {
     // with p0 + r >= k_end (the next work item's) and rows before the first sample are zero
     const int valid = t.k_end - p0, lead = p0 < GW ? GW - p0 : 0;
     if (valid < 128 || lead > 0) {
-      for (int i = glane; i < 8 * 128; i += gsize) {
+      for (int i = glane; i < 4 * 128; i += gsize) {
         const int plane = i >> 7, r = i & 127;
-        if (r >= valid || (plane >= 4 && r < lead))
+        if (r >= valid || (plane >= 2 && r < lead))
           *reinterpret_cast<uint4*>(st + A_IMG + plane * PLB + r * 16) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
-  // lanes 0..7 of the stage's group own one dy1 plane each: plane = copy*4 + part*2 + co group
+  // lanes 0..3 of the stage's group own one dy1 plane each: plane = copy*2 + co group
   static __device__ __forceinline__ bool bulk_stage(const Args& g, const TileCoord& t, int s, uint8_t* st,
                                                     int glane, int, uint64_t* full) {
-    if (glane >= 8) return false;
+    if (glane >= 4) return false;
     const int p0 = t.k_begin + s * 128;
     int cnt = t.k_end - p0 < 128 ? t.k_end - p0 : 128, src = p0, dst = 0;
-    if (glane >= 4) {
+    if (glane >= 2) {
       src = p0 - GW;
       if (src < 0) { dst = -src; cnt -= dst; src = 0; }
     }
     const uint32_t bytes = cnt > 0 ? (uint32_t)cnt * 16u : 0u;
     mbar_expect_tx(full, bytes);
     if (cnt > 0)
-      bulk_g2s(st + A_IMG + glane * PLB + dst * 16, g.dy1s + ((int64_t)(glane & 3) * g.rows + src) * 16, bytes, full);
+      bulk_g2s(st + A_IMG + glane * PLB + dst * 16, g.dy1s + ((int64_t)(glane & 1) * g.rows + src) * 16, bytes, full);
     return true;
   }
   static __device__ __forceinline__ void issue(const Args&, const TileCoord&, int s, uint32_t st,
                                                uint32_t, uint32_t d) {
-    constexpr uint32_t idesc = tc::make_idesc(64, true, true);     // x . [dy_hi | dy_lo | dy'_hi | dy'_lo]
+    constexpr uint32_t idesc = tc::make_idesc_h(32, true, true);   // [x ; x shifted] . [dy | dy']
     // a_img = st, b_hi = st + A_IMG; one descriptor derivation per stage
     const uint64_t da0 = tc::make_sdesc(st, 128, PLA), db0 = tc::make_sdesc(st + A_IMG, 128, PLB);
 #pragma unroll

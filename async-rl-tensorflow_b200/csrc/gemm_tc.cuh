@@ -346,6 +346,22 @@ __device__ __forceinline__ uint4 bytes8_to_bf16(uint32_t w0, uint32_t w1) {
   return o;
 }
 
+// 8 bytes (two u32 words) -> 8 exact fp16: 0x6400 | byte = 1024 + byte as fp16; subtracting 1024 is exact
+__device__ __forceinline__ uint32_t bytes2h2(uint32_t w, int sel) {
+  const uint32_t m = __byte_perm(w, 0x64646464u, sel);
+  const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&m), __floats2half2_rn(1024.f, 1024.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 bytes8_to_f16(uint32_t w0, uint32_t w1) {
+  // selector: result bytes = (src byte i, 0x64, src byte i+1, 0x64)
+  uint4 o;
+  o.x = bytes2h2(w0, 0x4140);
+  o.y = bytes2h2(w0, 0x4342);
+  o.z = bytes2h2(w1, 0x4140);
+  o.w = bytes2h2(w1, 0x4342);
+  return o;
+}
+
 struct TileCoord {
   int mt, nt, ks;        // tile indices (meaning is the policy's)
   int k_begin, k_end;    // reduction range of this work item (meaning is the policy's)

@@ -19,6 +19,7 @@ from .. import _cabi
 PARAM_NAMES = ("l1_w", "l1_b", "l2_w", "l2_b", "l4_w", "l4_b", "p_w", "p_b", "q_w", "q_b")
 A1_ELEMS, A2_ELEMS, FC, DA1_ELEMS = 6400, 2592, 256, 7056
 A1_STORE = 3200                                               # float32 words of storage per sample of a1 (fp16)
+DA1_STORE = 3528                                              # ... of d_a1 (fp16 on the 21x21 grid)
 
 
 def decode_a1(raw, n=None):
@@ -53,11 +54,11 @@ def encode_split(x):
 
 
 def decode_da1(raw, n):
-    """The gradient w.r.t. conv1's output (include/asyncrl_b200.h: split bf16 on the 21x21 grid,
-    [hi|lo][2 channel groups][n*441 + y*21 + x][8]) -> float32 [n,20,20,16]."""
-    b = raw.reshape(-1)[:n * DA1_ELEMS].view(torch.bfloat16).reshape(2, 2, n, 21, 21, 8)
-    v = b[0].float() + b[1].float()                           # [group, n, y, x, 8]
-    return v.permute(1, 2, 3, 0, 4).reshape(n, 21, 21, 16)[:, :20, :20]
+    """The gradient w.r.t. conv1's output (include/asyncrl_b200.h: one fp16 per value on the 21x21
+    grid, [2 channel groups][n*441 + y*21 + x][8], 14 112 bytes per sample, still multiplied by
+    tensor_scale) -> float32 [n,20,20,16]."""
+    b = raw.reshape(-1)[:n * DA1_STORE].view(torch.float16).reshape(2, n, 21, 21, 8)
+    return b.float().permute(1, 2, 3, 0, 4).reshape(n, 21, 21, 16)[:, :20, :20]
 
 
 def param_shapes(action_size):
@@ -149,7 +150,7 @@ class Network(object):
         # (groups of 8 samples x 256 columns) for the fc256 weight gradient: see d_h()
         self.d_l4 = torch.empty(N + (N + 7) // 8 * 8, FC, **f32)
         self.d_l2 = torch.empty(N, A2_ELEMS, **f32)
-        self.d_l1 = torch.empty(N, DA1_ELEMS, **f32)          # split bf16 on the 21x21 grid: see decode_da1
+        self.d_l1 = torch.empty(N, DA1_STORE, **f32)          # fp16 on the 21x21 grid: see decode_da1
         self.workspace = torch.empty(_cabi.workspace_bytes(A), dtype=torch.uint8, device=dev)
         self.loss_sums = torch.zeros(3, **f32)                # sum policy / value loss, entropy
         self.grad_norms = torch.zeros(len(PARAM_NAMES), **f32)

@@ -42,9 +42,9 @@
  *     must be refreshed whenever the parameters change (arl_clip_rmsprop, a checkpoint load, ...).
  *     src/network.py:decode_split turns a block back into f32 [rows][cols].
  *   - d_a1, the gradient w.r.t. conv1's output, is the reduction operand of the conv1 weight
- *     gradient: split bf16 on conv1's 21x21 space-to-depth grid,
- *     [part (hi, lo)][channel group (2)][row n*441 + y*21 + x][8 channels], rows y = 20 / x = 20
- *     zero: ARL_DA1_ELEMS = 7056 floats per sample.  arl_conv2_backward writes it (and, since it
+ *     gradient: ONE fp16 per value (x tensor_scale) on conv1's 21x21 space-to-depth grid,
+ *     [channel group (2)][row n*441 + y*21 + x][8 channels], rows y = 20 / x = 20 zero:
+ *     ARL_DA1_BYTES = 14 112 bytes per sample.  arl_conv2_backward writes it (and, since it
  *     has the values in registers, the conv1 bias gradient l1_b); arl_conv1_backward reads it.
  *     src/network.py:decode_da1 turns it into f32 [N,20,20,16].
  *   - parameters / gradients / RMSProp slots are flat f32 buffers in the
@@ -66,7 +66,8 @@ extern "C" {
 #define ARL_HISTORY 4            /* config.py:22 history_length                  */
 #define ARL_A1_ELEMS 6400        /* 20*20*16  conv1 output per sample            */
 #define ARL_A2_ELEMS 2592        /* 9*9*32    conv2 output per sample (flatten)  */
-#define ARL_DA1_ELEMS 7056       /* 21*21*16  floats of d_a1 per sample (grid)   */
+#define ARL_DA1_ELEMS 7056       /* 21*21*16  values of d_a1 per sample (grid)   */
+#define ARL_DA1_BYTES 14112      /* ... stored as fp16                          */
 #define ARL_FC 256               /* agent.py:251 / network.py:51                 */
 #define ARL_NUM_TENSORS 10       /* l1_w l1_b l2_w l2_b l4_w l4_b p_w p_b q_w q_b */
 #define ARL_MAX_ACTIONS 32
@@ -247,7 +248,7 @@ ARL_API int arl_returns_lossgrad(const float* rewards, const uint8_t* terminals,
  * Accumulation over the T steps of Algorithm 3 is the reduction over samples inside the
  * weight-gradient kernels.  grads is the flat buffer (overwritten).  Scratch buffers are
  * caller-owned: d_h [(N + roundup8(N)),256] (two split blocks, see the top of this file), d_a2 [N,2592],
- * d_a1 [N,ARL_DA1_ELEMS] (grid layout, see the top of this file),
+ * d_a1 [N * ARL_DA1_BYTES bytes] (fp16 grid layout, see the top of this file),
  * workspace >= arl_backward_workspace_bytes.  a2 = the rollout's conv2 outputs as a sequence of
  * split blocks of a2_block_rows rows each (one per forward call: a2_block_rows = num_envs);
  * prepared must hold arl_prepare_weights of the parameters the forward used. */

@@ -204,8 +204,8 @@ def test_backward_gradients_vs_oracle(pkg, cuda, A, B, T):
                  d_a1=rel_err(net.d_a1().cpu(), aux["d_a1"]))
     print("layer-gradient rel-err", ierrs)
     assert max(ierrs.values()) <= REL_TOL, ierrs
-    raw = net.d_l1.reshape(-1)[:N * 7056].view(torch.bfloat16).reshape(2, 2, N, 21, 21, 8)
-    assert float(raw[:, :, :, 20].abs().max()) == 0.0 and float(raw[:, :, :, :, 20].abs().max()) == 0.0
+    raw = net.d_l1.reshape(-1)[:N * 3528].view(torch.float16).reshape(2, N, 21, 21, 8)
+    assert float(raw[:, :, 20].abs().max()) == 0.0 and float(raw[:, :, :, 20].abs().max()) == 0.0
     # (2) free oracle (REPORTED; loosely gated): a pre-activation within rounding distance of 0 --
     # ~2e-4 relative now that a1 is stored as fp16 -- flips one relu and with it one gradient
     # column; with only T*B samples in the sums a handful of flips is visible in the 2-norm
