@@ -79,6 +79,7 @@ OTHER = {
     "arl_version": ([], c_int),
     "arl_backward_workspace_bytes": ([c_int], c_i64),
     "arl_prepared_floats": ([], c_i64),
+    "arl_a2_block_rows": ([c_int], c_i64),
     "arl_launch_count": ([c_int], c_i64),
     "arl_nature_workspace_bytes": ([c_int], c_i64),
     "arl_comm_size": ([], c_int),
@@ -165,6 +166,11 @@ def nature_param_layout(action_size):
     off = (c_i64 * 13)()
     check(load().arl_nature_param_layout(int(action_size), off), "arl_nature_param_layout")
     return list(off)
+
+
+def a2_block_rows(num_envs):
+    """Rows of one a2 block (envs per forward launch): see arl_a2_block_rows."""
+    return int(load().arl_a2_block_rows(int(num_envs)))
 
 
 def launch_count(reset=False):

@@ -87,6 +87,43 @@ extern "C" int64_t arl_backward_workspace_bytes(int action_size) {
   return (int64_t)8 * ARL_A2_ELEMS * ARL_FC * sizeof(float) + (1 << 20);
 }
 
+// Rows of one a2 block (= envs one forward launch handles).  A single launch of conv2 forward for
+// more than ~16K envs scatters its epilogue's 16-byte vectors over 324 chunk planes that are then
+// more than 256 KB apart -- TLB reach, not bandwidth: 0.32 of the HBM rate at 64K envs against 0.56
+// at 16K (profiles/r02_sweep_n1.json) -- so a rollout step of a very large batch runs as several
+// launches over env ranges, each writing its own a2 block.
+extern "C" int64_t arl_a2_block_rows(int num_envs) {
+  if (num_envs <= 16384) return num_envs;
+  for (int c = 16384; c >= 2048; c -= 128)
+    if (num_envs % c == 0) return c;
+  return num_envs;
+}
+
+static int forward_step(const float* params, float* prepared, int action_size, const uint8_t* ring,
+                        int num_envs, int ring_slots, int first_slot, float* a1, float* a2, float* h,
+                        float* logits, float* probs, float* value, int32_t* actions, int64_t env_id_base,
+                        int64_t step, const int64_t* step_dev, uint64_t seed, void* stream) {
+  const int chunk = (int)arl_a2_block_rows(num_envs);
+  for (int off = 0; off < num_envs; off += chunk) {
+    const int n = num_envs - off < chunk ? num_envs - off : chunk;
+    float* a1c = a1 + (size_t)off * 3200;                       // 12 800 bytes of fp16 per sample
+    float* a2c = a2 + (size_t)off * ARL_A2_ELEMS;
+    float* hc = h + (size_t)off * ARL_FC;
+    int rc = arl_conv1_forward(prepared, ring + (size_t)off * ring_slots * kPlane, a1c, n, ring_slots,
+                               first_slot, 1, stream);
+    if (rc) return rc;
+    rc = arl_conv2_forward(prepared, a1c, a2c, n, stream);
+    if (rc) return rc;
+    // fc256, then heads + softmax (+ the action draw) in one launch
+    rc = arl_fc_heads_forward(params, prepared, action_size, a2c, hc, logits + (size_t)off * action_size,
+                              probs + (size_t)off * action_size, value + off,
+                              actions ? actions + off : nullptr, env_id_base + off, step, step_dev, seed, n,
+                              stream);
+    if (rc) return rc;
+  }
+  return ARL_OK;
+}
+
 extern "C" int arl_forward(const float* params, float* prepared, int refresh_prepared, int action_size,
                            const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                            float* a1, float* a2, float* h, float* logits, float* probs, float* value,
@@ -95,11 +132,13 @@ extern "C" int arl_forward(const float* params, float* prepared, int refresh_pre
   int rc = ARL_OK;
   if (refresh_prepared) rc = arl_prepare_weights(params, prepared, stream);
   if (rc) return rc;
+  if (steps == 1)
+    return forward_step(params, prepared, action_size, ring, num_envs, ring_slots, first_slot, a1, a2, h,
+                        logits, probs, value, nullptr, 0, 0, nullptr, 0, stream);
   rc = arl_conv1_forward(prepared, ring, a1, num_envs, ring_slots, first_slot, steps, stream);
   if (rc) return rc;
   rc = arl_conv2_forward(prepared, a1, a2, N, stream);
   if (rc) return rc;
-  // fc256 + heads: one launch when the step fits the clustered kernel
   return arl_fc_heads_forward(params, prepared, action_size, a2, h, logits, probs, value, nullptr, 0, 0,
                               nullptr, 0, N, stream);
 }
@@ -113,12 +152,8 @@ extern "C" int arl_forward_sample(const float* params, float* prepared, int refr
   int rc = ARL_OK;
   if (refresh_prepared) rc = arl_prepare_weights(params, prepared, stream);
   if (rc) return rc;
-  rc = arl_conv1_forward(prepared, ring, a1, num_envs, ring_slots, first_slot, 1, stream);
-  if (rc) return rc;
-  rc = arl_conv2_forward(prepared, a1, a2, num_envs, stream);
-  if (rc) return rc;
-  return arl_fc_heads_forward(params, prepared, action_size, a2, h, logits, probs, value, actions,
-                              env_id_base, step, step_dev, seed, num_envs, stream);
+  return forward_step(params, prepared, action_size, ring, num_envs, ring_slots, first_slot, a1, a2, h,
+                      logits, probs, value, actions, env_id_base, step, step_dev, seed, stream);
 }
 
 extern "C" int arl_backward(const float* params, const float* prepared, int action_size,
@@ -133,7 +168,7 @@ extern "C" int arl_backward(const float* params, const float* prepared, int acti
   int rc = arl_heads_backward(params, action_size, h, dlogits, dvalue, d_h, grads, workspace, N,
                               tensor_scale, stream);
   if (rc) return rc;
-  rc = arl_fc_backward(prepared, a2, num_envs, d_h, d_a2, grads, workspace, N, unscale, stream);
+  rc = arl_fc_backward(prepared, a2, arl_a2_block_rows(num_envs), d_h, d_a2, grads, workspace, N, unscale, stream);
   if (rc) return rc;
   // l4_w .. q_b are final now: 98 % of the gradient bytes travel while the conv kernels run
   const bool comm = allreduce && arl_comm_size() > 1;

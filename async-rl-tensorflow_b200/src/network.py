@@ -212,12 +212,25 @@ class Network(object):
             return
         if refresh:
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
-        self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring), P(l1), B,
-                         history.ring_slots, history.first_slot(0), 1, st)
-        self._timed_call("arl_conv2_forward", P(self.fc_w), P(l1), P(l2), B, st)
-        # fc256 + heads as the one fused launch arl_forward makes (timed as arl_fc_forward)
-        self._timed_call("arl_fc_heads_forward", P(self.params), P(self.fc_w), A, P(l2), P(l4), P(logits),
-                         P(probs), P(value), None, 0, 0, None, 0, B, st)
+        self._timed_layers(history, l1, l2, l4, logits, probs, value, None, 0, 0, None, 0)
+
+    def _timed_layers(self, history, l1, l2, l4, logits, probs, value, actions, env_id_base, step, sd, seed):
+        """The per-layer entries arl_forward / arl_forward_sample are made of, one event pair each
+        (bench.py): the same launches in the same order, env range by env range when the batch is
+        larger than one a2 block (arl_a2_block_rows)."""
+        P, st = _cabi.ptr, _cabi.stream_ptr()
+        B, A = self.num_envs, self.action_size
+        c = _cabi.a2_block_rows(B)
+        for o in range(0, B, c):
+            r = slice(o, o + c)
+            self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring[r]), P(l1[r]), c,
+                             history.ring_slots, history.first_slot(0), 1, st)
+            self._timed_call("arl_conv2_forward", P(self.fc_w), P(l1[r]), P(l2[r]), c, st)
+            # fc256, then heads + softmax (+ the action draw) as one launch
+            self._timed_call("arl_fc_heads_forward", P(self.params), P(self.fc_w), A, P(l2[r]), P(l4[r]),
+                             P(logits[r]), P(probs[r]), P(value[r]),
+                             P(actions[r]) if actions is not None else None, int(env_id_base) + o,
+                             int(step), sd, int(seed), c, st)
 
     def forward(self, history, t, refresh=None):
         """Forward of the current stack into rollout slot ``t``; returns (logits, policy, value)."""
@@ -243,12 +256,8 @@ class Network(object):
             return self.sampled_action[r]
         if refresh:
             _cabi.call("arl_prepare_weights", P(self.params), P(self.fc_w), st)
-        self._timed_call("arl_conv1_forward", P(self.fc_w), P(history.ring), P(self.l1[r]), B,
-                         history.ring_slots, history.first_slot(0), 1, st)
-        self._timed_call("arl_conv2_forward", P(self.fc_w), P(self.l1[r]), P(self.l2[r]), B, st)
-        self._timed_call("arl_fc_heads_forward", P(self.params), P(self.fc_w), A, P(self.l2[r]),
-                         P(self.l4[r]), P(self.policy_logits[r]), P(self.policy[r]), P(self.value[r]),
-                         P(self.sampled_action[r]), int(env_id_base), int(step), sd, int(seed), B, st)
+        self._timed_layers(history, self.l1[r], self.l2[r], self.l4[r], self.policy_logits[r], self.policy[r],
+                           self.value[r], self.sampled_action[r], env_id_base, step, sd, seed)
         return self.sampled_action[r]
 
     def a1(self):
@@ -258,8 +267,9 @@ class Network(object):
     def a2(self):
         """conv2 activations of the rollout as float32 [N,2592] (NHWC flatten, agent.py:231-232),
         decoded from the per-step split blocks."""
-        B = self.num_envs
-        return torch.cat([decode_split(self.l2[self._rows(t)], B, A2_ELEMS) for t in range(self.t_max)])
+        B, c = self.num_envs, _cabi.a2_block_rows(self.num_envs)
+        return torch.cat([decode_split(self.l2[t * B + o:t * B + o + c], c, A2_ELEMS)
+                          for t in range(self.t_max) for o in range(0, B, c)])
 
     @staticmethod
     def pick_tensor_scale(grad_scale):
@@ -373,8 +383,8 @@ class Network(object):
         N = T * B
         self._timed_call("arl_heads_backward", P(self.params), A, P(self.l4), P(self.d_logits),
                          P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, S, st)
-        self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), B, P(self.d_l4), P(self.d_l2),
-                         P(self.grads), P(self.workspace), N, 1.0 / S, st)
+        self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), _cabi.a2_block_rows(B), P(self.d_l4),
+                         P(self.d_l2), P(self.grads), P(self.workspace), N, 1.0 / S, st)
         if allreduce:                                          # same bucket order as arl_backward
             lo = self.offsets[4]
             _cabi.call("arl_allreduce_begin", P(self.grads), lo, self.offsets[-1] - lo, st)

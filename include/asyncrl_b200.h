@@ -172,6 +172,10 @@ ARL_API int arl_fc_heads_forward(const float* params, const float* prepared, int
 
 /* The four above back to back, after arl_prepare_weights when refresh_prepared != 0 (pass 1
  * unless `prepared` was made from these very parameters by an earlier call). */
+/* Rows of one a2 block = the envs one forward launch handles: num_envs up to 16 384, else the
+ * largest divisor of num_envs that is <= 16 384 (arl_forward / arl_forward_sample with steps == 1
+ * then run several launches over env ranges, arl_backward hands this to arl_fc_backward). */
+ARL_API int64_t arl_a2_block_rows(int num_envs);
 ARL_API int arl_forward(const float* params, float* prepared, int refresh_prepared, int action_size,
                 const uint8_t* ring, int num_envs, int ring_slots, int first_slot, int steps,
                 float* a1, float* a2, float* h, float* logits, float* probs, float* value,

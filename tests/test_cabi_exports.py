@@ -17,7 +17,7 @@ def header_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = header_symbols()
-    assert len(syms) == 56, syms
+    assert len(syms) == 57, syms
     for must in ("arl_preprocess_push", "arl_forward", "arl_backward", "arl_sample_actions",
                  "arl_returns_lossgrad", "arl_clip_rmsprop", "arl_param_layout", "arl_last_error",
                  "arl_comm_init", "arl_allreduce_grads"):      # SURVEY §8b minimum export set

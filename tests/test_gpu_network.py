@@ -498,3 +498,47 @@ def test_train_with_summary_and_checkpoint_resume(pkg, cuda, tmp_path):
     assert agent2.load_checkpoint(str(ck)) and agent2.step_op == 20
     assert bool((agent2.network.params == agent.network.params).all())
     assert bool((agent2.network.rms == agent.network.rms).all())
+
+
+def test_chunked_forward_for_very_large_batches(pkg, cuda):
+    """More than 16 384 envs per step run as several forward launches over env ranges, each with its
+    own a2 block (arl_a2_block_rows): the outputs are those of the two halves run on their own (bit
+    for bit: a sample's forward does not depend on its batch) and the gradient is their sum."""
+    A, B, T = 6, 18432, 1
+    assert pkg._cabi.a2_block_rows(B) == 9216 and pkg._cabi.a2_block_rows(4096) == 4096
+    assert pkg._cabi.a2_block_rows(65536) == 16384 and pkg._cabi.a2_block_rows(16385) == 16385
+    params = make_params(A, seed=8, scale=2.0)
+    g = torch.Generator(device=cuda).manual_seed(5)
+    cfg = pkg.config.get_config({"model": "m1", "num_envs": B, "t_max": T})
+    hist = pkg.History(cfg, num_envs=B, device=cuda)
+    hist.ring.copy_(torch.randint(0, 256, tuple(hist.ring.shape), dtype=torch.uint8, device=cuda, generator=g))
+    rng = np.random.default_rng(1)
+    acts = torch.as_tensor(rng.integers(0, A, B).astype(np.int32), device=cuda)
+    rew = torch.as_tensor(rng.choice([-1.0, 0.0, 1.0], (T, B)).astype(np.float32), device=cuda)
+    term = torch.as_tensor((rng.random((T, B)) < 0.05).astype(np.uint8), device=cuda)
+
+    def run(envs, lo):
+        c = pkg.config.get_config({"model": "m1", "num_envs": envs, "t_max": T})
+        net = net_for(pkg, A, envs, T, params)
+        h = pkg.History(c, num_envs=envs, device=cuda)
+        h.ring.copy_(hist.ring[lo:lo + envs])
+        h.head = hist.head
+        sampled = net.forward_sample(h, 0, step=7, seed=123, env_id_base=lo).clone()
+        h.add(torch.zeros(envs, 84, 84, dtype=torch.uint8, device=cuda))        # one push: s_0 is 1 back
+        net.compute_gradients(h, rew[:, lo:lo + envs].contiguous(), term[:, lo:lo + envs].contiguous(),
+                              torch.zeros(envs, device=cuda), actions=acts[lo:lo + envs].contiguous(),
+                              grad_scale=1.0 / B)
+        torch.cuda.synchronize()
+        return net, sampled
+
+    full, s_full = run(B, 0)
+    total = torch.zeros_like(full.grads)
+    for lo in (0, B // 2):
+        half, s_half = run(B // 2, lo)
+        r = slice(lo, lo + B // 2)
+        assert torch.equal(half.policy_logits, full.policy_logits[r]) and torch.equal(half.value, full.value[r])
+        assert torch.equal(s_half, s_full[r])
+        total += half.grads
+    err = float((total - full.grads).abs().max()) / float(full.grads.abs().max())
+    print("chunked forward: gradient additivity", err)
+    assert err <= 1e-5
