@@ -42,6 +42,9 @@ def _run(pkg, variant, M, N, K, k_splits=1, seed=0):
     (0, 128, 256, 32), (0, 128, 256, 2592), (0, 300, 256, 64), (0, 4096, 256, 2592),
     (1, 128, 64, 32), (1, 1000, 256, 2592), (1, 5, 256, 96),
     (2, 128, 256, 256), (2, 777, 2592, 256), (2, 64, 48, 40),
+    # K == 256: the resident-weight dgrad (FcDgradRes); ragged N tile, row tiles that do not divide
+    # evenly over the CTAs of an N tile (empty trailing items), one CTA per N tile
+    (2, 3000, 2592, 256), (2, 1500, 208, 256), (2, 100, 2592, 256), (2, 20480, 2592, 256),
 ])
 def test_gemm_variants_vs_float64(pkg, cuda, variant, M, N, K):
     e = _run(pkg, variant, M, N, K)
