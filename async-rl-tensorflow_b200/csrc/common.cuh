@@ -194,6 +194,28 @@ __device__ __forceinline__ int sample_index(const float* p, int A, uint32_t x) {
   return a;
 }
 
+// Programmatic dependent launch for the small kernels between the tensor-core kernels: the launch
+// (and whatever the kernel does before pdl_wait(): staging parameters the update wrote long ago)
+// overlaps the tail of its predecessor in the stream; pdl_wait() returns when the predecessor has
+// completed and its writes are visible.  EVERY kernel launched this way must call pdl_wait() --
+// a kernel that skipped it would let its successor run ahead of its predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

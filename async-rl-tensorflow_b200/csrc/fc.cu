@@ -79,6 +79,7 @@ int split_rows(const float* X, int64_t ld, int rows, int chunks, void* out, cuda
 __global__ void __launch_bounds__(256)
 colsum_split256_kernel(const uint8_t* __restrict__ xs, float* __restrict__ partials, int rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
   const int per = (rows + gridDim.x - 1) / gridDim.x;
   const int beg = per * blockIdx.x, end = min(rows, beg + per);
   const int64_t part = (int64_t)32 * rows * 16;
@@ -374,7 +375,7 @@ extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a
   if (rc) return rc;
   // bias grad
   const int grid = (int)((num_samples + 63) / 64 < num_sms() ? (num_samples + 63) / 64 : num_sms());
-  colsum_split256_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_h, part, M);
+  ARL_CUDA(launch_pdl(colsum_split256_kernel, dim3(grid), dim3(256), 0, st, (const uint8_t*)d_h, part, M));
   ARL_LAUNCH_CHECK("colsum_split256_kernel");
   return reduce_partials_scaled(part, gb, grid, ARL_FC, grad_unscale, st);
 }

@@ -38,7 +38,6 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                  int32_t* __restrict__ actions, uint64_t env_id_base, uint64_t step, uint64_t seed,
                  const int64_t* __restrict__ step_dev) {
   extern __shared__ __align__(16) float sm[];   // [A+1][8][32]
-  if (actions != nullptr && step_dev != nullptr) step += (uint64_t)*step_dev;
   const int J = A + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 256 * J; i += kHfThreads) {
@@ -47,6 +46,11 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
   }
   const float bias = lane < A ? pb[lane] : 0.f, qb0 = qb[0];
   __syncthreads();
+  // launched with programmatic stream serialization: everything above (the parameters, written by
+  // the update long before) overlaps the tail of the fc256 kernel; h and the step counter are
+  // touched only after it has completed
+  pdl_wait();
+  if (actions != nullptr && step_dev != nullptr) step += (uint64_t)*step_dev;
   const int64_t stride = (int64_t)gridDim.x * (kHfThreads / 32);
   for (int64_t n = (int64_t)blockIdx.x * (kHfThreads / 32) + warp; n < num_samples; n += stride) {
     const float4* hp = reinterpret_cast<const float4*>(h + n * 256) + lane * 2;
@@ -222,6 +226,7 @@ __global__ void returns_lossgrad_kernel(const float* __restrict__ rewards,
                                         float grad_scale) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;
+  pdl_wait();
   if (n < (int64_t)T * B) {
     const int t = (int)(n / B), b = (int)(n - (int64_t)t * B);
     float R = v_boot[b];
@@ -297,6 +302,7 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
     acc[j] = 0.f;
   }
   float bacc = 0.f;                                   // thread j < J: sum of dz[:, j]
+  pdl_wait();                                         // (the weights above were written by the update)
   const int64_t beg = per * blockIdx.x;                // per is a multiple of 8: sample chunks are not split
   const int64_t end = beg + per < num_samples ? beg + per : num_samples;
   const int64_t lo_part = (int64_t)32 * num_samples * 16;
@@ -421,11 +427,12 @@ int heads_forward_sample(const float* params, int action_size, const float* h, f
   const ParamLayout L = param_layout(action_size);
   const size_t smem = (size_t)(action_size + 1) * 256 * sizeof(float);
   const int64_t ctas = (num_samples + kHfThreads / 32 - 1) / (kHfThreads / 32);   // one warp per sample
-  const int grid = (int)(ctas < 2LL * num_sms() ? ctas : 2LL * num_sms());
-  heads_fwd_kernel<<<grid, kHfThreads, smem, st>>>(
-      params + L.off[T_PW], params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h,
-      logits, probs, value, num_samples, action_size, actions, (uint64_t)env_id_base, (uint64_t)step, seed,
-      step_dev);
+  // up to 4 CTAs per SM: one env step of 4096 samples is ONE round of warps (two rounds cost a second
+  // exposed load latency)
+  const int grid = (int)(ctas < 4LL * num_sms() ? ctas : 4LL * num_sms());
+  ARL_CUDA(launch_pdl(heads_fwd_kernel, dim3(grid), dim3(kHfThreads), smem, st, params + L.off[T_PW],
+                      params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h, logits, probs, value,
+                      num_samples, action_size, actions, (uint64_t)env_id_base, (uint64_t)step, seed, step_dev));
   ARL_LAUNCH_CHECK("heads_fwd_kernel");
   return ARL_OK;
 }
@@ -540,9 +547,10 @@ extern "C" int arl_returns_lossgrad(const float* rewards, const uint8_t* termina
               "arl_returns_lossgrad: action_size %d outside [1,%d]", action_size, ARL_MAX_ACTIONS);
   if (t_max == 0 || num_envs == 0) return ARL_OK;
   const int64_t total = (int64_t)t_max * num_envs;
-  returns_lossgrad_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      rewards, terminals, actions, logits, value, v_boot, returns, dlogits, dvalue, loss_sums,
-      t_max, num_envs, action_size, gamma, beta, reward_min, reward_max, grad_scale);
+  ARL_CUDA(launch_pdl(returns_lossgrad_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0,
+                      (cudaStream_t)stream, rewards, terminals, actions, logits, value, v_boot, returns, dlogits,
+                      dvalue, loss_sums, t_max, num_envs, action_size, gamma, beta, reward_min, reward_max,
+                      grad_scale));
   ARL_LAUNCH_CHECK("returns_lossgrad_kernel");
   return ARL_OK;
 }
@@ -611,15 +619,9 @@ extern "C" int arl_heads_backward(const float* params, int action_size, const fl
   float* part = (float*)workspace;
   uint8_t* dhs = (uint8_t*)d_h;
   uint8_t* dhsT = dhs + (size_t)num_samples * 256 * sizeof(float);
-  if (J <= 8)
-    heads_bwd_kernel<8><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
-                                             dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
-  else if (J <= 20)
-    heads_bwd_kernel<20><<<grid, 256, 0, st>>>(params + L.off[T_PW], params + L.off[T_QW], h,
-                                              dlogits, dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
-  else
-    heads_bwd_kernel<ARL_MAX_ACTIONS + 1><<<grid, 256, 0, st>>>(
-        params + L.off[T_PW], params + L.off[T_QW], h, dlogits, dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale);
+  auto kern = J <= 8 ? heads_bwd_kernel<8> : J <= 20 ? heads_bwd_kernel<20> : heads_bwd_kernel<ARL_MAX_ACTIONS + 1>;
+  ARL_CUDA(launch_pdl(kern, dim3(grid), dim3(256), 0, st, params + L.off[T_PW], params + L.off[T_QW], h, dlogits,
+                      dvalue, dhs, dhsT, part, num_samples, per, A, tensor_scale));
   ARL_LAUNCH_CHECK("heads_bwd_kernel");
   return reduce_partials(part, g, grid, 256 * J + J, st);
 }

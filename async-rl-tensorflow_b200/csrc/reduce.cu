@@ -8,6 +8,7 @@ namespace arl {
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, float* __restrict__ out,
                                        int num_partials, int n, float alpha) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (i >= n) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int p = 0;
@@ -30,6 +31,7 @@ reduce_partials_wide_kernel(const float* __restrict__ partials, float* __restric
   __shared__ float red[32][33];
   const int e = threadIdx.x & 31, s = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
+  pdl_wait();
   // eight loads in flight per thread: the bias-gradient reductions are ONE block walking 2368
   // partials (74 per thread); with two loads in flight they took 17 and 36 us (ncu launch list)
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -60,9 +62,11 @@ reduce_partials_wide_kernel(const float* __restrict__ partials, float* __restric
 int reduce_partials_scaled(const float* partials, float* out, int num_partials, int n, float alpha,
                            cudaStream_t stream) {
   if (n >= 65536 || num_partials < 16)
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, num_partials, n, alpha);
+    ARL_CUDA(launch_pdl(reduce_partials_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, partials, out,
+                        num_partials, n, alpha));
   else
-    reduce_partials_wide_kernel<<<(n + 31) / 32, 1024, 0, stream>>>(partials, out, num_partials, n, alpha);
+    ARL_CUDA(launch_pdl(reduce_partials_wide_kernel, dim3((n + 31) / 32), dim3(1024), 0, stream, partials, out,
+                        num_partials, n, alpha));
   ARL_LAUNCH_CHECK("reduce_partials_kernel");
   return ARL_OK;
 }

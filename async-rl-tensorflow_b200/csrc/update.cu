@@ -35,6 +35,7 @@ sumsq_kernel(const float* __restrict__ grads, float* __restrict__ partial, Updat
   const int64_t beg = plan.off[t] + (int64_t)(blockIdx.x - plan.chunk_begin[t]) * kChunk;
   const int64_t end = beg + kChunk < plan.off[t + 1] ? beg + kChunk : plan.off[t + 1];
   float s = 0.f;
+  pdl_wait();
   for (int64_t i = beg + threadIdx.x; i < end; i += kUpThreads) {
     const float g = grads[i];
     s = fmaf(g, g, s);
@@ -169,6 +170,7 @@ rmsprop_kernel(float* __restrict__ params, float* __restrict__ rms, const float*
                long long step_offset, double base_lr, long long max_step) {
   __shared__ float s_scale;
   __shared__ float s_part[kUpThreads];
+  pdl_wait();
   // agent.py:393-395 on the device (the step counter lives in device memory under a CUDA graph):
   // the same double expression the host evaluates, rounded to float once
   if (step_dev != nullptr)
@@ -292,12 +294,12 @@ static int clip_rmsprop_offsets(float* params, float* rms, const float* grads, c
     }
     ARL_LAUNCH_CHECK("p2p_reduce_sumsq_kernel");
   } else {
-    sumsq_kernel<<<chunks, kUpThreads, 0, st>>>(grads, partial, plan);
+    ARL_CUDA(launch_pdl(sumsq_kernel, dim3(chunks), dim3(kUpThreads), 0, st, grads, partial, plan));
     ARL_LAUNCH_CHECK("sumsq_kernel");
   }
-  rmsprop_kernel<<<chunks, kUpThreads, 0, st>>>(params, rms, grads, partial, norms_out, plan, lr,
-                                               decay, eps, clip_norm, step_dev, (long long)step_offset,
-                                               base_lr, (long long)max_step);
+  ARL_CUDA(launch_pdl(rmsprop_kernel, dim3(chunks), dim3(kUpThreads), 0, st, params, rms, grads, partial, norms_out,
+                      plan, lr, decay, eps, clip_norm, step_dev, (long long)step_offset, base_lr,
+                      (long long)max_step));
   ARL_LAUNCH_CHECK("rmsprop_kernel");
   return ARL_OK;
 }
