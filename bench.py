@@ -362,7 +362,10 @@ def main():
     def units_of(entry):
         if entry == "arl_clip_rmsprop":
             return n_params
-        return B * T if entry.endswith("_backward") or entry == "arl_returns_lossgrad" else B
+        if entry.endswith("_backward") or entry == "arl_returns_lossgrad":
+            return B * T
+        # above 16 384 envs the forward entries run once per env range (arl_a2_block_rows)
+        return cabi.a2_block_rows(B) if entry.endswith("_forward") else B
 
     def roof(entry, avg_ms):
         kname, flop_per, bytes_per, impl_per = work[entry]
