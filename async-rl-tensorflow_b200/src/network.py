@@ -385,16 +385,21 @@ class Network(object):
                          P(self.d_value), P(self.d_l4), P(self.grads), P(self.workspace), N, S, st)
         self._timed_call("arl_fc_backward", P(self.fc_w), P(self.l2), _cabi.a2_block_rows(B), P(self.d_l4),
                          P(self.d_l2), P(self.grads), P(self.workspace), N, 1.0 / S, st)
-        if allreduce:                                          # same bucket order as arl_backward
+        # the exchange as arl_backward does it: ONE all-reduce after the last backward kernel, or
+        # (ARL_ALLREDUCE_OVERLAP=1) the l4_w..q_b bucket on the side stream from here on
+        overlap = allreduce and os.environ.get("ARL_ALLREDUCE_OVERLAP", "")[:1] == "1"
+        if overlap:
             lo = self.offsets[4]
             _cabi.call("arl_allreduce_begin", P(self.grads), lo, self.offsets[-1] - lo, st)
         self._timed_call("arl_conv2_backward", P(self.fc_w), P(self.l1), P(self.d_l2),
                          P(self.d_l1), P(self.grads), P(self.workspace), N, 1.0 / S, st)
         self._timed_call("arl_conv1_backward", P(history.ring), P(self.d_l1), P(self.grads),
                          P(self.workspace), B, history.ring_slots, history.first_slot(T), T, 1.0 / S, st)
-        if allreduce:
+        if overlap:
             _cabi.call("arl_allreduce_begin", P(self.grads), 0, self.offsets[4], st)
             _cabi.call("arl_allreduce_end", st)
+        elif allreduce:
+            self._timed_call("arl_allreduce_grads", P(self.grads), self.offsets[-1], st)
         return self.grads
 
     # -- async-Q mode (agent.py:169-207, 298-314): the Q head lives in the p_w/p_b slot ---------

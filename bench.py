@@ -71,6 +71,9 @@ def entry_work(A):
                                stack + a1, stack + da1s),
         # per PARAMETER (unit = one parameter): grad, rms, param read; rms, param written
         "arl_clip_rmsprop": ("sumsq_kernel + rmsprop_kernel", 6.0, 20, 24),
+        # N > 2 GPUs (collective 'library'): the sum of the flat gradient over the ranks, per PARAMETER
+        # (one read + one write of the local buffer; the time is launch + NVLink latency + rank skew)
+        "arl_allreduce_grads": ("ncclAllReduce (launched by the library)", 1.0, 8, 8),
     }
 
 
@@ -360,7 +363,7 @@ def main():
     traffic_all = load_traffic()
 
     def units_of(entry):
-        if entry == "arl_clip_rmsprop":
+        if entry in ("arl_clip_rmsprop", "arl_allreduce_grads"):
             return n_params
         if entry.endswith("_backward") or entry == "arl_returns_lossgrad":
             return B * T
