@@ -342,8 +342,11 @@ ARL_API int arl_clip_rmsprop_sched(float* params, float* rms, const float* grads
  *   arl_allreduce_grads   in-place sum over ranks of grads[0, count) on `stream`.
  *   arl_allreduce_begin / arl_allreduce_end   the same for a slice, on the library's side stream,
  *     ordered after what is already queued on `stream`; `end` makes `stream` wait for all slices
- *     begun.  arl_backward(allreduce = 1) uses them: the l4_w..q_b slice (98 % of the bytes) is
- *     final after the fc256 weight gradient and travels while the conv backward kernels run. */
+ *     begun.  arl_backward(allreduce = 1) sums the whole buffer with ONE arl_allreduce_grads after
+ *     its last kernel; with ARL_ALLREDUCE_OVERLAP=1 in the environment it sends the l4_w..q_b slice
+ *     (98 % of the bytes, final after the fc256 weight gradient) through begin / end while the conv
+ *     backward kernels run instead -- measured: nothing is hidden (the persistent conv kernels leave
+ *     NCCL no SMs), profiles/r02_allreduce_overlap.txt. */
 #define ARL_COMM_ID_BYTES 128
 ARL_API int arl_comm_unique_id(uint8_t* id_out);
 ARL_API int arl_comm_init(const uint8_t* id_bytes, int rank, int nranks);
