@@ -20,7 +20,8 @@ int reduce_partials_scaled(const float* partials, float* out, int num_partials, 
                            cudaStream_t stream);
 int heads_forward_sample(const float* params, int action_size, const float* h, float* logits, float* probs,
                          float* value, int32_t* actions, int64_t env_id_base, int64_t step,
-                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st);
+                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st,
+                         bool after_fc = false);
 
 // X fp32 [rows][8*chunks] (row stride ld) -> one split block [part][chunk][row][8 bf16].
 // Thread = (row, chunk): reads 32 contiguous bytes, writes one hi and one lo vector.
@@ -272,14 +273,19 @@ extern "C" int arl_prepare_weights(const float* params, float* prepared, void* s
   ARL_REQUIRE(params && prepared, "arl_prepare_weights: null pointer");
   ARL_REQUIRE(aligned16(params) && aligned16(prepared), "arl_prepare_weights: pointers must be 16-byte aligned");
   const ParamLayout L = param_layout(1);
-  int rc = split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8,
-                      reinterpret_cast<uint8_t*>(prepared) + kPrepFcW, (cudaStream_t)stream);
+  // The conv images FIRST: the conv kernels copy their resident image into shared memory BEFORE
+  // griddepcontrol.wait (programmatic dependent launch), which is only sound for data that was
+  // complete before their immediate predecessor in the stream started.  With this order the kernel
+  // a forward launched right after this call overlaps with is split_cols (a plain launch: it began
+  // after build_images had completed), whose output the fc256 kernels read after their wait.
+  int rc = conv_prepare(params, prepared, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = split_rows(params + L.off[T_L4W], ARL_FC, ARL_A2_ELEMS, ARL_FC / 8,
+                  reinterpret_cast<uint8_t*>(prepared) + kPrepFcW, (cudaStream_t)stream);
   if (rc) return rc;
   // l4_w^T [256][2592] for the K-major B operand of the clustered forward
-  rc = split_cols(params + L.off[T_L4W], ARL_FC, ARL_FC, ARL_A2_ELEMS,
-                  reinterpret_cast<uint8_t*>(prepared) + kPrepFcWT, (cudaStream_t)stream);
-  if (rc) return rc;
-  return conv_prepare(params, prepared, (cudaStream_t)stream);
+  return split_cols(params + L.off[T_L4W], ARL_FC, ARL_FC, ARL_A2_ELEMS,
+                    reinterpret_cast<uint8_t*>(prepared) + kPrepFcWT, (cudaStream_t)stream);
 }
 
 static int fc_forward_impl(const float* params, const float* prepared, const float* a2, float* h,
@@ -327,7 +333,7 @@ extern "C" int arl_fc_heads_forward(const float* params, const float* prepared, 
   if (rc) return rc;
   // heads + softmax + (optionally) the Philox draw: one warp-per-sample kernel
   return heads_forward_sample(params, action_size, h, logits, probs, value, actions, env_id_base, step, step_dev,
-                              seed, num_samples, (cudaStream_t)stream);
+                              seed, num_samples, (cudaStream_t)stream, /*after_fc=*/true);
 }
 
 extern "C" int arl_fc_backward(const float* prepared, const float* a2, int64_t a2_block_rows,

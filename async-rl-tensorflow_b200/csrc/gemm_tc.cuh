@@ -531,7 +531,8 @@ __global__ void __launch_bounds__(cta_threads<P>(), 1) tc_kernel(typename P::Arg
   const uint32_t tmem_base = *tmem_base_slot;
   const int items = P::num_items(g);
   // Programmatic dependent launch: everything above (barriers, TMEM, the resident weight image --
-  // written by arl_prepare_weights, never by the kernel just before this one) overlaps the tail of
+  // written by arl_prepare_weights, never by the kernel just before this one: arl_prepare_weights
+  // builds the conv images first and ends with the fc256 splits) overlaps the tail of
   // the previous kernel in the stream; its results are touched only after the wait.  The next
   // kernel may begin its own prologue as soon as SMs free up.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -36,8 +36,11 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                  const float* __restrict__ h, float* __restrict__ logits,
                  float* __restrict__ probs, float* __restrict__ value, int64_t num_samples, int A,
                  int32_t* __restrict__ actions, uint64_t env_id_base, uint64_t step, uint64_t seed,
-                 const int64_t* __restrict__ step_dev) {
+                 const int64_t* __restrict__ step_dev, int wait_first) {
   extern __shared__ __align__(16) float sm[];   // [A+1][8][32]
+  // wait_first: the kernel before this one in the stream may have written the parameters (a
+  // stand-alone arl_heads_forward right after an update): nothing is read before the wait
+  if (wait_first) pdl_wait();
   const int J = A + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 256 * J; i += kHfThreads) {
@@ -46,10 +49,11 @@ heads_fwd_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
   }
   const float bias = lane < A ? pb[lane] : 0.f, qb0 = qb[0];
   __syncthreads();
-  // launched with programmatic stream serialization: everything above (the parameters, written by
-  // the update long before) overlaps the tail of the fc256 kernel; h and the step counter are
+  // launched with programmatic stream serialization behind the fc256 kernel (arl_fc_heads_forward):
+  // everything above (the parameters -- not written by fc256, and whatever ran before fc256 had
+  // completed when fc256 passed its own wait) overlaps fc256's tail; h and the step counter are
   // touched only after it has completed
-  pdl_wait();
+  if (!wait_first) pdl_wait();
   if (actions != nullptr && step_dev != nullptr) step += (uint64_t)*step_dev;
   const int64_t stride = (int64_t)gridDim.x * (kHfThreads / 32);
   for (int64_t n = (int64_t)blockIdx.x * (kHfThreads / 32) + warp; n < num_samples; n += stride) {
@@ -295,6 +299,7 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
   __shared__ float dt[kHbSub][257];
   const int J = A + 1;
   const int k = threadIdx.x;
+  pdl_wait();      // before the weights too: the kernel before this one may be the update
   float w[JMAX], acc[JMAX];
 #pragma unroll
   for (int j = 0; j < JMAX; ++j) {
@@ -302,7 +307,6 @@ heads_bwd_kernel(const float* __restrict__ pw, const float* __restrict__ qw,
     acc[j] = 0.f;
   }
   float bacc = 0.f;                                   // thread j < J: sum of dz[:, j]
-  pdl_wait();                                         // (the weights above were written by the update)
   const int64_t beg = per * blockIdx.x;                // per is a multiple of 8: sample chunks are not split
   const int64_t end = beg + per < num_samples ? beg + per : num_samples;
   const int64_t lo_part = (int64_t)32 * num_samples * 16;
@@ -423,7 +427,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 namespace arl {
 int heads_forward_sample(const float* params, int action_size, const float* h, float* logits, float* probs,
                          float* value, int32_t* actions, int64_t env_id_base, int64_t step,
-                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st) {
+                         const int64_t* step_dev, uint64_t seed, int64_t num_samples, cudaStream_t st,
+                         bool after_fc) {
   const ParamLayout L = param_layout(action_size);
   const size_t smem = (size_t)(action_size + 1) * 256 * sizeof(float);
   const int64_t ctas = (num_samples + kHfThreads / 32 - 1) / (kHfThreads / 32);   // one warp per sample
@@ -432,7 +437,8 @@ int heads_forward_sample(const float* params, int action_size, const float* h, f
   const int grid = (int)(ctas < 4LL * num_sms() ? ctas : 4LL * num_sms());
   ARL_CUDA(launch_pdl(heads_fwd_kernel, dim3(grid), dim3(kHfThreads), smem, st, params + L.off[T_PW],
                       params + L.off[T_PB], params + L.off[T_QW], params + L.off[T_QB], h, logits, probs, value,
-                      num_samples, action_size, actions, (uint64_t)env_id_base, (uint64_t)step, seed, step_dev));
+                      num_samples, action_size, actions, (uint64_t)env_id_base, (uint64_t)step, seed, step_dev,
+                      after_fc ? 0 : 1));
   ARL_LAUNCH_CHECK("heads_fwd_kernel");
   return ARL_OK;
 }
@@ -448,7 +454,7 @@ extern "C" int arl_heads_forward(const float* params, int action_size, const flo
   ARL_REQUIRE(aligned16(h), "arl_heads_forward: h must be 16-byte aligned");
   if (num_samples == 0) return ARL_OK;
   return heads_forward_sample(params, action_size, h, logits, probs, value, nullptr, 0, 0, nullptr, 0,
-                              num_samples, (cudaStream_t)stream);
+                              num_samples, (cudaStream_t)stream, /*after_fc=*/false);
 }
 
 extern "C" int arl_sample_actions(const float* probs, int32_t* actions, int num_envs,
