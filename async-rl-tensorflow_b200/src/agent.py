@@ -353,7 +353,9 @@ class Agent(BaseModel):
             hist.head = new_head                                 # host state first: the launches read it
             refresh = self.network._fc_w_stale() if will_update else False
 
-            k1_eager = hist.timer is not None                    # bench.py: event pair around K1
+            # bench.py: an event pair around K1 -- launched eagerly between its events, or (when the
+            # events can be graph nodes) captured with the rest of the step
+            k1_eager = hist.timer is not None and not hist.timer_in_graph
             if k1_eager:
                 hist.push_into(screen, new_head)
 
@@ -367,7 +369,8 @@ class Agent(BaseModel):
                 if will_update:
                     self._update_launches(refresh)
             self._run(('observe', t, new_head, screen.data_ptr(), reward.data_ptr(),
-                       terminal.data_ptr(), tuple(screen.shape), will_update, refresh, k1_eager),
+                       terminal.data_ptr(), tuple(screen.shape), will_update, refresh, k1_eager,
+                       hist.timer is not None),
                       launches)
             self._step_dev_host = self.step + 1
             self.t += 1

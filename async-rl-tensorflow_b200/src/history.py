@@ -64,7 +64,8 @@ class History(object):
         self.ring = torch.zeros(self.num_envs, self.ring_slots, SCREEN, SCREEN,
                                 dtype=torch.uint8, device=self.device)   # history.py:10-11
         self.head = self.ring_slots - 1
-        self.timer = None
+        self.timer = None                     # bench.py: callable that brackets K1 with an event pair
+        self.timer_in_graph = False           # ... as event-record nodes INSIDE the captured graph
         resize = getattr(config, 'resize', 'cv2')                # environment.py:5-12 branch
         if resize not in ('cv2', 'pil'):
             raise NotImplementedError("resize=%r" % (resize,))
