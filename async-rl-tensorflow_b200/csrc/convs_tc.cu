@@ -513,7 +513,7 @@ struct Conv2DgradArgs {
   const uint8_t* w_img;  // prepared: transposed bf16 [hi | lo] image of l2_w
   const uint8_t* a1s;    // relu mask of conv1: sign of its fp16 output
   const float* dy2;      // [N, 81, 32]
-  uint8_t* dy1s;         // conv1 output gradient, split bf16 on the conv1 X grid ("dy1s", see below)
+  uint8_t* dy1s;         // conv1 output gradient, one fp16 per value on the conv1 X grid ("dy1s", see below)
   float* bias_partials;  // [grid * 8 epilogue warps][16]: column sums of dy1 (= the conv1 bias gradient)
   int64_t rows;          // 121 * num_samples
   int num_samples;

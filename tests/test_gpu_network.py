@@ -63,7 +63,7 @@ def test_forward_layers_vs_oracle(pkg, cuda, A, B, T, R, first):
                    T, a1.data_ptr(), a2.data_ptr(), h.data_ptr(), lg.data_ptr(), pr.data_ptr(),
                    v.data_ptr(), pkg._cabi.stream_ptr())
     torch.cuda.synchronize()
-    a1 = pkg.network.decode_a1(a1)                                # device layout: split bf16, blocked
+    a1 = pkg.network.decode_a1(a1)                                # device layout: fp16, blocked
     a2 = pkg.network.decode_split(a2, N, 2592)                    # one split block of the call's N rows
     assert rel_err(pkg.network.decode_split(fc_w[:2592 * 256], 2592, 256).cpu(), params["l4_w"]) <= 1e-5
     logits, value, keep = a3c.forward(a3c.to_torch(params), ring_stacks(ring_np, first, T), keep=True)
