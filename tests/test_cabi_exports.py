@@ -42,6 +42,19 @@ def test_param_layout_is_the_reference_order(pkg):
     assert lib.arl_param_layout(6, None) == -1
 
 
+def test_a2_block_rows_is_a_pure_host_function(pkg):
+    """Rows of one a2 block = envs one forward launch handles (api.cu): the whole batch up to 16 384
+    envs, above that the largest divisor <= 16 384 that is a multiple of 128 (>= 2048), else one
+    launch again -- the value arl_fc_backward needs to walk a2."""
+    f = pkg._cabi.a2_block_rows
+    assert [f(n) for n in (1, 4096, 16384)] == [1, 4096, 16384]
+    assert f(32768) == 16384 and f(65536) == 16384 and f(18432) == 9216 and f(20480) == 10240
+    assert f(16385) == 16385 and f(3 * 16384 + 1) == 3 * 16384 + 1      # no divisor: one launch
+    for n in (24576, 40960, 49152, 61440):
+        c = f(n)
+        assert n % c == 0 and 2048 <= c <= 16384 and c % 128 == 0
+
+
 def test_no_cpu_fallback(pkg):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
