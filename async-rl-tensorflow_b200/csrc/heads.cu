@@ -396,6 +396,7 @@ __global__ void act_update_kernel(const float* __restrict__ step_reward,
                                   const int32_t* __restrict__ lives_after, int is_training,
                                   float* __restrict__ reward, uint8_t* __restrict__ terminal, int n) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (b >= n) return;
   const bool lost = is_training && lives_before[b] > lives_after[b];
   reward[b] = step_reward[b] - (lost ? 1.0f : 0.0f);
@@ -406,6 +407,7 @@ __global__ void observe_store_kernel(const float* __restrict__ reward, const uin
                                      float* __restrict__ reward_slot, uint8_t* __restrict__ terminal_slot,
                                      int n, int64_t* step_counter, int64_t inc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   if (b == 0 && step_counter != nullptr) *step_counter += inc;      // agent.py:55: the loop's step
   if (b >= n) return;
   reward_slot[b] = reward[b];
@@ -568,8 +570,9 @@ extern "C" int arl_act_update(const float* step_reward, const uint8_t* step_term
               "arl_act_update: null pointer");
   ARL_REQUIRE(num_envs >= 0, "arl_act_update: negative size");
   if (num_envs == 0) return ARL_OK;
-  act_update_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      step_reward, step_terminal, lives_before, lives_after, is_training, reward, terminal, num_envs);
+  ARL_CUDA(launch_pdl(act_update_kernel, dim3((num_envs + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
+                      step_reward, step_terminal, lives_before, lives_after, is_training, reward, terminal,
+                      num_envs));
   ARL_LAUNCH_CHECK("act_update_kernel");
   return ARL_OK;
 }
@@ -579,8 +582,8 @@ extern "C" int arl_observe_store(const float* reward, const uint8_t* terminal, f
   ARL_REQUIRE(reward && terminal && reward_slot && terminal_slot, "arl_observe_store: null pointer");
   ARL_REQUIRE(num_envs >= 0, "arl_observe_store: negative size");
   if (num_envs == 0) return ARL_OK;
-  observe_store_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      reward, terminal, reward_slot, terminal_slot, num_envs, nullptr, 0);
+  ARL_CUDA(launch_pdl(observe_store_kernel, dim3((num_envs + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
+                      reward, terminal, reward_slot, terminal_slot, num_envs, (int64_t*)nullptr, (int64_t)0));
   ARL_LAUNCH_CHECK("observe_store_kernel");
   return ARL_OK;
 }
@@ -591,8 +594,8 @@ extern "C" int arl_observe_store_advance(const float* reward, const uint8_t* ter
   ARL_REQUIRE(reward && terminal && reward_slot && terminal_slot && step_counter,
               "arl_observe_store_advance: null pointer");
   ARL_REQUIRE(num_envs >= 1, "arl_observe_store_advance: num_envs must be >= 1");
-  observe_store_kernel<<<(num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      reward, terminal, reward_slot, terminal_slot, num_envs, step_counter, inc);
+  ARL_CUDA(launch_pdl(observe_store_kernel, dim3((num_envs + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
+                      reward, terminal, reward_slot, terminal_slot, num_envs, step_counter, inc));
   ARL_LAUNCH_CHECK("observe_store_kernel");
   return ARL_OK;
 }

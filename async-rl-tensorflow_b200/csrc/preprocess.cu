@@ -174,8 +174,6 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     mbar_init(&sm.full[0][warp], 1);
     mbar_init(&sm.full[1][warp], 1);
     fence_mbar_init();
-    if (frames_here > 0) issue_loads(0);
-    if (frames_here > 1) issue_loads(1);
   }
   if (tid == kK1Threads - 1) {
     for (int k = 0; k < 2; ++k) {
@@ -185,6 +183,14 @@ preprocess_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ ring
     fence_mbar_init();
   }
   for (int i = tid; i < kBitmapWords; i += kK1Threads) sm.fix[i] = g_luma_fix[i];
+  // launched programmatically: the barriers and the correction bitmap (static data) are set up
+  // while the kernel before this one is still running; the frames (whoever produced them) and the
+  // ring are touched only after it has completed
+  pdl_wait();
+  if (warp < kComputeWarps && lane == 0) {
+    if (frames_here > 0) issue_loads(0);
+    if (frames_here > 1) issue_loads(1);
+  }
   __syncthreads();
   // the next kernel in the stream (conv1 forward, launched with programmatic stream serialization)
   // may run its prologue on SMs this kernel has left; it waits for this grid before reading the ring
@@ -510,8 +516,8 @@ extern "C" int arl_preprocess_push(const uint8_t* frames, uint8_t* ring, int num
               "arl_preprocess_push: frames and ring must be 16-byte aligned");
   if (num_envs == 0) return ARL_OK;
   const int grid = num_envs < num_sms() ? num_envs : num_sms();
-  preprocess_kernel<<<grid, kK1Threads, sizeof(K1Smem), (cudaStream_t)stream>>>(
-      frames, ring, num_envs, ring_slots, slot, replicate);
+  ARL_CUDA(launch_pdl(preprocess_kernel, dim3(grid), dim3(kK1Threads), sizeof(K1Smem), (cudaStream_t)stream,
+                      frames, ring, num_envs, ring_slots, slot, replicate));
   ARL_LAUNCH_CHECK("preprocess_kernel");
   return ARL_OK;
 }
